@@ -1,0 +1,241 @@
+"""ctypes binding of the C ABI in include/bopy_b200.h (bopy_b200/lib/libbopy_b200.so).
+
+This is the only module that touches the shared library.  It fails loudly: a missing library or
+a non-zero status raises NativeLibraryError -- there is no CPU fallback behind it.
+PyTorch is used for device buffers and streams only.
+"""
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int64, c_uint64, c_void_p
+
+from .exceptions import NativeLibraryError
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libbopy_b200.so")
+ABI_VERSION = 1
+
+OK, ERR_BAD_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_READY = 0, -1, -2, -3, -4
+F64, F32 = 0, 1
+KERNEL_IDS = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3}
+ACQ_IDS = {None: -1, "none": -1, "lcb": 0, "ei": 1, "poi": 2}
+PEAK_IDS = {"fp64_fma": 0, "fp32_fma": 1, "fp64_mma": 2}
+
+# name -> (restype, argtypes); mirrors include/bopy_b200.h line by line
+_SIGNATURES = {
+    "bopy_abi_version": (c_int, []),
+    "bopy_last_error": (c_char_p, []),
+    "bopy_gp_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int64, c_int]),
+    "bopy_gp_destroy": (None, [c_void_p]),
+    "bopy_gp_set_state": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_double,
+                                  c_double, c_double, c_double, c_void_p]),
+    "bopy_gp_posterior_acq": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_double, c_void_p, c_void_p,
+                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "bopy_gp_predict_diag": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "bopy_acq_eval": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p]),
+    "bopy_acq_argmin": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                                c_void_p]),
+    "bopy_acq_from_moments": (c_int, [c_int, c_double, c_double, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                      c_void_p, c_void_p, c_void_p]),
+    "bopy_gp_predict_cov": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "bopy_candidates_uniform": (c_int, [c_uint64, c_int64, c_int64, c_int, POINTER(c_double), POINTER(c_double),
+                                        c_void_p, c_void_p]),
+    "bopy_measure_peak": (c_int, [c_int, POINTER(c_double)]),
+    "bopy_gp_launch_info": (c_int, [c_void_p, c_int64, POINTER(c_int), POINTER(c_int), POINTER(c_int64)]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise NativeLibraryError if it is missing or mismatched."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m bopy_b200.build` (nvcc, sm_100a). "
+            "bopy_b200 has no CPU fallback for the posterior/acquisition path.")
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as exc:
+        raise NativeLibraryError(f"cannot load {LIB_PATH}: {exc}") from exc
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as exc:
+            raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from exc
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.bopy_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(f"ABI version mismatch: library {lib.bopy_abi_version()}, binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != OK:
+        msg = load().bopy_last_error().decode("utf-8", "replace")
+        raise NativeLibraryError(f"{what} failed with status {status}: {msg}")
+
+
+def _ptr(t):
+    """Raw device pointer of a torch tensor, or NULL."""
+    return c_void_p(0) if t is None else c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    import torch
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def resolve_device(device=None):
+    """torch.device('cuda', i) for None | int | str | torch.device."""
+    torch = require_cuda()
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    if isinstance(device, int):
+        return torch.device("cuda", device)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise NativeLibraryError(f"bopy_b200 runs on CUDA devices only (got {dev})")
+    return torch.device("cuda", torch.cuda.current_device() if dev.index is None else dev.index)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise NativeLibraryError("no CUDA device is visible; bopy_b200 runs the posterior/acquisition path on a "
+                                 "B200 only (no CPU fallback)")
+    return torch
+
+
+class NativeGP:
+    """Owner of one `bopy_gp*` handle (one per device; not thread-safe)."""
+
+    def __init__(self, n, d, kernel="rbf", dtype="f64", device=None):
+        torch = require_cuda()
+        self.lib = load()
+        self.device = resolve_device(device)
+        self.n, self.d = int(n), int(d)
+        self.dtype = {"f64": F64, "f32": F32}[dtype]
+        self.dtype_name = dtype
+        self.kernel = kernel
+        handle = c_void_p()
+        check(self.lib.bopy_gp_create(byref(handle), self.device.index, self.dtype, KERNEL_IDS[kernel], self.n, self.d),
+              "bopy_gp_create")
+        self._handle = handle
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self.lib.bopy_gp_destroy(self._handle)
+            self._handle = None
+
+    __del__ = close
+
+    def _dev64(self, a, shape=None):
+        import numpy as np
+        torch = require_cuda()
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device, dtype=torch.float64, non_blocking=True).contiguous()
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {shape}, got {tuple(t.shape)}")
+        return t
+
+    def set_state(self, X, L, alpha, length_scale, amplitude=1.0, noise_level=0.0, y_mean=0.0, y_std=1.0):
+        """Upload (X_train_, L_, alpha_) and the kernel hyper-parameters; packs L on the device."""
+        import numpy as np
+        torch = require_cuda()
+        Xd = self._dev64(X, (self.n, self.d))
+        Ld = self._dev64(L, (self.n, self.n))
+        ad = self._dev64(alpha, (self.n,))
+        ls = np.atleast_1d(np.asarray(length_scale, dtype=np.float64))
+        ls_c = (c_double * len(ls))(*ls.tolist())
+        with torch.cuda.device(self.device):
+            check(self.lib.bopy_gp_set_state(self._handle, _ptr(Xd), _ptr(Ld), _ptr(ad), ls_c, len(ls),
+                                             float(amplitude), float(noise_level), float(y_mean), float(y_std),
+                                             _stream(self.device)), "bopy_gp_set_state")
+        # the library packed private copies and synchronised: nothing needs to stay alive
+
+    def candidates(self, x):
+        """(m, d) fp64 device tensor from numpy / torch input."""
+        t = self._dev64(x)
+        if t.dim() != 2 or t.shape[1] != self.d:
+            raise ValueError(f"candidates must be (m, {self.d})")
+        return t
+
+    def sweep(self, Xs, acq=None, eta=0.0, kappa=2.0, want_mean=False, want_var=False, want_acq=False,
+              want_min=False, index_base=0):
+        """One fused launch over device candidates Xs (m, d).  Returns a dict of device tensors."""
+        torch = require_cuda()
+        m = Xs.shape[0]
+        dev = self.device
+        out = {}
+        mean = torch.empty(m, dtype=torch.float64, device=dev) if want_mean else None
+        var = torch.empty(m, dtype=torch.float64, device=dev) if want_var else None
+        acqv = torch.empty(m, dtype=torch.float64, device=dev) if want_acq else None
+        minv = torch.empty(1, dtype=torch.float64, device=dev) if want_min else None
+        mini = torch.empty(1, dtype=torch.int64, device=dev) if want_min else None
+        with torch.cuda.device(dev):
+            check(self.lib.bopy_gp_posterior_acq(self._handle, _ptr(Xs), m, ACQ_IDS[acq], float(eta), float(kappa),
+                                                 _ptr(mean), _ptr(var), _ptr(acqv), int(index_base), _ptr(minv),
+                                                 _ptr(mini), _stream(dev)), "bopy_gp_posterior_acq")
+        out.update(mean=mean, var=var, acq=acqv, min_val=minv, min_idx=mini)
+        return out
+
+    def predict_cov(self, Xs):
+        torch = require_cuda()
+        m = Xs.shape[0]
+        mean = torch.empty(m, dtype=torch.float64, device=self.device)
+        cov = torch.empty((m, m), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.bopy_gp_predict_cov(self._handle, _ptr(Xs), m, _ptr(mean), _ptr(cov), _stream(self.device)),
+                  "bopy_gp_predict_cov")
+        return mean, cov
+
+    def launch_info(self, m):
+        g, l, w = c_int(), c_int(), c_int64()
+        check(self.lib.bopy_gp_launch_info(self._handle, int(m), byref(g), byref(l), byref(w)), "bopy_gp_launch_info")
+        return {"grid": g.value, "launches": l.value, "workspace_bytes": w.value}
+
+
+def acquisition_from_moments(acq, mean, var, eta=0.0, kappa=2.0, want_min=False, index_base=0):
+    """LCB/EI/POI epilogue (+ optional argmin) on device tensors mean, var (m,) fp64 -- the same device
+    code as the fused sweep's epilogue, for surrogates that are not B200-native."""
+    torch = require_cuda()
+    lib = load()
+    m = mean.shape[0]
+    out = torch.empty(m, dtype=torch.float64, device=mean.device)
+    minv = torch.empty(1, dtype=torch.float64, device=mean.device) if want_min else None
+    mini = torch.empty(1, dtype=torch.int64, device=mean.device) if want_min else None
+    with torch.cuda.device(mean.device):
+        check(lib.bopy_acq_from_moments(ACQ_IDS[acq], float(eta), float(kappa), _ptr(mean), _ptr(var), m, _ptr(out),
+                                        int(index_base), _ptr(minv), _ptr(mini), _stream(mean.device)),
+              "bopy_acq_from_moments")
+    return out, minv, mini
+
+
+def candidates_uniform(seed, index_base, m, lowers, uppers, device=None):
+    """Counter-based uniform candidates in a box, generated on the device: (m, d) fp64 tensor."""
+    torch = require_cuda()
+    lib = load()
+    d = len(lowers)
+    dev = resolve_device(device)
+    out = torch.empty((int(m), d), dtype=torch.float64, device=dev)
+    lo = (c_double * d)(*[float(v) for v in lowers])
+    hi = (c_double * d)(*[float(v) for v in uppers])
+    with torch.cuda.device(dev):
+        check(lib.bopy_candidates_uniform(int(seed), int(index_base), int(m), d, lo, hi, _ptr(out), _stream(dev)),
+              "bopy_candidates_uniform")
+    return out
+
+
+def measure_peak(what):
+    """TFLOP/s of a register-resident FMA/MMA loop on the current device ('fp64_fma' | 'fp32_fma' | 'fp64_mma')."""
+    require_cuda()
+    v = c_double()
+    check(load().bopy_measure_peak(PEAK_IDS[what], byref(v)), "bopy_measure_peak")
+    return v.value

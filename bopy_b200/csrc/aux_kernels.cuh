@@ -1,0 +1,181 @@
+// One-time packing of the fitted state into the solve layout, the full-covariance view, the
+// counter-based candidate generator and the FMA/MMA peak microbenchmarks.
+#pragma once
+#include "common.cuh"
+#include "sweep_kernel.cuh"
+
+namespace bopy {
+
+// L with identity padding beyond n (rows/cols >= n): the padded system solves to v = 0 there.
+__device__ __forceinline__ double L_at(const double* __restrict__ L, int n, int r, int c) {
+    return (r < n && c < n) ? L[(size_t)r * n + c] : (r == c ? 1.0 : 0.0);
+}
+
+// Dinv[I] = inv(L_II), 128 x 128 lower triangular, fp64 forward substitution (column j per thread).
+// Dinv doubles as the column store: thread j only re-reads what it wrote itself.
+__global__ void dinv_kernel(const double* __restrict__ L, int n, double* Dinv) {
+    const int I = blockIdx.x, j = threadIdx.x, base = I * BM;
+    double* D = Dinv + (size_t)I * BM * BM;
+    for (int r = 0; r < BM; ++r) {
+        double x = 0.0;
+        if (r >= j) {
+            double s = (r == j) ? 1.0 : 0.0;
+            for (int k = j; k < r; ++k) s = fma(-L_at(L, n, base + r, base + k), D[(size_t)k * BM + j], s);
+            x = s / L_at(L, n, base + r, base + r);
+        }
+        D[(size_t)r * BM + j] = x;
+    }
+}
+
+// Operand tile (I, Jc): [k][row] = -L[I*BM+row][Jc*KC+k] below the diagonal block, Dinv[I][row][.] on it.
+template <typename T>
+__global__ void pack_tiles_kernel(const double* __restrict__ L, int n, const double* __restrict__ Dinv, T* out) {
+    using G = Geo<T>;
+    constexpr int KC = G::KC, CH = G::CH, TE = TILE_BYTES / sizeof(T);
+    const int I = blockIdx.y, Jc = blockIdx.x;
+    if (Jc >= (I + 1) * CH) return;
+    __shared__ double tmp[KC][BM + 1];
+    for (int e = threadIdx.x; e < BM * KC; e += blockDim.x) {
+        const int r = e / KC, k = e - r * KC;
+        double v;
+        if (Jc < I * CH)
+            v = -L_at(L, n, I * BM + r, Jc * KC + k);
+        else
+            v = Dinv[((size_t)I * BM + r) * BM + (Jc - I * CH) * KC + k];
+        tmp[k][r] = v;
+    }
+    __syncthreads();
+    T* dst = out + ((size_t)CH * I * (I + 1) / 2 + Jc) * TE;
+    for (int e = threadIdx.x; e < BM * KC; e += blockDim.x) {
+        const int k = e / BM, r = e - k * BM;
+        dst[e] = static_cast<T>(tmp[k][r]);
+    }
+}
+
+struct LsParam {
+    double v[MAX_D];
+};
+
+// Xt[I][q][r] = X[I*BM+r][q] / l_q (q < d), Xt[I][d][r] = alpha[I*BM+r]; zero beyond n
+__global__ void pack_x_kernel(const double* __restrict__ X, const double* __restrict__ alpha, int n, int d,
+                              LsParam ls, double* Xt) {
+    const int I = blockIdx.x, r = threadIdx.x, row = I * BM + r;
+    double* dst = Xt + (size_t)I * (d + 1) * BM;
+    for (int q = 0; q < d; ++q) dst[q * BM + r] = row < n ? __ddiv_rn(X[(size_t)row * d + q], ls.v[q]) : 0.0;
+    dst[d * BM + r] = row < n ? alpha[row] : 0.0;
+}
+
+// cov[a][b] = (k(x_a, x_b) - sum_i V[i,a] V[i,b]) * y_std^2   ($SK/_gpr.py:466-469); V in the sweep's tile layout
+template <typename T, int KIND>
+__global__ void cov_kernel(const T* __restrict__ Vws, int n_pad, int n, const double* __restrict__ Xs, long long m,
+                           int d, LsParam ls, double amp, double kss, double y_var, double* cov) {
+    const long long a = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= m || b >= m) return;
+    const T* Va = Vws + (a / BN) * (long long)n_pad * BN + (a % BN);
+    const T* Vb = Vws + (b / BN) * (long long)n_pad * BN + (b % BN);
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s = fma((double)Va[(size_t)i * BN], (double)Vb[(size_t)i * BN], s);
+    double prior = kss;
+    if (a != b) {
+        double d2 = 0.0;
+        for (int q = 0; q < d; ++q) {
+            const double df = __dadd_rn(__ddiv_rn(Xs[a * d + q], ls.v[q]), -__ddiv_rn(Xs[b * d + q], ls.v[q]));
+            d2 = __dadd_rn(d2, __dmul_rn(df, df));
+        }
+        prior = __dmul_rn(amp, base_kernel<KIND>(d2));
+    }
+    cov[a * m + b] = __dmul_rn(__dadd_rn(prior, -s), y_var);
+}
+
+// acquisition epilogue on given moments + block-wide arg-min; one block (small m)
+__global__ void moments_kernel(int acq, double eta, double kappa, const double* __restrict__ mean,
+                               const double* __restrict__ var, long long m, double* acq_out, long long index_base,
+                               double* min_val, long long* min_idx) {
+    __shared__ MinLoc red[32];
+    MinLoc v;
+    v.val = 0.0;
+    v.idx = -1;
+    for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+        MinLoc c;
+        c.val = acquisition_value(acq, mean[i], var[i], eta, kappa);
+        c.idx = index_base + i;
+        if (acq_out) acq_out[i] = c.val;
+        if (minloc_better(c, v)) v = c;
+    }
+    v = minloc_warp_reduce(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (minloc_better(red[w], v)) v = red[w];
+        if (min_val) *min_val = v.val;
+        if (min_idx) *min_idx = v.idx;
+    }
+}
+
+struct BoxParam {
+    double lo[MAX_D], hi[MAX_D];
+};
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__global__ void candidates_kernel(unsigned long long seed, long long index_base, long long m, int d, BoxParam box,
+                                  double* out) {
+    const long long total = m * d;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / d;
+        const int j = (int)(e - i * d);
+        const unsigned long long ctr = (unsigned long long)(index_base + i) * (unsigned long long)d + j + 1ULL;
+        const unsigned long long z = splitmix64(seed + 0x9E3779B97F4A7C15ULL * ctr);
+        const double u = __dmul_rn((double)(z >> 11), 1.0 / 9007199254740992.0);
+        out[e] = __dadd_rn(box.lo[j], __dmul_rn(u, __dadd_rn(box.hi[j], -box.lo[j])));
+    }
+}
+
+// ---- register-resident peak microbenchmarks ---------------------------------------------------------
+template <typename T> __global__ void peak_fma_kernel(T* out, int iters, T x, T y) {
+    T a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = static_cast<T>(threadIdx.x + k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = fma(a[k], x, y);
+    }
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+    if (s == static_cast<T>(-1.2345)) out[0] = s;
+}
+
+// mma.sync m8n8k4 f64 (DMMA): 256 MACs per warp instruction
+__global__ void peak_dmma_kernel(double* out, int iters, double x, double y) {
+    double c[8][2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        c[k][0] = threadIdx.x + k;
+        c[k][1] = threadIdx.x - k;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[k][0]), "+d"(c[k][1])
+                             : "d"(x), "d"(y));
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+    if (s == -1.2345) out[0] = s;
+}
+
+}  // namespace bopy

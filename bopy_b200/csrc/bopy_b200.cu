@@ -1,0 +1,403 @@
+// C ABI of the B200-native bopy hot path (see include/bopy_b200.h for the contract).
+#include "bopy_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "aux_kernels.cuh"
+#include "common.cuh"
+#include "sweep_kernel.cuh"
+
+using namespace bopy;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t err__ = (expr);                                                                \
+        if (err__ != cudaSuccess)                                                                  \
+            return fail(BOPY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__),  \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+size_t elem_size(int dtype) { return dtype == BOPY_F64 ? sizeof(double) : sizeof(float); }
+
+}  // namespace
+
+struct bopy_gp {
+    int device = 0, dtype = BOPY_F64, kernel = BOPY_KERNEL_RBF;
+    long long n = 0;
+    int d = 0, n_blocks = 0, n_pad = 0, sm_count = 0;
+    void* Lt = nullptr;        // packed factor tiles
+    double* Xt = nullptr;      // [n_blocks][d+1][BM]
+    double* Dinv = nullptr;    // [n_blocks][BM][BM] fp64 inverted diagonal blocks
+    void* Vws = nullptr;       // [sm_count][n_pad][BN]
+    MinLoc* partials = nullptr;
+    double ls[MAX_D];
+    double amp = 1.0, noise = 0.0, y_mean = 0.0, y_std = 1.0;
+    bool ready = false;
+};
+
+namespace {
+
+long long packed_tiles(const bopy_gp* gp) {
+    const long long ch = gp->dtype == BOPY_F64 ? Geo<double>::CH : Geo<float>::CH;
+    return ch * gp->n_blocks * (gp->n_blocks + 1) / 2;
+}
+
+template <typename T, int KIND> int launch_sweep_t(const SweepParams& p, int grid, cudaStream_t st) {
+    const size_t smem = sweep_smem_bytes<T>(p.d);
+    CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<T, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sweep_kernel<T, KIND><<<grid, NT, smem, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
+template <typename T> int launch_sweep_k(int kernel, const SweepParams& p, int grid, cudaStream_t st) {
+    switch (kernel) {
+        case BOPY_KERNEL_RBF: return launch_sweep_t<T, K_RBF>(p, grid, st);
+        case BOPY_KERNEL_MATERN12: return launch_sweep_t<T, K_M12>(p, grid, st);
+        case BOPY_KERNEL_MATERN32: return launch_sweep_t<T, K_M32>(p, grid, st);
+        case BOPY_KERNEL_MATERN52: return launch_sweep_t<T, K_M52>(p, grid, st);
+    }
+    return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
+}
+
+template <typename T> int launch_cov_k(const bopy_gp* gp, const void* Vws, const double* Xs, long long m,
+                                       const LsParam& ls, double* cov, cudaStream_t st) {
+    dim3 block(16, 16), grid((unsigned)((m + 15) / 16), (unsigned)((m + 15) / 16));
+    const double kss = gp->amp + gp->noise, yv = gp->y_std * gp->y_std;
+    const T* V = reinterpret_cast<const T*>(Vws);
+    switch (gp->kernel) {
+        case BOPY_KERNEL_RBF:
+            cov_kernel<T, K_RBF><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
+            break;
+        case BOPY_KERNEL_MATERN12:
+            cov_kernel<T, K_M12><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
+            break;
+        case BOPY_KERNEL_MATERN32:
+            cov_kernel<T, K_M32><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
+            break;
+        default:
+            cov_kernel<T, K_M52><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
+            break;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
+int check_ready(const bopy_gp* gp) {
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    if (!gp->ready) return fail(BOPY_ERR_NOT_READY, "bopy_gp_set_state has not been called on this handle");
+    return BOPY_OK;
+}
+
+// the one place the sweep is launched from
+int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, double kappa, double* mean_out,
+              double* var_out, double* acq_out, long long index_base, double* min_val, long long* min_idx,
+              void* Vws, int slot_per_tile, cudaStream_t st) {
+    SweepParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.Lt = gp->Lt;
+    p.Xt = gp->Xt;
+    p.Vws = Vws;
+    p.Xs = Xs;
+    p.m = m;
+    p.ntiles = (m + BN - 1) / BN;
+    p.n = (int)gp->n;
+    p.n_blocks = gp->n_blocks;
+    p.d = gp->d;
+    p.slot_per_tile = slot_per_tile;
+    for (int q = 0; q < gp->d; ++q) p.ls[q] = gp->ls[q];
+    p.amp = gp->amp;
+    p.kss = gp->amp + gp->noise;
+    p.y_mean = gp->y_mean;
+    p.y_std = gp->y_std;
+    p.y_var = gp->y_std * gp->y_std;
+    p.acq = acq;
+    p.eta = eta;
+    p.kappa = kappa;
+    p.mean_out = mean_out;
+    p.var_out = var_out;
+    p.acq_out = acq_out;
+    p.index_base = index_base;
+    const bool want_min = (min_val != nullptr || min_idx != nullptr);
+    p.partials = want_min ? gp->partials : nullptr;
+    const int grid = (int)std::min<long long>(p.ntiles, gp->sm_count);
+    int rc = gp->dtype == BOPY_F64 ? launch_sweep_k<double>(gp->kernel, p, grid, st)
+                                   : launch_sweep_k<float>(gp->kernel, p, grid, st);
+    if (rc != BOPY_OK) return rc;
+    if (want_min) {
+        minloc_finalize_kernel<<<1, 256, 0, st>>>(gp->partials, grid, min_val, min_idx);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return BOPY_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bopy_abi_version(void) { return BOPY_B200_ABI_VERSION; }
+
+const char* bopy_last_error(void) { return g_last_error.c_str(); }
+
+int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, int d) {
+    if (out == nullptr) return fail(BOPY_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    if (dtype != BOPY_F64 && dtype != BOPY_F32) return fail(BOPY_ERR_BAD_ARG, "dtype must be BOPY_F64 or BOPY_F32");
+    if (kernel < BOPY_KERNEL_RBF || kernel > BOPY_KERNEL_MATERN52) return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
+    if (n < 1) return fail(BOPY_ERR_BAD_ARG, "n must be >= 1 (got %lld)", (long long)n);
+    if (d < 1) return fail(BOPY_ERR_BAD_ARG, "d must be >= 1 (got %d)", d);
+    if (d > MAX_D) return fail(BOPY_ERR_UNSUPPORTED, "d = %d exceeds the supported maximum of %d", d, MAX_D);
+    if (n > (1 << 20)) return fail(BOPY_ERR_UNSUPPORTED, "n = %lld exceeds the supported maximum", (long long)n);
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(BOPY_ERR_BAD_ARG, "device %d out of range (%d visible)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(BOPY_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    bopy_gp* gp = new (std::nothrow) bopy_gp();
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "out of host memory");
+    gp->device = device;
+    gp->dtype = dtype;
+    gp->kernel = kernel;
+    gp->n = n;
+    gp->d = d;
+    gp->n_blocks = (int)((n + BM - 1) / BM);
+    gp->n_pad = gp->n_blocks * BM;
+    gp->sm_count = prop.multiProcessorCount;
+    const size_t es = elem_size(dtype);
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&gp->Lt, (size_t)packed_tiles(gp) * TILE_BYTES);
+    if (e == cudaSuccess) e = cudaMalloc(&gp->Xt, (size_t)gp->n_blocks * (d + 1) * BM * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&gp->Dinv, (size_t)gp->n_blocks * BM * BM * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&gp->Vws, (size_t)gp->sm_count * gp->n_pad * BN * es);
+    if (e == cudaSuccess) e = cudaMalloc(&gp->partials, (size_t)gp->sm_count * sizeof(MinLoc));
+    if (e != cudaSuccess) {
+        bopy_gp_destroy(gp);
+        return fail(BOPY_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out = gp;
+    return BOPY_OK;
+}
+
+void bopy_gp_destroy(bopy_gp* gp) {
+    if (gp == nullptr) return;
+    cudaSetDevice(gp->device);
+    cudaFree(gp->Lt);
+    cudaFree(gp->Xt);
+    cudaFree(gp->Dinv);
+    cudaFree(gp->Vws);
+    cudaFree(gp->partials);
+    delete gp;
+}
+
+int bopy_gp_set_state(bopy_gp* gp, const double* X_dev, const double* L_dev, const double* alpha_dev,
+                      const double* length_scale_host, int n_ls, double amplitude, double noise_level,
+                      double y_mean, double y_std, void* stream) {
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    if (X_dev == nullptr || L_dev == nullptr || alpha_dev == nullptr || length_scale_host == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "X_dev, L_dev, alpha_dev and length_scale_host must be non-NULL");
+    if (n_ls != 1 && n_ls != gp->d) return fail(BOPY_ERR_BAD_ARG, "n_ls must be 1 or d = %d (got %d)", gp->d, n_ls);
+    for (int q = 0; q < n_ls; ++q)
+        if (!(length_scale_host[q] > 0.0)) return fail(BOPY_ERR_BAD_ARG, "length_scale[%d] must be positive", q);
+    if (!(amplitude > 0.0)) return fail(BOPY_ERR_BAD_ARG, "amplitude must be positive");
+    if (!(noise_level >= 0.0)) return fail(BOPY_ERR_BAD_ARG, "noise_level must be non-negative");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    gp->ready = false;
+    LsParam ls;
+    for (int q = 0; q < MAX_D; ++q) ls.v[q] = 1.0;
+    for (int q = 0; q < gp->d; ++q) {
+        gp->ls[q] = length_scale_host[n_ls == 1 ? 0 : q];
+        ls.v[q] = gp->ls[q];
+    }
+    gp->amp = amplitude;
+    gp->noise = noise_level;
+    gp->y_mean = y_mean;
+    gp->y_std = y_std;
+    const int n = (int)gp->n;
+    dinv_kernel<<<gp->n_blocks, BM, 0, st>>>(L_dev, n, gp->Dinv);
+    CUDA_TRY(cudaGetLastError());
+    if (gp->dtype == BOPY_F64) {
+        dim3 grid(gp->n_blocks * Geo<double>::CH, gp->n_blocks);
+        pack_tiles_kernel<double><<<grid, 256, 0, st>>>(L_dev, n, gp->Dinv, reinterpret_cast<double*>(gp->Lt));
+    } else {
+        dim3 grid(gp->n_blocks * Geo<float>::CH, gp->n_blocks);
+        pack_tiles_kernel<float><<<grid, 256, 0, st>>>(L_dev, n, gp->Dinv, reinterpret_cast<float*>(gp->Lt));
+    }
+    CUDA_TRY(cudaGetLastError());
+    pack_x_kernel<<<gp->n_blocks, BM, 0, st>>>(X_dev, alpha_dev, n, gp->d, ls, gp->Xt);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
+    gp->ready = true;
+    return BOPY_OK;
+}
+
+int bopy_gp_posterior_acq(bopy_gp* gp, const double* Xs_dev, int64_t m, int acq, double eta, double kappa,
+                          double* mean_out, double* var_out, double* acq_out, int64_t index_base,
+                          double* min_val_out, int64_t* min_idx_out, void* stream) {
+    int rc = check_ready(gp);
+    if (rc != BOPY_OK) return rc;
+    if (Xs_dev == nullptr) return fail(BOPY_ERR_BAD_ARG, "Xs_dev is NULL");
+    if (m < 1) return fail(BOPY_ERR_BAD_ARG, "m must be >= 1 (got %lld)", (long long)m);
+    if (acq < BOPY_ACQ_NONE || acq > BOPY_ACQ_POI) return fail(BOPY_ERR_BAD_ARG, "unknown acquisition id %d", acq);
+    if (acq == BOPY_ACQ_NONE && (acq_out != nullptr || min_val_out != nullptr || min_idx_out != nullptr))
+        return fail(BOPY_ERR_BAD_ARG, "acquisition outputs requested with BOPY_ACQ_NONE");
+    CUDA_TRY(cudaSetDevice(gp->device));
+    return run_sweep(gp, Xs_dev, m, acq, eta, kappa, mean_out, var_out, acq_out, index_base, min_val_out,
+                     reinterpret_cast<long long*>(min_idx_out), gp->Vws, 0, static_cast<cudaStream_t>(stream));
+}
+
+int bopy_gp_predict_diag(bopy_gp* gp, const double* Xs_dev, int64_t m, double* mean_out, double* var_out,
+                         void* stream) {
+    return bopy_gp_posterior_acq(gp, Xs_dev, m, BOPY_ACQ_NONE, 0.0, 0.0, mean_out, var_out, nullptr, 0, nullptr,
+                                 nullptr, stream);
+}
+
+int bopy_acq_eval(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m, double* acq_out,
+                  void* stream) {
+    if (acq_out == nullptr) return fail(BOPY_ERR_BAD_ARG, "acq_out is NULL");
+    return bopy_gp_posterior_acq(gp, Xs_dev, m, acq, eta, kappa, nullptr, nullptr, acq_out, 0, nullptr, nullptr, stream);
+}
+
+int bopy_acq_argmin(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
+                    int64_t index_base, double* min_val_out, int64_t* min_idx_out, void* stream) {
+    if (min_val_out == nullptr || min_idx_out == nullptr) return fail(BOPY_ERR_BAD_ARG, "min outputs are NULL");
+    return bopy_gp_posterior_acq(gp, Xs_dev, m, acq, eta, kappa, nullptr, nullptr, nullptr, index_base, min_val_out,
+                                 min_idx_out, stream);
+}
+
+int bopy_acq_from_moments(int acq, double eta, double kappa, const double* mean_dev, const double* var_dev,
+                          int64_t m, double* acq_out, int64_t index_base, double* min_val_out,
+                          int64_t* min_idx_out, void* stream) {
+    if (mean_dev == nullptr || var_dev == nullptr) return fail(BOPY_ERR_BAD_ARG, "mean_dev / var_dev is NULL");
+    if (m < 1) return fail(BOPY_ERR_BAD_ARG, "m must be >= 1 (got %lld)", (long long)m);
+    if (acq < BOPY_ACQ_LCB || acq > BOPY_ACQ_POI) return fail(BOPY_ERR_BAD_ARG, "unknown acquisition id %d", acq);
+    moments_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+        acq, eta, kappa, mean_dev, var_dev, m, acq_out, index_base, min_val_out,
+        reinterpret_cast<long long*>(min_idx_out));
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
+int bopy_gp_predict_cov(bopy_gp* gp, const double* Xs_dev, int64_t m, double* mean_out, double* cov_out,
+                        void* stream) {
+    int rc = check_ready(gp);
+    if (rc != BOPY_OK) return rc;
+    if (Xs_dev == nullptr || cov_out == nullptr) return fail(BOPY_ERR_BAD_ARG, "Xs_dev / cov_out is NULL");
+    if (m < 1) return fail(BOPY_ERR_BAD_ARG, "m must be >= 1 (got %lld)", (long long)m);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    const long long ntiles = (m + BN - 1) / BN;
+    void* Vall = nullptr;
+    CUDA_TRY(cudaMalloc(&Vall, (size_t)ntiles * gp->n_pad * BN * elem_size(gp->dtype)));
+    rc = run_sweep(gp, Xs_dev, m, BOPY_ACQ_NONE, 0.0, 0.0, mean_out, nullptr, nullptr, 0, nullptr, nullptr, Vall, 1, st);
+    if (rc == BOPY_OK) {
+        LsParam ls;
+        for (int q = 0; q < MAX_D; ++q) ls.v[q] = q < gp->d ? gp->ls[q] : 1.0;
+        rc = gp->dtype == BOPY_F64 ? launch_cov_k<double>(gp, Vall, Xs_dev, m, ls, cov_out, st)
+                                   : launch_cov_k<float>(gp, Vall, Xs_dev, m, ls, cov_out, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(Vall);
+    if (rc != BOPY_OK) return rc;
+    if (e != cudaSuccess) return fail(BOPY_ERR_CUDA, "predict_cov failed: %s", cudaGetErrorString(e));
+    return BOPY_OK;
+}
+
+int bopy_candidates_uniform(uint64_t seed, int64_t index_base, int64_t m, int d, const double* lowers_host,
+                            const double* uppers_host, double* out_dev, void* stream) {
+    if (lowers_host == nullptr || uppers_host == nullptr || out_dev == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "lowers/uppers/out must be non-NULL");
+    if (m < 1 || d < 1 || d > MAX_D) return fail(BOPY_ERR_BAD_ARG, "need m >= 1 and 1 <= d <= %d", MAX_D);
+    if (index_base < 0) return fail(BOPY_ERR_BAD_ARG, "index_base must be >= 0");
+    BoxParam box;
+    for (int q = 0; q < MAX_D; ++q) {
+        box.lo[q] = q < d ? lowers_host[q] : 0.0;
+        box.hi[q] = q < d ? uppers_host[q] : 1.0;
+    }
+    const long long total = (long long)m * d;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    candidates_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(seed, index_base, m, d, box, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
+int bopy_measure_peak(int what, double* tflops_out) {
+    if (tflops_out == nullptr) return fail(BOPY_ERR_BAD_ARG, "tflops_out is NULL");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    const int grid = prop.multiProcessorCount * 8, block = 256;
+    void* sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, 64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best_ms = 1e30, flops = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        if (what == BOPY_PEAK_FP64_FMA) {
+            const int iters = 512;
+            peak_fma_kernel<double><<<grid, block>>>(reinterpret_cast<double*>(sink), iters, 1.0000001, 1e-9);
+            flops = 2.0 * grid * block * (double)iters * 64;
+        } else if (what == BOPY_PEAK_FP32_FMA) {
+            const int iters = 1024;
+            peak_fma_kernel<float><<<grid, block>>>(reinterpret_cast<float*>(sink), iters, 1.0000001f, 1e-9f);
+            flops = 2.0 * grid * block * (double)iters * 64;
+        } else if (what == BOPY_PEAK_FP64_MMA) {
+            const int iters = 512;
+            peak_dmma_kernel<<<grid, block>>>(reinterpret_cast<double*>(sink), iters, 1.0000001, 1e-9);
+            flops = 2.0 * grid * (block / 32) * (double)iters * 32 * 256;
+        } else {
+            cudaFree(sink);
+            return fail(BOPY_ERR_BAD_ARG, "unknown peak id %d", what);
+        }
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best_ms = std::min(best_ms, (double)ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    CUDA_TRY(cudaGetLastError());
+    *tflops_out = flops / (best_ms * 1e-3) / 1e12;
+    return BOPY_OK;
+}
+
+int bopy_gp_launch_info(const bopy_gp* gp, int64_t m, int* grid_out, int* launches_out, int64_t* workspace_bytes_out) {
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    const long long ntiles = (m + BN - 1) / BN;
+    if (grid_out) *grid_out = (int)std::min<long long>(ntiles, gp->sm_count);
+    if (launches_out) *launches_out = 2;  // sweep_kernel + minloc_finalize_kernel (argmin); 1 without argmin
+    if (workspace_bytes_out) *workspace_bytes_out = (int64_t)gp->sm_count * gp->n_pad * BN * (int64_t)elem_size(gp->dtype);
+    return BOPY_OK;
+}
+
+}  // extern "C"

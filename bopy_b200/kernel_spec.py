@@ -1,0 +1,66 @@
+"""Translate a fitted scikit-learn kernel into the flat description the C ABI takes.
+
+Supported (what bopy's users build, bopy/surrogate.py:72-91 + tests/test_surrogate.py:24-27):
+``RBF``, ``Matern(nu in {0.5, 1.5, 2.5})``, optionally multiplied by ``ConstantKernel``s and
+optionally summed with one ``WhiteKernel``.  Anything else raises: the B200 path never silently
+approximates a kernel it does not implement.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+_MATERN_IDS = {0.5: "matern12", 1.5: "matern32", 2.5: "matern52"}
+
+
+@dataclass
+class FlatKernel:
+    kernel: str               # 'rbf' | 'matern12' | 'matern32' | 'matern52'  (bopy_kernel enum names)
+    length_scale: np.ndarray  # (1,) isotropic or (d,) ARD
+    amplitude: float          # product of the ConstantKernel factors
+    noise_level: float        # WhiteKernel level; enters k(x, x) only
+
+
+class UnsupportedKernelError(ValueError):
+    pass
+
+
+def flatten_sklearn_kernel(kernel) -> FlatKernel:
+    from sklearn.gaussian_process import kernels as sk
+
+    amplitude, noise, base = 1.0, 0.0, None
+
+    def visit_factor(node):
+        nonlocal amplitude, base
+        if isinstance(node, sk.Product):
+            visit_factor(node.k1)
+            visit_factor(node.k2)
+        elif isinstance(node, sk.ConstantKernel):
+            amplitude *= float(node.constant_value)
+        elif isinstance(node, (sk.Matern, sk.RBF)):
+            if base is not None:
+                raise UnsupportedKernelError("products of two stationary kernels are not supported")
+            base = node
+        else:
+            raise UnsupportedKernelError(f"unsupported kernel component: {node!r}")
+
+    if isinstance(kernel, sk.Sum):
+        terms = (kernel.k1, kernel.k2)
+        whites = [t for t in terms if isinstance(t, sk.WhiteKernel)]
+        others = [t for t in terms if not isinstance(t, sk.WhiteKernel)]
+        if len(whites) != 1 or len(others) != 1:
+            raise UnsupportedKernelError(f"only `stationary + WhiteKernel` sums are supported, got {kernel!r}")
+        noise = float(whites[0].noise_level)
+        visit_factor(others[0])
+    else:
+        visit_factor(kernel)
+    if base is None:
+        raise UnsupportedKernelError(f"no RBF / Matern component in {kernel!r}")
+    if isinstance(base, sk.Matern):
+        nu = float(base.nu)
+        if nu not in _MATERN_IDS:
+            raise UnsupportedKernelError(f"Matern nu={nu} is not supported (0.5, 1.5, 2.5 are)")
+        name = _MATERN_IDS[nu]
+    else:
+        name = "rbf"
+    ls = np.atleast_1d(np.asarray(base.length_scale, dtype=np.float64)).copy()
+    return FlatKernel(kernel=name, length_scale=ls, amplitude=amplitude, noise_level=noise)

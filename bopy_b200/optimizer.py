@@ -1,0 +1,221 @@
+"""Acquisition optimisers: `optimize() -> OptimizationResult(x_min (b, d), f_min (b,))`.
+
+The interface is the reference's (bopy/optimizer.py:17-67).  The reference's only base optimiser
+probes the acquisition ONE point per call through Fortran DIRECT (bopy/optimizer.py:95-107); here
+the base optimiser is `CandidateSweepOptimizer`: a large counter-based candidate set is generated
+on the device, the fused posterior -> acquisition -> argmin kernel sweeps it, and optional zoom
+rounds re-sweep shrinking boxes around the incumbent.  `DirectOptimizer` is kept for drop-in use
+(scipy's DIRECT instead of the unmaintained `scipydirect`); the batch wrappers are unchanged logic.
+"""
+from abc import ABC, abstractmethod
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _native
+from .acquisition import (AcquisitionFunction, OneShotBatchAcquisitionFunction,
+                          SequentialBatchAcquisitionFunction)
+from .bounds import Bounds
+
+
+@dataclass
+class OptimizationResult:
+    """x_min: (batch_size, n_dimensions) argmin; f_min: (batch_size,) acquisition value there."""
+
+    x_min: np.ndarray
+    f_min: np.ndarray
+
+
+class Optimizer(ABC):
+    """Finds the minimiser of `acquisition_function` inside `bounds`."""
+
+    def __init__(self, acquisition_function: AcquisitionFunction, bounds: Bounds):
+        self.acquisition_function = acquisition_function
+        self.bounds = bounds
+
+    def optimize(self) -> OptimizationResult:
+        x_min, f_min = self._optimize()
+        return OptimizationResult(x_min=x_min, f_min=f_min)
+
+    @abstractmethod
+    def _optimize(self) -> Tuple[np.ndarray, np.ndarray]:
+        ...
+
+
+class CandidateSweepOptimizer(Optimizer):
+    """Batched argmin of the acquisition over `n_candidates` uniform candidates (+ zoom rounds).
+
+    Parameters
+    ----------
+    n_candidates : int
+        Size of the global sweep.  Candidates come from the counter-based generator
+        (`bopy_candidates_uniform`): candidate i depends only on (seed, i), so any sharding of the
+        index range over GPUs sees the same set.
+    zoom_rounds, zoom_candidates, zoom_shrink :
+        After the global sweep, `zoom_rounds` local sweeps of `zoom_candidates` points in a box of
+        half-width `zoom_shrink**k * (upper - lower) / 2` around the incumbent (clipped to the bounds);
+        the incumbent itself is candidate 0 of every round, so the value never gets worse.
+    seed : int
+        Base seed; the k-th call to `optimize()` uses seed + k.
+    process_group : torch.distributed group or None
+        With a group, each rank sweeps its contiguous slice of the index range and ONE min-loc
+        all-gather picks the winner (see bopy_b200/distributed.py).
+    """
+
+    def __init__(self, acquisition_function: AcquisitionFunction, bounds: Bounds, n_candidates: int = 1 << 20,
+                 zoom_rounds: int = 0, zoom_candidates: int = 1 << 14, zoom_shrink: float = 0.25, seed: int = 0,
+                 process_group=None, distributed: bool = False):
+        super().__init__(acquisition_function, bounds)
+        if n_candidates < 1:
+            raise ValueError("`n_candidates` must be positive.")
+        self.n_candidates = int(n_candidates)
+        self.zoom_rounds = int(zoom_rounds)
+        self.zoom_candidates = int(zoom_candidates)
+        self.zoom_shrink = float(zoom_shrink)
+        self.seed = int(seed)
+        self.process_group = process_group
+        self.distributed = distributed or process_group is not None
+        self._calls = 0
+
+    def _sweep_box(self, seed, lowers, uppers, m, incumbent=None):
+        """argmin over m candidates in [lowers, uppers); returns (x (d,), value)."""
+        from .distributed import sharded_argmin
+        acq = self.acquisition_function
+        if self.distributed:
+            return sharded_argmin(acq, seed, lowers, uppers, m, group=self.process_group, incumbent=incumbent)
+        torch = _native.require_cuda()
+        xs = _native.candidates_uniform(seed, 0, m, lowers, uppers)
+        if incumbent is not None:
+            xs[0] = torch.as_tensor(incumbent, dtype=torch.float64, device=xs.device)
+        idx, val = acq.argmin(xs)
+        return xs[idx].cpu().numpy(), val
+
+    def _optimize(self) -> Tuple[np.ndarray, np.ndarray]:
+        lo = np.asarray(self.bounds.lowers, dtype=np.float64)
+        hi = np.asarray(self.bounds.uppers, dtype=np.float64)
+        seed = self.seed + 7919 * self._calls
+        self._calls += 1
+        x, val = self._sweep_box(seed, lo, hi, self.n_candidates)
+        half = (hi - lo) / 2.0
+        for k in range(1, self.zoom_rounds + 1):
+            half = half * self.zoom_shrink
+            zl, zu = np.maximum(lo, x - half), np.minimum(hi, x + half)
+            x, val = self._sweep_box(seed + k, zl, zu, self.zoom_candidates, incumbent=x)
+        return np.array([x]), np.array([val])
+
+
+class DirectOptimizer(Optimizer):
+    """DIRECT global optimiser, one acquisition probe per call (bopy/optimizer.py:70-107).
+
+    The reference binds the Fortran `scipydirect.minimize`; this uses `scipy.optimize.direct`
+    (the same algorithm).  `direct_kwargs` accepts scipydirect's names (`maxf`, `maxT`, `eps`,
+    `algmethod`) and maps them onto scipy's (`maxfun`, `maxiter`, `eps`, `locally_biased`).
+    """
+
+    _RENAMED = {"maxf": "maxfun", "maxT": "maxiter", "algmethod": "locally_biased"}
+
+    def __init__(self, acquisition_function: AcquisitionFunction, bounds: Bounds, **direct_kwargs: Dict[str, Any]):
+        super().__init__(acquisition_function, bounds)
+        self.direct_kwargs = direct_kwargs
+
+    def _optimize(self) -> Tuple[np.ndarray, np.ndarray]:
+        from scipy.optimize import direct
+
+        kwargs = {}
+        for key, value in self.direct_kwargs.items():
+            name = self._RENAMED.get(key, key)
+            kwargs[name] = bool(value) if name == "locally_biased" else value
+
+        def objective(point):
+            return float(self.acquisition_function(np.asarray(point, dtype=np.float64).reshape(1, -1))[0])
+
+        res = direct(objective, bounds=list(zip(self.bounds.lowers, self.bounds.uppers)), **kwargs)
+        return np.array([res.x]), np.array([res.fun])
+
+
+class SequentialBatchOptimizer(Optimizer):
+    """Builds a batch by optimising / updating a SequentialBatchAcquisitionFunction `batch_size` times
+    (bopy/optimizer.py:110-167)."""
+
+    def __init__(self, acquisition_function: SequentialBatchAcquisitionFunction, bounds: Bounds,
+                 base_optimizer: Optimizer, batch_size: int):
+        super().__init__(acquisition_function, bounds)
+        self.base_optimizer = base_optimizer
+        self.batch_size = batch_size
+        self.x_mins = []
+        self.f_mins = []
+
+    def start_batch(self) -> None:
+        self.x_mins, self.f_mins = [], []
+
+    def add_to_batch(self, optimization_result: OptimizationResult) -> None:
+        self.x_mins.append(optimization_result.x_min)
+        self.f_mins.append(optimization_result.f_min)
+
+    def get_batch(self) -> Tuple[np.ndarray, np.ndarray]:
+        return np.concatenate(self.x_mins), np.concatenate(self.f_mins)
+
+    def _optimize(self) -> Tuple[np.ndarray, np.ndarray]:
+        acq = self.acquisition_function
+        self.start_batch()
+        acq.start_batch()
+        for _ in range(self.batch_size):
+            picked = self.base_optimizer.optimize()
+            self.add_to_batch(picked)
+            acq.add_to_batch(picked)
+        acq.finish_batch()
+        return self.get_batch()
+
+
+class OneShotBatchOptimizerStrategy(ABC):
+    """Chooses `batch_size` of the points one global optimisation pass evaluated."""
+
+    @abstractmethod
+    def select(self, x: np.ndarray, a_x: np.ndarray, batch_size: int) -> Tuple[np.ndarray, np.ndarray]:
+        raise NotImplementedError
+
+
+class OneShotBatchOptimizerRandomSamplingStrategy(OneShotBatchOptimizerStrategy):
+    """Uniformly random subset (with replacement, like the reference: bopy/optimizer.py:186-197)."""
+
+    def select(self, x, a_x, batch_size):
+        chosen = np.random.choice(len(x), size=batch_size)
+        return x[chosen], a_x[chosen]
+
+
+class OneShotBatchOptimizerKDPPSamplingStrategy(OneShotBatchOptimizerStrategy):
+    """k-DPP sample with likelihood kernel(x) + alpha I (bopy/optimizer.py:200-232); needs `dppy`."""
+
+    def __init__(self, kernel: Callable[[np.ndarray], np.ndarray], alpha: float = 1e-5):
+        super().__init__()
+        self.kernel = kernel
+        self.alpha = alpha
+
+    def select(self, x, a_x, batch_size):
+        try:
+            from dppy.finite_dpps import FiniteDPP
+        except ImportError as exc:  # the dependency is optional and absent from this image
+            raise ImportError("the k-DPP strategy needs the `dppy` package") from exc
+        dpp = FiniteDPP("likelihood", L=self.kernel(x) + self.alpha * np.eye(len(x)))
+        dpp.sample_exact_k_dpp(size=batch_size)
+        chosen = dpp.list_of_samples[0]
+        return x[chosen], a_x[chosen]
+
+
+class OneShotBatchOptimizer(Optimizer):
+    """One global pass of `base_optimizer`, then `strategy` picks the batch from the logged evaluations
+    (bopy/optimizer.py:235-276)."""
+
+    def __init__(self, acquisition_function: OneShotBatchAcquisitionFunction, bounds: Bounds,
+                 base_optimizer: Optimizer, batch_size: int, strategy: OneShotBatchOptimizerStrategy):
+        super().__init__(acquisition_function, bounds)
+        self.base_optimizer = base_optimizer
+        self.batch_size = batch_size
+        self.strategy = strategy
+
+    def _optimize(self) -> Tuple[np.ndarray, np.ndarray]:
+        self.acquisition_function.start_optimization()
+        self.base_optimizer.optimize()
+        xs, a_xs = self.acquisition_function.get_evaluations()
+        return self.strategy.select(xs, a_xs, self.batch_size)

@@ -1,0 +1,127 @@
+"""Surrogate models: the `fit` / `predict` interface of bopy/surrogate.py with the posterior on a B200.
+
+`Surrogate` keeps the reference's template (validate -> store references -> `_fit` -> mark fitted;
+validate -> `_predict`, bopy/surrogate.py:26-69).  `B200GPSurrogate` takes the same constructor
+argument as the reference's `ScipyGPSurrogate` (a scikit-learn `GaussianProcessRegressor`), lets
+scikit-learn do the fit exactly as the reference does (bopy/surrogate.py:87-88; the fit is not on
+the hot path), then hands the fitted state to the C ABI.  Every prediction afterwards --
+`predict` (mean + full covariance), `predict_diag`, the fused acquisition values and the fused
+acquisition argmin -- runs in the sm_100a kernels.  numpy in, numpy out.
+"""
+from abc import ABC, abstractmethod
+from typing import Tuple
+
+import numpy as np
+
+from . import _native
+from .kernel_spec import flatten_sklearn_kernel
+from .mixin import FittableMixin
+
+
+class Surrogate(FittableMixin, ABC):
+    """A probabilistic stand-in for the objective: `fit(x, y)` then `predict(x) -> (mean, cov)`."""
+
+    def __init__(self):
+        super().__init__()
+        self.has_been_fitted = False
+        self.n_dimensions = -1
+        self.x = np.array([])
+        self.y = np.array([])
+
+    def fit(self, x: np.ndarray, y: np.ndarray) -> None:
+        """x: (n_samples, n_dimensions), y: (n_samples,).  Keeps references to both."""
+        self._validate_ok_for_fitting(x, y)
+        self.x, self.y = x, y
+        self._fit(x, y)
+        self._confirm_fit()
+
+    def predict(self, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """x: (n_samples, n_dimensions) -> mean (n_samples,), covariance (n_samples, n_samples)."""
+        self._validate_ok_for_predicting(x)
+        return self._predict(x)
+
+    @abstractmethod
+    def _fit(self, x: np.ndarray, y: np.ndarray) -> None:
+        ...
+
+    @abstractmethod
+    def _predict(self, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        ...
+
+
+class B200GPSurrogate(Surrogate):
+    """scikit-learn GP regressor whose posterior is evaluated by the B200 kernels.
+
+    Parameters
+    ----------
+    gp : sklearn.gaussian_process.GaussianProcessRegressor
+        Same object the reference's ScipyGPSurrogate wraps (bopy/surrogate.py:82-85).
+    dtype : 'f64' | 'f32'
+        Arithmetic of the triangular solve.  'f64' matches the reference to ~1e-12; 'f32' keeps the
+        kernel tile, the mean and the variance reduction in fp64 and solves in fp32.
+    device : int | str | torch.device | None
+        CUDA device (default: current).
+    """
+
+    def __init__(self, gp, dtype: str = "f64", device=None):
+        super().__init__()
+        if dtype not in ("f64", "f32"):
+            raise ValueError("dtype must be 'f64' or 'f32'")
+        self.gp = gp
+        self.dtype = dtype
+        self.device = device
+        self.native = None          # _native.NativeGP once fitted
+        self.kernel_spec = None
+
+    # -- fit: host (scikit-learn), then upload ---------------------------------------------------
+    def _fit(self, x: np.ndarray, y: np.ndarray) -> None:
+        self.gp.fit(x, y)
+        self.load_fitted_state()
+
+    def load_fitted_state(self) -> None:
+        """(Re)install the state of `self.gp` -- X_train_, L_, alpha_, kernel_, y mean/std -- on the device."""
+        gp = self.gp
+        spec = flatten_sklearn_kernel(gp.kernel_)
+        X = np.ascontiguousarray(gp.X_train_, dtype=np.float64)
+        n, d = X.shape
+        if np.ndim(gp.alpha_) != 1:
+            raise ValueError("multi-target GPs are not supported")
+        if (self.native is None or self.native.n != n or self.native.d != d
+                or self.native.kernel != spec.kernel):
+            if self.native is not None:
+                self.native.close()
+            self.native = _native.NativeGP(n, d, kernel=spec.kernel, dtype=self.dtype, device=self.device)
+        self.native.set_state(
+            X, gp.L_, gp.alpha_, spec.length_scale, amplitude=spec.amplitude, noise_level=spec.noise_level,
+            y_mean=float(np.ravel(gp._y_train_mean)[0]), y_std=float(np.ravel(gp._y_train_std)[0]))
+        self.kernel_spec = spec
+
+    # -- the reference contract --------------------------------------------------------------------
+    def _predict(self, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        xs = self.native.candidates(x)
+        mean, cov = self.native.predict_cov(xs)
+        return mean.cpu().numpy(), cov.cpu().numpy()
+
+    # -- additive, diagonal-only and fused entry points ---------------------------------------------
+    def predict_diag(self, x) -> Tuple[np.ndarray, np.ndarray]:
+        """mean (m,), var (m,) = diagonal of `predict` without the m x m matrix."""
+        self._validate_ok_for_predicting(x)
+        out = self.native.sweep(self.native.candidates(x), want_mean=True, want_var=True)
+        return out["mean"].cpu().numpy(), out["var"].cpu().numpy()
+
+    def acquisition_values(self, kind: str, x, eta: float = 0.0, kappa: float = 2.0) -> np.ndarray:
+        """Fused posterior -> acquisition; (m,) numpy."""
+        out = self.native.sweep(self.native.candidates(x), acq=kind, eta=eta, kappa=kappa, want_acq=True)
+        return out["acq"].cpu().numpy()
+
+    def acquisition_argmin(self, kind: str, x, eta: float = 0.0, kappa: float = 2.0, index_base: int = 0):
+        """Fused posterior -> acquisition -> argmin over the rows of x (numpy or device tensor).
+
+        Returns (index, value) with np.argmin's rules (first minimum; first NaN wins)."""
+        out = self.native.sweep(self.native.candidates(x), acq=kind, eta=eta, kappa=kappa, want_min=True,
+                                index_base=index_base)
+        return int(out["min_idx"].item()), float(out["min_val"].item())
+
+
+# Drop-in name: code written against the reference keeps working and runs on the B200.
+ScipyGPSurrogate = B200GPSurrogate

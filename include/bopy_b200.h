@@ -1,0 +1,130 @@
+/*
+ * bopy_b200.h -- C ABI of the B200-native GP posterior -> acquisition -> argmin path.
+ *
+ * The reference (tompretty/bopy) is pure Python and has no FFI / plugin registry; its seams for
+ * this path are three template methods.  Each entry point below names the reference interface it
+ * stands behind (paths relative to /root/reference; $SK = sklearn/gaussian_process of
+ * scikit-learn 1.9.0, the library the reference delegates the arithmetic to):
+ *
+ *   bopy_gp_set_state      <- state left by ScipyGPSurrogate._fit     bopy/surrogate.py:87-88
+ *                             ($SK/_gpr.py:349-367: X_train_, L_, alpha_, kernel_, y mean/std)
+ *   bopy_gp_predict_cov    <- ScipyGPSurrogate._predict                bopy/surrogate.py:90-91
+ *                             ($SK/_gpr.py:446-473, return_cov branch)
+ *   bopy_gp_predict_diag   <- np.diag(sigma) as every acquisition uses it   bopy/acquisition.py:84-85,100-101,124-125
+ *   bopy_acq_eval          <- LCB._f / EI._f / POI._f                  bopy/acquisition.py:83-85, 99-106, 123-128
+ *   bopy_acq_argmin        <- Optimizer._optimize() -> (x_min, f_min)  bopy/optimizer.py:65-67, 99-107
+ *                             (np.argmin rules: first minimum, first NaN wins)
+ *   bopy_candidates_uniform<- the candidate set an optimiser sweeps (bounds: bopy/bounds.py:36-54)
+ *
+ * Conventions
+ *   - plain C, no CUDA / torch types: a stream is passed as `void*` (a cudaStream_t), device
+ *     buffers as raw pointers.  The caller owns every buffer it passes and keeps it alive until
+ *     the stream has been synchronised; the handle owns only its private packed copies/workspace.
+ *   - all state and all inputs/outputs are IEEE fp64 (what the reference computes in); `dtype`
+ *     selects the arithmetic of the triangular solve (fp64, or fp32 with fp64 kernel tile / mean /
+ *     variance accumulation).
+ *   - every call returns BOPY_OK (0) or a negative error code; the message is available from
+ *     bopy_last_error() (thread-local).  Nothing throws across the boundary.  There is no CPU
+ *     fallback: without a CUDA device every compute entry returns BOPY_ERR_CUDA.
+ *   - calls are asynchronous on the given stream unless stated otherwise.  A handle is not
+ *     thread-safe; use one handle per device (one process per GPU).
+ */
+#ifndef BOPY_B200_H
+#define BOPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BOPY_B200_ABI_VERSION 1
+
+typedef struct bopy_gp bopy_gp;
+
+enum bopy_status {
+    BOPY_OK = 0,
+    BOPY_ERR_BAD_ARG = -1,
+    BOPY_ERR_CUDA = -2,
+    BOPY_ERR_UNSUPPORTED = -3,
+    BOPY_ERR_NOT_READY = -4
+};
+
+enum bopy_dtype { BOPY_F64 = 0, BOPY_F32 = 1 };
+
+/* base kernel k(r), r = |x/l - x'/l|  ($SK/kernels.py:1558-1570 RBF, :1713-1729 Matern) */
+enum bopy_kernel { BOPY_KERNEL_RBF = 0, BOPY_KERNEL_MATERN12 = 1, BOPY_KERNEL_MATERN32 = 2, BOPY_KERNEL_MATERN52 = 3 };
+
+/* acquisition functions, MINIMISATION convention (bopy/acquisition.py:14-17) */
+enum bopy_acq { BOPY_ACQ_NONE = -1, BOPY_ACQ_LCB = 0, BOPY_ACQ_EI = 1, BOPY_ACQ_POI = 2 };
+
+/* what bopy_measure_peak times */
+enum bopy_peak { BOPY_PEAK_FP64_FMA = 0, BOPY_PEAK_FP32_FMA = 1, BOPY_PEAK_FP64_MMA = 2 };
+
+int bopy_abi_version(void);
+const char* bopy_last_error(void);
+
+/* Create a handle for a GP with n training points in d dimensions (1 <= d <= 32) on CUDA `device`. */
+int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, int d);
+void bopy_gp_destroy(bopy_gp* gp);
+
+/*
+ * Install the fitted state.  X_dev (n,d) row-major, L_dev (n,n) row-major lower Cholesky factor of
+ * K + alpha*I (entries above the diagonal are ignored), alpha_dev (n,): device pointers, fp64.
+ * length_scale_host: n_ls = 1 (isotropic) or d (ARD) host doubles.  amplitude = ConstantKernel
+ * value, noise_level = WhiteKernel level (enters k(x,x) only), y_mean / y_std = target
+ * normalisation ($SK/_gpr.py:275-285).  Packs L into the solve layout (negated off-diagonal tiles,
+ * inverted 128x128 diagonal blocks) on the device; synchronises the stream before returning.
+ */
+int bopy_gp_set_state(bopy_gp* gp, const double* X_dev, const double* L_dev, const double* alpha_dev,
+                      const double* length_scale_host, int n_ls, double amplitude, double noise_level,
+                      double y_mean, double y_std, void* stream);
+
+/*
+ * The fused sweep.  For candidates Xs_dev (m,d) row-major fp64 computes posterior mean and variance
+ * (diagonal only, never the m x m matrix), the acquisition `acq` (eta = min(y) for EI/POI, kappa for
+ * LCB) and the argmin over the m candidates.  Every output pointer may be NULL: mean_out/var_out/
+ * acq_out (m,) fp64; min_val_out/min_idx_out one fp64 / int64 (index = index_base + local index;
+ * first-minimum and first-NaN rules of np.argmin).
+ */
+int bopy_gp_posterior_acq(bopy_gp* gp, const double* Xs_dev, int64_t m, int acq, double eta, double kappa,
+                          double* mean_out, double* var_out, double* acq_out,
+                          int64_t index_base, double* min_val_out, int64_t* min_idx_out, void* stream);
+
+/* Named views of the fused sweep. */
+int bopy_gp_predict_diag(bopy_gp* gp, const double* Xs_dev, int64_t m, double* mean_out, double* var_out,
+                         void* stream);
+int bopy_acq_eval(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
+                  double* acq_out, void* stream);
+int bopy_acq_argmin(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
+                    int64_t index_base, double* min_val_out, int64_t* min_idx_out, void* stream);
+
+/* The acquisition epilogue alone, on posterior moments already on the device (mean_dev, var_dev (m,) fp64):
+ * the same device code as the fused sweep's epilogue.  Serves surrogates that are not B200-native (a
+ * user-defined Surrogate subclass whose predict() ran elsewhere); intended for small m. */
+int bopy_acq_from_moments(int acq, double eta, double kappa, const double* mean_dev, const double* var_dev,
+                          int64_t m, double* acq_out, int64_t index_base, double* min_val_out,
+                          int64_t* min_idx_out, void* stream);
+
+/* The Surrogate.predict contract: mean (m,) and the full covariance (m,m) row-major, fp64.
+ * Needs an (n_pad x m) workspace inside the handle; intended for small m (plots, fantasies). */
+int bopy_gp_predict_cov(bopy_gp* gp, const double* Xs_dev, int64_t m, double* mean_out, double* cov_out,
+                        void* stream);
+
+/* Counter-based uniform candidates in a box: out_dev (m,d) row-major fp64,
+ * x[i][j] = lo[j] + u * (hi[j] - lo[j]), u = (splitmix64(seed + G*((index_base+i)*d + j + 1)) >> 11) * 2^-53.
+ * Identical for every sharding of the index range (restated in oracle/gp_oracle.py). */
+int bopy_candidates_uniform(uint64_t seed, int64_t index_base, int64_t m, int d, const double* lowers_host,
+                            const double* uppers_host, double* out_dev, void* stream);
+
+/* Register-resident FMA / MMA microbenchmark on the current device: the roofline denominator of the
+ * solve.  Synchronous.  Writes TFLOP/s (2 flops per FMA). */
+int bopy_measure_peak(int what, double* tflops_out);
+
+/* Introspection used by bench.py / tests: thread blocks one sweep launches and kernels per sweep. */
+int bopy_gp_launch_info(const bopy_gp* gp, int64_t m, int* grid_out, int* launches_out, int64_t* workspace_bytes_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOPY_B200_H */

@@ -1,0 +1,220 @@
+"""Host-side behaviour of the drop-in API that needs no GPU: argument validation (messages verbatim from the
+reference, bopy/mixin.py:34-64 / tests/test_surrogate.py:55-101), bounds, designs, objectives, the BayesOpt loop
+and its callbacks driven with CPU test doubles, kernel flattening, loud failure without CUDA."""
+import numpy as np
+import pytest
+from sklearn.gaussian_process import GaussianProcessRegressor
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel, DotProduct, Matern, WhiteKernel
+
+import bopy_b200
+from bopy_b200.acquisition import EI, LCB, POI, AcquisitionFunction, KriggingBeliever, OneShotBatchAcquisitionFunction
+from bopy_b200.bayes_opt import BayesOpt, BOResult
+from bopy_b200.benchmark_functions import bohachevsky, branin, forrester, hartmann6
+from bopy_b200.bounds import Bound, Bounds
+from bopy_b200.callback import EVENTS, Callback
+from bopy_b200.exceptions import NativeLibraryError, NotFittedError
+from bopy_b200.initial_design import (LatinHypercubeInitialDesign, SobolSequenceInitialDesign,
+                                      UniformRandomInitialDesign)
+from bopy_b200.kernel_spec import UnsupportedKernelError, flatten_sklearn_kernel
+from bopy_b200.optimizer import (OneShotBatchOptimizer, OneShotBatchOptimizerRandomSamplingStrategy,
+                                 OptimizationResult, Optimizer, SequentialBatchOptimizer)
+from bopy_b200.surrogate import B200GPSurrogate, ScipyGPSurrogate, Surrogate
+
+
+def make_surrogate():
+    return ScipyGPSurrogate(gp=GaussianProcessRegressor(kernel=Matern(nu=1.5), alpha=1e-5, normalize_y=True))
+
+
+class TestArgumentsToFit:
+    @pytest.mark.parametrize("x, y, message", [
+        (np.array([]), np.array([1.0]), "`x` must contain at least one sample"),
+        (np.array([[1.0]]), np.array([]), "`y` must contain at least one sample"),
+        (np.array([[1.0]]), np.array([1.0, 1.0]), "`x` and `y` must have the same number of samples"),
+        (np.array([[[1.0]]]), np.array([1.0]), "`x` must be 2D"),
+        (np.array([[1.0]]), np.array([[1.0]]), "`y` must be 1D"),
+    ])
+    def test_bad_fit_arguments_raise_before_anything_runs(self, x, y, message):
+        with pytest.raises(ValueError, match=message):
+            make_surrogate().fit(x=x, y=y)
+        for cls in (LCB, EI, POI):
+            with pytest.raises(ValueError, match=message):
+                cls(make_surrogate()).fit(x, y)
+
+
+def test_predict_before_fit_raises_not_fitted():
+    x = np.linspace(0, 1, 10).reshape(-1, 1)
+    with pytest.raises(NotFittedError, match="must be fitted first"):
+        make_surrogate().predict(x)
+    for cls in (LCB, EI, POI):
+        with pytest.raises(NotFittedError, match="must be fitted first"):
+            cls(make_surrogate())(x)
+
+
+def test_predict_argument_validation_after_fit():
+    sur = make_surrogate()
+    sur.has_been_fitted, sur.n_dimensions = True, 1   # validation is host-side and precedes any device work
+    with pytest.raises(ValueError, match="`x` must contain at least one sample"):
+        sur.predict(np.array([]))
+    with pytest.raises(ValueError, match="`x` must be 2D"):
+        sur.predict(np.array([1.0]))
+    with pytest.raises(ValueError, match="`x` must have the same number of dimensions as the training data"):
+        sur.predict(np.array([[1.0, 1.0]]))
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    x = np.linspace(0, 1, 10).reshape(-1, 1)
+    with pytest.raises(NativeLibraryError, match="no CPU fallback"):
+        make_surrogate().fit(x, forrester(x))
+
+
+def test_drop_in_names_and_constructors():
+    assert ScipyGPSurrogate is B200GPSurrogate and issubclass(B200GPSurrogate, Surrogate)
+    sur = make_surrogate()
+    assert LCB(sur).kappa == 2.0 and LCB(sur, kappa=0.5).kappa == 0.5
+    assert EI(sur)._eta == np.inf and POI(sur)._eta == np.inf
+    for mod in ("acquisition", "bayes_opt", "benchmark_functions", "bounds", "callback", "exceptions",
+                "initial_design", "mixin", "optimizer", "surrogate"):
+        assert hasattr(bopy_b200, mod)
+
+
+def test_bounds():
+    with pytest.raises(ValueError, match="`lower` must be less than `upper`"):
+        Bound(lower=1.0, upper=0.0)
+    with pytest.raises(ValueError, match="`lower` must be less than `upper`"):
+        Bound(lower=1.0, upper=1.0)
+    with pytest.raises(ValueError, match="`bounds` must contain at least one bound."):
+        Bounds(bounds=[])
+    b = Bounds(bounds=[Bound(0.0, 1.0), Bound(-2.0, 3.0)])
+    assert b.n_dimensions == 2 and b.lowers == [0.0, -2.0] and b.uppers == [1.0, 3.0]
+
+
+@pytest.mark.parametrize("design", [UniformRandomInitialDesign(), SobolSequenceInitialDesign(),
+                                    LatinHypercubeInitialDesign()])
+def test_initial_designs(design):
+    bounds = Bounds(bounds=[Bound(-1.0, 2.0), Bound(10.0, 11.0)])
+    with pytest.raises(ValueError, match="`n_points` must be positive."):
+        design.generate(bounds, 0)
+    pts = design.generate(bounds, 10)
+    assert pts.shape == (10, 2)
+    assert (pts >= np.array(bounds.lowers)).all() and (pts <= np.array(bounds.uppers)).all()
+
+
+def test_benchmark_functions():
+    assert forrester(np.array([[0.757249]]))[0] == pytest.approx(-6.02074, abs=1e-5)
+    assert bohachevsky(np.zeros((1, 2)))[0] == pytest.approx(0.0, abs=1e-12)
+    assert branin(np.array([[np.pi, 2.275], [-np.pi, 12.275], [9.42478, 2.475]])) == pytest.approx(0.397887, abs=1e-5)
+    assert hartmann6(np.array([[0.20169, 0.150011, 0.476874, 0.275332, 0.311652, 0.6573]]))[0] == \
+        pytest.approx(-3.32237, abs=1e-5)
+    assert forrester(np.zeros((4, 1))).shape == (4,) and hartmann6(np.zeros((3, 6))).shape == (3,)
+
+
+def test_kernel_flattening():
+    f = flatten_sklearn_kernel(ConstantKernel(2.5) * RBF([0.2, 0.7, 1.3]) + WhiteKernel(1e-3))
+    assert (f.kernel, f.amplitude, f.noise_level) == ("rbf", 2.5, 1e-3) and f.length_scale.tolist() == [0.2, 0.7, 1.3]
+    f = flatten_sklearn_kernel(Matern(length_scale=0.4, nu=2.5) * ConstantKernel(3.0) * ConstantKernel(0.5))
+    assert (f.kernel, f.amplitude, f.noise_level) == ("matern52", 1.5, 0.0) and f.length_scale.tolist() == [0.4]
+    assert flatten_sklearn_kernel(Matern(nu=0.5)).kernel == "matern12"
+    assert flatten_sklearn_kernel(RBF()).kernel == "rbf"
+    for bad in (DotProduct(), RBF() * RBF(), Matern(nu=3.5), RBF() + RBF(), ConstantKernel(1.0)):
+        with pytest.raises(UnsupportedKernelError):
+            flatten_sklearn_kernel(bad)
+
+
+# ---- the loop, driven with CPU test doubles (host logic only) --------------------------------------------------
+class NearestSurrogate(Surrogate):
+    def _fit(self, x, y):
+        pass
+
+    def _predict(self, x):
+        d = np.abs(x[:, None, 0] - self.x[None, :, 0])
+        return self.y[np.argmin(d, axis=1)], np.diag(np.min(d, axis=1) + 1e-3)
+
+
+class MeanAcquisition(AcquisitionFunction):
+    def _f(self, x):
+        mean, _ = self.surrogate.predict(x)
+        return mean
+
+
+class GridOptimizer(Optimizer):
+    def _optimize(self):
+        grid = np.linspace(self.bounds.lowers[0], self.bounds.uppers[0], 101).reshape(-1, 1)
+        values = self.acquisition_function(grid)
+        i = int(np.argmin(values))
+        return grid[i:i + 1], values[i:i + 1]
+
+
+class Recorder(Callback):
+    def __init__(self):
+        self.seen = []
+
+    def __getattribute__(self, name):
+        if name in EVENTS:
+            return lambda *args: object.__getattribute__(self, "seen").append((name, len(args)))
+        return object.__getattribute__(self, name)
+
+
+def make_loop(callbacks=None, optimizer_factory=None):
+    bounds = Bounds(bounds=[Bound(0.0, 1.0)])
+    sur = NearestSurrogate()
+    acq = MeanAcquisition(sur)
+    opt = (optimizer_factory or GridOptimizer)(acq, bounds)
+    return BayesOpt(objective_function=forrester, surrogate=sur, acquisition_function=acq, optimizer=opt,
+                    initial_design=UniformRandomInitialDesign(), bounds=bounds, callbacks=callbacks)
+
+
+def test_bayes_opt_loop_results_and_shapes():
+    np.random.seed(0)
+    bo = make_loop()
+    res = bo.run(n_trials=3, n_initial_design=5)
+    assert isinstance(res, BOResult)
+    assert res.x_opt.shape == (1, 1) and np.isscalar(res.f_opt + 0.0)
+    assert res.initial_design_result.x_selected.shape == (5, 1)
+    assert res.initial_design_result.f_selected.shape == (5,)
+    assert len(res.trial_results) == 3
+    for t in res.trial_results:
+        assert t.x_selected.shape == (1, 1) and t.f_selected.shape == (1,) and t.x_opt_so_far.shape == (1, 1)
+    assert bo.x.shape == (8, 1) and bo.y.shape == (8,)
+    assert res.f_opt == bo.y.min()
+    assert bo.surrogate.x is bo.x and bo.surrogate.y is bo.y          # references, not copies
+
+
+def test_every_callback_fires_in_order():
+    np.random.seed(0)
+    rec = Recorder()
+    make_loop(callbacks=[rec]).run(n_trials=1, n_initial_design=5)
+    assert rec.seen == [("on_initial_design_end", 1), ("on_acquisition_optimized", 2), ("on_surrogate_updated", 1),
+                        ("on_acquisition_updated", 1), ("on_trial_end", 1), ("on_bo_end", 1)]
+
+
+def test_sequential_batch_optimizer_with_kriging_believer():
+    np.random.seed(0)
+    bounds = Bounds(bounds=[Bound(0.0, 1.0)])
+    sur = NearestSurrogate()
+    x = np.random.rand(6, 1)
+    sur.fit(x, forrester(x))
+    kb = KriggingBeliever(MeanAcquisition(sur))
+    kb.fit(x, forrester(x))
+    opt = SequentialBatchOptimizer(kb, bounds, base_optimizer=GridOptimizer(kb, bounds), batch_size=3)
+    res = opt.optimize()
+    assert isinstance(res, OptimizationResult) and res.x_min.shape == (3, 1) and res.f_min.shape == (3,)
+    assert len(sur.x) == 6                                           # fantasies removed by finish_batch
+
+
+def test_one_shot_batch_optimizer_logs_and_selects():
+    np.random.seed(0)
+    bounds = Bounds(bounds=[Bound(0.0, 1.0)])
+    sur = NearestSurrogate()
+    x = np.random.rand(6, 1)
+    sur.fit(x, forrester(x))
+    acq = OneShotBatchAcquisitionFunction(MeanAcquisition(sur))
+    acq.fit(x, forrester(x))
+    opt = OneShotBatchOptimizer(acq, bounds, base_optimizer=GridOptimizer(acq, bounds), batch_size=4,
+                                strategy=OneShotBatchOptimizerRandomSamplingStrategy())
+    res = opt.optimize()
+    assert res.x_min.shape == (4, 1) and res.f_min.shape == (4,)
+    xs, a_xs = acq.get_evaluations()
+    assert xs.shape == (101, 1) and a_xs.shape == (101,)

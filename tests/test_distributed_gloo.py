@@ -1,0 +1,77 @@
+"""The N>1 path on CPU: world_size-2 gloo group, sharded index ranges, one min-loc exchange.
+The device pieces (candidate generator, fused argmin) are replaced by the oracle's numpy restatements."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from bopy_b200.distributed import minloc_better, reduce_minloc, shard_range
+
+
+def test_shard_range_partitions_exactly():
+    for m in (1, 7, 128, 100_003, 1 << 24):
+        for world in (1, 2, 3, 8):
+            cuts = [shard_range(m, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == m
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            sizes = [e - s for s, e in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_minloc_ordering_is_np_argmin():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        v = rng.choice([0.0, -0.0, 1.0, -1.0, np.nan, 2.5], size=6)
+        recs = [(float(x), i) for i, x in enumerate(v)]
+        rng.shuffle(recs)
+        assert reduce_minloc(recs)[1] == int(np.argmin(v))
+    assert not minloc_better((1.0, -1), (5.0, 3)) and minloc_better((5.0, 3), (1.0, -1))
+
+
+class FakeAcquisition:
+    """argmin over candidate rows with the numpy oracle of a toy acquisition (a(x) = |x - 0.3|_1)."""
+
+    def argmin(self, xs, index_base=0):
+        v = np.abs(xs.numpy() - 0.3).sum(1)
+        i = int(np.argmin(v))
+        return index_base + i, float(v[i])
+
+
+def _worker(rank, world, port, m, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bopy_b200._native as native
+    from bopy_b200.distributed import all_reduce_minloc, sharded_argmin
+    from oracle import gp_oracle as O
+    native.candidates_uniform = lambda seed, base, mm, lo, hi, device=None: torch.from_numpy(
+        O.candidates_uniform(seed, base, mm, lo, hi))
+    x, val = sharded_argmin(FakeAcquisition(), 42, [0.0, 0.0], [1.0, 1.0], m)
+    nan_case = all_reduce_minloc(float("nan") if rank == 1 else -5.0, 10 + rank)
+    tie_case = all_reduce_minloc(1.25, 100 - rank)
+    if rank == 0:
+        out.put((x.tolist(), val, nan_case, tie_case))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("m", [1, 1001])
+def test_sharded_argmin_over_gloo_matches_single_process(m):
+    from oracle import gp_oracle as O
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = 29500 + (os.getpid() + m) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, m, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    x, val, nan_case, tie_case = out.get()
+    xs = O.candidates_uniform(42, 0, m, [0.0, 0.0], [1.0, 1.0])
+    v = np.abs(xs - 0.3).sum(1)
+    assert x == xs[int(np.argmin(v))].tolist() and val == float(v.min())
+    assert np.isnan(nan_case[0]) and nan_case[1] == 11          # a NaN beats every number
+    assert tie_case == (1.25, 99)                                # equal values: lowest global index wins

@@ -1,0 +1,230 @@
+"""The reference's API-conformance tests (tests/test_surrogate.py, test_acquisiton.py, test_optimizer.py,
+test_bayes_opt.py, test_callback.py of /root/reference) restated against bopy_b200 on the GPU, plus numeric
+parity of the public API against the oracle.  -m gpu."""
+import numpy as np
+import pytest
+from sklearn.gaussian_process import GaussianProcessRegressor
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern
+
+from bopy_b200.acquisition import EI, LCB, POI, KriggingBeliever, OneShotBatchAcquisitionFunction
+from bopy_b200.bayes_opt import BayesOpt
+from bopy_b200.benchmark_functions import forrester
+from bopy_b200.bounds import Bound, Bounds
+from bopy_b200.callback import Callback
+from bopy_b200.initial_design import UniformRandomInitialDesign
+from bopy_b200.optimizer import (CandidateSweepOptimizer, DirectOptimizer, OneShotBatchOptimizer,
+                                 OneShotBatchOptimizerRandomSamplingStrategy, OptimizationResult,
+                                 SequentialBatchOptimizer)
+from bopy_b200.surrogate import ScipyGPSurrogate, Surrogate
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+n_samples = 10
+
+
+@pytest.fixture(scope="module")
+def x():
+    return np.linspace(0, 1, n_samples).reshape(-1, 1)
+
+
+@pytest.fixture(scope="module")
+def y(x):
+    return forrester(x)
+
+
+@pytest.fixture(scope="module")
+def trained_surrogate(x, y):
+    s = ScipyGPSurrogate(gp=GaussianProcessRegressor(kernel=Matern(nu=1.5), alpha=1e-5, normalize_y=True))
+    s.fit(x, y)
+    return s
+
+
+class TestSurrogateAfterFitting:
+    def test_shapes_and_references(self, trained_surrogate, x, y):
+        mean, cov = trained_surrogate.predict(x)
+        assert mean.shape == (n_samples,) and cov.shape == (n_samples, n_samples)
+        assert isinstance(mean, np.ndarray) and isinstance(cov, np.ndarray)
+        assert trained_surrogate.x is x and trained_surrogate.y is y
+
+    def test_predict_matches_sklearn(self, trained_surrogate):
+        grid = np.linspace(0, 1, 200).reshape(-1, 1)
+        mean, cov = trained_surrogate.predict(grid)
+        r_mean, r_cov = trained_surrogate.gp.predict(grid, return_cov=True)
+        scale = float(np.ravel(trained_surrogate.gp._y_train_std)[0])
+        np.testing.assert_allclose(mean, r_mean, rtol=1e-9, atol=1e-9 * scale)
+        np.testing.assert_allclose(cov, r_cov, rtol=1e-9, atol=1e-11 * scale ** 2)
+        d_mean, d_var = trained_surrogate.predict_diag(grid)
+        np.testing.assert_allclose(d_var, np.diag(r_cov), rtol=1e-9, atol=1e-11 * scale ** 2)
+        assert np.array_equal(d_mean, mean)
+
+    def test_validation_after_fit(self, trained_surrogate):
+        with pytest.raises(ValueError, match="`x` must contain at least one sample"):
+            trained_surrogate.predict(x=np.array([]))
+        with pytest.raises(ValueError, match="`x` must be 2D"):
+            trained_surrogate.predict(x=np.array([1.0]))
+        with pytest.raises(ValueError, match="`x` must have the same number of dimensions as the training data"):
+            trained_surrogate.predict(x=np.array([[1.0, 1.0]]))
+
+    def test_refit_with_more_data_rebuilds_the_device_state(self, x, y):
+        s = ScipyGPSurrogate(gp=GaussianProcessRegressor(kernel=ConstantKernel(1.0) * RBF(0.2), alpha=1e-8,
+                                                         normalize_y=True, optimizer=None))
+        s.fit(x[:6], y[:6])
+        m6, _ = s.predict(x)
+        s.fit(x, y)
+        m10, _ = s.predict(x)
+        np.testing.assert_allclose(m10, s.gp.predict(x), rtol=1e-9, atol=1e-9)
+        assert not np.allclose(m6, m10)
+
+
+@pytest.fixture(scope="module", params=[LCB, EI, POI], ids=["LCB", "EI", "POI"])
+def trained_acquisition(request):
+    xx = np.linspace(-np.pi, np.pi, n_samples).reshape(-1, 1)
+    yy = np.sin(xx).flatten()
+    s = ScipyGPSurrogate(gp=GaussianProcessRegressor(kernel=Matern()))
+    s.fit(xx, yy)
+    a = request.param(surrogate=s)
+    a.fit(xx, yy)
+    return a, xx, yy
+
+
+class TestAcquisition:
+    def test_output_dimensions(self, trained_acquisition):
+        a, xx, _ = trained_acquisition
+        out = a(xx)
+        assert out.shape == (n_samples,) and isinstance(out, np.ndarray)
+
+    def test_values_match_the_reference_formulas(self, trained_acquisition):
+        a, xx, yy = trained_acquisition
+        grid = np.linspace(-np.pi, np.pi, 501).reshape(-1, 1)
+        got = a(grid)
+        st = O.state_from_sklearn(a.surrogate.gp)
+        mean, var = O.posterior_diag(st, grid)
+        ref = O.acquisition(a.kind, mean, var, eta=float(np.min(yy)), kappa=2.0)
+        resolved = var > 1e-7
+        np.testing.assert_allclose(got[resolved], ref[resolved], rtol=1e-6, atol=1e-9)
+        idx, val = a.argmin(grid)
+        assert idx == int(np.argmin(got)) and val == got[idx]
+
+    def test_foreign_surrogate_uses_the_device_epilogue(self, trained_acquisition):
+        a, xx, yy = trained_acquisition
+
+        class HostSurrogate(Surrogate):
+            def __init__(self, gp):
+                super().__init__()
+                self.gp = gp
+
+            def _fit(self, x, y):
+                pass
+
+            def _predict(self, x):
+                return self.gp.predict(x, return_cov=True)
+
+        host = HostSurrogate(a.surrogate.gp)
+        host.fit(xx, yy)
+        b = type(a)(host)
+        b.fit(xx, yy)
+        grid = np.linspace(-np.pi, np.pi, 97).reshape(-1, 1)
+        got, want = b(grid), a(grid)
+        mean, cov = host.predict(grid)
+        resolved = np.diag(cov) > 1e-7
+        np.testing.assert_allclose(got[resolved], want[resolved], rtol=1e-6, atol=1e-9)
+        assert b.argmin(grid)[0] == int(np.argmin(got))
+
+
+def forrester_setup(surrogate_dtype="f64"):
+    bounds = Bounds(bounds=[Bound(lower=0.0, upper=1.0)])
+    sur = ScipyGPSurrogate(gp=GaussianProcessRegressor(kernel=ConstantKernel(1.0) * RBF(0.2), alpha=1e-8,
+                                                       normalize_y=True, optimizer=None), dtype=surrogate_dtype)
+    return bounds, sur
+
+
+class TestOptimizers:
+    @pytest.fixture(scope="class")
+    def fitted(self):
+        bounds, sur = forrester_setup()
+        xx = np.linspace(0, 1, 8).reshape(-1, 1)
+        yy = forrester(xx)
+        sur.fit(xx, yy)
+        acq = LCB(sur, kappa=2.0)
+        acq.fit(xx, yy)
+        return bounds, sur, acq, xx, yy
+
+    def test_candidate_sweep_optimizer(self, fitted):
+        bounds, sur, acq, _, _ = fitted
+        res = CandidateSweepOptimizer(acq, bounds, n_candidates=1 << 16, seed=3).optimize()
+        assert isinstance(res, OptimizationResult)
+        assert isinstance(res.x_min, np.ndarray) and res.x_min.shape == (1, 1)
+        assert isinstance(res.f_min, np.ndarray) and res.f_min.shape == (1,)
+        grid = np.linspace(0, 1, 20001).reshape(-1, 1)
+        truth = acq(grid)
+        assert res.f_min[0] <= truth.min() + 1e-3 * np.ptp(truth)
+        assert abs(acq(res.x_min)[0] - res.f_min[0]) <= 1e-12 * max(1.0, abs(res.f_min[0]))
+        zoomed = CandidateSweepOptimizer(acq, bounds, n_candidates=1 << 12, zoom_rounds=3, seed=3).optimize()
+        coarse = CandidateSweepOptimizer(acq, bounds, n_candidates=1 << 12, seed=3).optimize()
+        assert zoomed.f_min[0] <= coarse.f_min[0]
+        assert zoomed.f_min[0] <= truth.min() + 1e-6 * np.ptp(truth)
+
+    def test_direct_optimizer(self, fitted):
+        bounds, sur, acq, _, _ = fitted
+        res = DirectOptimizer(acq, bounds, maxf=100).optimize()
+        assert res.x_min.shape == (1, 1) and res.f_min.shape == (1,)
+        assert 0.0 <= res.x_min[0, 0] <= 1.0
+
+    def test_sequential_batch_with_kriging_believer(self, fitted):
+        bounds, sur, _, xx, yy = fitted
+        kb = KriggingBeliever(LCB(sur))
+        kb.fit(xx, yy)
+        base = CandidateSweepOptimizer(kb, bounds, n_candidates=1 << 12)
+        res = SequentialBatchOptimizer(kb, bounds, base_optimizer=base, batch_size=2).optimize()
+        assert res.x_min.shape == (2, 1) and res.f_min.shape == (2,)
+        assert len(sur.x) == len(xx)
+        assert abs(res.x_min[0, 0] - res.x_min[1, 0]) > 1e-6      # the believer moved the second pick
+
+    def test_one_shot_batch(self, fitted):
+        bounds, sur, _, xx, yy = fitted
+        acq = OneShotBatchAcquisitionFunction(LCB(sur))
+        acq.fit(xx, yy)
+        res = OneShotBatchOptimizer(acq, bounds, base_optimizer=DirectOptimizer(acq, bounds, maxf=100), batch_size=2,
+                                    strategy=OneShotBatchOptimizerRandomSamplingStrategy()).optimize()
+        assert res.x_min.shape == (2, 1) and res.f_min.shape == (2,)
+
+
+class Recorder(Callback):
+    def __init__(self):
+        self.events = []
+
+    def on_initial_design_end(self, bo):
+        self.events.append("on_initial_design_end")
+
+    def on_acquisition_optimized(self, bo, opt_result):
+        assert isinstance(opt_result, OptimizationResult)
+        self.events.append("on_acquisition_optimized")
+
+    def on_surrogate_updated(self, bo):
+        self.events.append("on_surrogate_updated")
+
+    def on_acquisition_updated(self, bo):
+        self.events.append("on_acquisition_updated")
+
+    def on_trial_end(self, bo):
+        self.events.append("on_trial_end")
+
+    def on_bo_end(self, bo):
+        self.events.append("on_bo_end")
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_bayes_opt_finds_the_forrester_minimum(dtype):
+    np.random.seed(0)
+    bounds, sur = forrester_setup(dtype)
+    acq = LCB(sur, kappa=2.0)
+    rec = Recorder()
+    bo = BayesOpt(objective_function=forrester, surrogate=sur, acquisition_function=acq,
+                  optimizer=CandidateSweepOptimizer(acq, bounds, n_candidates=1 << 14, zoom_rounds=2, seed=1),
+                  initial_design=UniformRandomInitialDesign(), bounds=bounds, callbacks=[rec])
+    res = bo.run(n_trials=12, n_initial_design=5)
+    assert res.x_opt.shape == (1, 1) and len(res.trial_results) == 12
+    assert res.f_opt < -5.9 and abs(res.x_opt[0, 0] - 0.757249) < 0.02       # global minimum -6.0207 at 0.7572
+    assert rec.events[0] == "on_initial_design_end" and rec.events[-1] == "on_bo_end"
+    assert rec.events.count("on_trial_end") == 12 and rec.events.count("on_acquisition_optimized") == 12
