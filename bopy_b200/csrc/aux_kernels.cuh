@@ -27,11 +27,13 @@ __global__ void dinv_kernel(const double* __restrict__ L, int n, double* Dinv) {
     }
 }
 
-// Operand tile (I, Jc): [k][row] = -L[I*BM+row][Jc*KC+k] below the diagonal block, Dinv[I][row][.] on it.
-template <typename T>
-__global__ void pack_tiles_kernel(const double* __restrict__ L, int n, const double* __restrict__ Dinv, T* out) {
-    using G = Geo<T>;
-    constexpr int KC = G::KC, CH = G::CH, TE = TILE_BYTES / sizeof(T);
+// Operand tile (I, Jc): logical [k][row] = -L[I*BM+row][Jc*KC+k] below the diagonal block, Dinv[I][row][.] on it;
+// stored at the policy's physical index (XOR-swizzled for the DMMA engine).
+template <class P>
+__global__ void pack_tiles_kernel(const double* __restrict__ L, int n, const double* __restrict__ Dinv,
+                                  typename P::Elem* out) {
+    using T = typename P::Elem;
+    constexpr int KC = P::KC, CH = P::CH, TE = TILE_BYTES / sizeof(T);
     const int I = blockIdx.y, Jc = blockIdx.x;
     if (Jc >= (I + 1) * CH) return;
     __shared__ double tmp[KC][BM + 1];
@@ -48,7 +50,7 @@ __global__ void pack_tiles_kernel(const double* __restrict__ L, int n, const dou
     T* dst = out + ((size_t)CH * I * (I + 1) / 2 + Jc) * TE;
     for (int e = threadIdx.x; e < BM * KC; e += blockDim.x) {
         const int k = e / BM, r = e - k * BM;
-        dst[e] = static_cast<T>(tmp[k][r]);
+        dst[P::a_index(k, r)] = static_cast<T>(tmp[k][r]);
     }
 }
 
@@ -66,16 +68,18 @@ __global__ void pack_x_kernel(const double* __restrict__ X, const double* __rest
 }
 
 // cov[a][b] = (k(x_a, x_b) - sum_i V[i,a] V[i,b]) * y_std^2   ($SK/_gpr.py:466-469); V in the sweep's tile layout
-template <typename T, int KIND>
-__global__ void cov_kernel(const T* __restrict__ Vws, int n_pad, int n, const double* __restrict__ Xs, long long m,
-                           int d, LsParam ls, double amp, double kss, double y_var, double* cov) {
+template <class P, int KIND>
+__global__ void cov_kernel(const typename P::Elem* __restrict__ Vws, int n_pad, int n, const double* __restrict__ Xs,
+                           long long m, int d, LsParam ls, double amp, double kss, double y_var, double* cov) {
+    using T = typename P::Elem;
     const long long a = (long long)blockIdx.y * blockDim.y + threadIdx.y;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= m || b >= m) return;
-    const T* Va = Vws + (a / BN) * (long long)n_pad * BN + (a % BN);
-    const T* Vb = Vws + (b / BN) * (long long)n_pad * BN + (b % BN);
+    const T* Va = Vws + (a / BN) * (long long)n_pad * BN;
+    const T* Vb = Vws + (b / BN) * (long long)n_pad * BN;
+    const int ca = (int)(a % BN), cb = (int)(b % BN);
     double s = 0.0;
-    for (int i = 0; i < n; ++i) s = fma((double)Va[(size_t)i * BN], (double)Vb[(size_t)i * BN], s);
+    for (int i = 0; i < n; ++i) s = fma((double)Va[P::b_index(i, ca)], (double)Vb[P::b_index(i, cb)], s);
     double prior = kss;
     if (a != b) {
         double d2 = 0.0;

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -54,6 +55,7 @@ struct bopy_gp {
     double ls[MAX_D];
     double amp = 1.0, noise = 0.0, y_mean = 0.0, y_std = 1.0;
     bool ready = false;
+    bool fma64 = false;        // fp64 solve with the register-tiled FMA engine instead of DMMA (BOPY_B200_F64_ENGINE=fma)
 };
 
 namespace {
@@ -63,45 +65,52 @@ long long packed_tiles(const bopy_gp* gp) {
     return ch * gp->n_blocks * (gp->n_blocks + 1) / 2;
 }
 
-template <typename T, int KIND> int launch_sweep_t(const SweepParams& p, int grid, cudaStream_t st) {
-    const size_t smem = sweep_smem_bytes<T>(p.d);
-    CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<T, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sweep_kernel<T, KIND><<<grid, NT, smem, st>>>(p);
+template <class P, int KIND> int launch_sweep_t(const SweepParams& p, int grid, cudaStream_t st) {
+    const size_t smem = sweep_smem_bytes<P>(p.d);
+    CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<P, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sweep_kernel<P, KIND><<<grid, NT_ALL, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     return BOPY_OK;
 }
 
-template <typename T> int launch_sweep_k(int kernel, const SweepParams& p, int grid, cudaStream_t st) {
+template <class P> int launch_sweep_k(int kernel, const SweepParams& p, int grid, cudaStream_t st) {
     switch (kernel) {
-        case BOPY_KERNEL_RBF: return launch_sweep_t<T, K_RBF>(p, grid, st);
-        case BOPY_KERNEL_MATERN12: return launch_sweep_t<T, K_M12>(p, grid, st);
-        case BOPY_KERNEL_MATERN32: return launch_sweep_t<T, K_M32>(p, grid, st);
-        case BOPY_KERNEL_MATERN52: return launch_sweep_t<T, K_M52>(p, grid, st);
+        case BOPY_KERNEL_RBF: return launch_sweep_t<P, K_RBF>(p, grid, st);
+        case BOPY_KERNEL_MATERN12: return launch_sweep_t<P, K_M12>(p, grid, st);
+        case BOPY_KERNEL_MATERN32: return launch_sweep_t<P, K_M32>(p, grid, st);
+        case BOPY_KERNEL_MATERN52: return launch_sweep_t<P, K_M52>(p, grid, st);
     }
     return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
 }
 
-template <typename T> int launch_cov_k(const bopy_gp* gp, const void* Vws, const double* Xs, long long m,
-                                       const LsParam& ls, double* cov, cudaStream_t st) {
+template <class P> int launch_cov_k(const bopy_gp* gp, const void* Vws, const double* Xs, long long m,
+                                    const LsParam& ls, double* cov, cudaStream_t st) {
     dim3 block(16, 16), grid((unsigned)((m + 15) / 16), (unsigned)((m + 15) / 16));
     const double kss = gp->amp + gp->noise, yv = gp->y_std * gp->y_std;
-    const T* V = reinterpret_cast<const T*>(Vws);
+    const typename P::Elem* V = reinterpret_cast<const typename P::Elem*>(Vws);
     switch (gp->kernel) {
         case BOPY_KERNEL_RBF:
-            cov_kernel<T, K_RBF><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
+            cov_kernel<P, K_RBF><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
             break;
         case BOPY_KERNEL_MATERN12:
-            cov_kernel<T, K_M12><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
+            cov_kernel<P, K_M12><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
             break;
         case BOPY_KERNEL_MATERN32:
-            cov_kernel<T, K_M32><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
+            cov_kernel<P, K_M32><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
             break;
         default:
-            cov_kernel<T, K_M52><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
+            cov_kernel<P, K_M52><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
             break;
     }
     CUDA_TRY(cudaGetLastError());
     return BOPY_OK;
+}
+
+// engine selection: fp64 -> DMMA warp tiles (or FMA thread tiles on request), fp32 -> FMA thread tiles
+template <class F> int dispatch_engine(const bopy_gp* gp, F&& f) {
+    if (gp->dtype == BOPY_F32) return f(FmaPolicy<float>(0));
+    if (gp->fma64) return f(FmaPolicy<double>(0));
+    return f(DmmaPolicy(0));
 }
 
 int check_ready(const bopy_gp* gp) {
@@ -142,8 +151,7 @@ int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, d
     const bool want_min = (min_val != nullptr || min_idx != nullptr);
     p.partials = want_min ? gp->partials : nullptr;
     const int grid = (int)std::min<long long>(p.ntiles, gp->sm_count);
-    int rc = gp->dtype == BOPY_F64 ? launch_sweep_k<double>(gp->kernel, p, grid, st)
-                                   : launch_sweep_k<float>(gp->kernel, p, grid, st);
+    int rc = dispatch_engine(gp, [&](auto pol) { return launch_sweep_k<decltype(pol)>(gp->kernel, p, grid, st); });
     if (rc != BOPY_OK) return rc;
     if (want_min) {
         minloc_finalize_kernel<<<1, 256, 0, st>>>(gp->partials, grid, min_val, min_idx);
@@ -188,6 +196,8 @@ int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, 
     gp->n_blocks = (int)((n + BM - 1) / BM);
     gp->n_pad = gp->n_blocks * BM;
     gp->sm_count = prop.multiProcessorCount;
+    const char* engine = std::getenv("BOPY_B200_F64_ENGINE");
+    gp->fma64 = engine != nullptr && std::strcmp(engine, "fma") == 0;
     const size_t es = elem_size(dtype);
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&gp->Lt, (size_t)packed_tiles(gp) * TILE_BYTES);
@@ -241,13 +251,12 @@ int bopy_gp_set_state(bopy_gp* gp, const double* X_dev, const double* L_dev, con
     const int n = (int)gp->n;
     dinv_kernel<<<gp->n_blocks, BM, 0, st>>>(L_dev, n, gp->Dinv);
     CUDA_TRY(cudaGetLastError());
-    if (gp->dtype == BOPY_F64) {
-        dim3 grid(gp->n_blocks * Geo<double>::CH, gp->n_blocks);
-        pack_tiles_kernel<double><<<grid, 256, 0, st>>>(L_dev, n, gp->Dinv, reinterpret_cast<double*>(gp->Lt));
-    } else {
-        dim3 grid(gp->n_blocks * Geo<float>::CH, gp->n_blocks);
-        pack_tiles_kernel<float><<<grid, 256, 0, st>>>(L_dev, n, gp->Dinv, reinterpret_cast<float*>(gp->Lt));
-    }
+    dispatch_engine(gp, [&](auto pol) {
+        using P = decltype(pol);
+        dim3 grid(gp->n_blocks * P::CH, gp->n_blocks);
+        pack_tiles_kernel<P><<<grid, 256, 0, st>>>(L_dev, n, gp->Dinv, reinterpret_cast<typename P::Elem*>(gp->Lt));
+        return BOPY_OK;
+    });
     CUDA_TRY(cudaGetLastError());
     pack_x_kernel<<<gp->n_blocks, BM, 0, st>>>(X_dev, alpha_dev, n, gp->d, ls, gp->Xt);
     CUDA_TRY(cudaGetLastError());
@@ -318,8 +327,7 @@ int bopy_gp_predict_cov(bopy_gp* gp, const double* Xs_dev, int64_t m, double* me
     if (rc == BOPY_OK) {
         LsParam ls;
         for (int q = 0; q < MAX_D; ++q) ls.v[q] = q < gp->d ? gp->ls[q] : 1.0;
-        rc = gp->dtype == BOPY_F64 ? launch_cov_k<double>(gp, Vall, Xs_dev, m, ls, cov_out, st)
-                                   : launch_cov_k<float>(gp, Vall, Xs_dev, m, ls, cov_out, st);
+        rc = dispatch_engine(gp, [&](auto pol) { return launch_cov_k<decltype(pol)>(gp, Vall, Xs_dev, m, ls, cov_out, st); });
     }
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(Vall);

@@ -10,11 +10,16 @@
 //   argmin  = np.argmin rules                     bopy/optimizer.py:99-107
 //
 // One CTA owns a tile of BN = 128 candidates and walks the n/128 block rows of L in order:
-//   R_I = K*_I - sum_{J<I} L_IJ V_J     register-tiled FMA GEMM, operands streamed by bulk async copies
+//   R_I = K*_I - sum_{J<I} L_IJ V_J     GEMM, operands streamed by bulk async copies (TMA)
 //   V_I = inv(L_II) R_I                 second GEMM against the pre-inverted 128x128 diagonal block
-// L is stored pre-tiled ([k][row] tiles of 8 KB, off-diagonal tiles negated, diagonal blocks inverted) so
-// that every operand tile is ONE contiguous cp.async.bulk (TMA) transfer; V_J tiles live in an L2-resident
-// per-CTA workspace in the same tile layout.
+// L is stored pre-tiled (8 KB [k][row] tiles, off-diagonal tiles negated, diagonal blocks inverted) so that
+// every operand tile is ONE contiguous cp.async.bulk transfer; V_J tiles live in a per-CTA workspace in the
+// same tile layout.  Warp roles: warps 0-7 compute (setmaxnreg 232), warp 8 (one lane, setmaxnreg 40) is the TMA producer running ahead
+// through a 4-stage mbarrier ring, across block-row boundaries.
+//
+// Two inner-product engines ("policies"):
+//   DmmaPolicy      fp64, mma.sync.m8n8k4.f64 (DMMA), warp tile 32 rows x 64 candidates, XOR-swizzled tiles
+//   FmaPolicy<T>    register-tiled FMA, thread tile 8 x 8 (used for the fp32 solve)
 #pragma once
 #include "common.cuh"
 
@@ -23,10 +28,13 @@ namespace bopy {
 enum { K_RBF = 0, K_M12 = 1, K_M32 = 2, K_M52 = 3 };
 enum { A_NONE = -1, A_LCB = 0, A_EI = 1, A_POI = 2 };
 
+constexpr int NT_ALL = NT + 128;  // 8 compute warps + one producer warpgroup (register budgets are per 4 warps)
+constexpr int REGS_COMPUTE = 232, REGS_PRODUCER = 40;  // setmaxnreg: 8*32*232 + 4*32*40 <= 65536
+
 struct SweepParams {
-    const void* Lt;     // packed factor tiles, tile (I, Jc) at ((CH*I*(I+1)/2 + Jc) * KC*BM), layout [k][row]
+    const void* Lt;     // packed factor tiles, tile (I, Jc) at ((CH*I*(I+1)/2 + Jc) * tile elements)
     const double* Xt;   // [n_blocks][d+1][BM]: X/l (dimension-major) then alpha, zero padded
-    void* Vws;          // [slots][n_pad][BN] solve workspace
+    void* Vws;          // [slots][n_pad][BN] solve workspace (policy tile layout)
     const double* Xs;   // candidates (m, d) row-major
     long long m, ntiles;
     int n, n_blocks, d;
@@ -87,37 +95,130 @@ __device__ __forceinline__ float4 pack_vec(const float* r) { return make_float4(
 __device__ __forceinline__ void unpack_vec(double* r, const double2& v) { r[0] = v.x; r[1] = v.y; }
 __device__ __forceinline__ void unpack_vec(float* r, const float4& v) { r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w; }
 
-// acc[8][8] += A[k][rows] (x) B[k][cands] over one tile of KC contraction steps
-template <typename T>
-__device__ __forceinline__ void mma_chunk(T (&acc)[8][8], const T* __restrict__ As, const T* __restrict__ Bs,
-                                          int ty, int tx) {
-    using G = Geo<T>;
-    using V = typename VecOf<T>::type;
-    constexpr int VEC = G::VEC, KC = G::KC, NV = 8 / VEC;
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        T a[8], b[8];
-#pragma unroll
-        for (int g = 0; g < NV; ++g) {
-            unpack_vec(&a[g * VEC], *reinterpret_cast<const V*>(&As[k * BM + ty * VEC + g * 16 * VEC]));
-            unpack_vec(&b[g * VEC], *reinterpret_cast<const V*>(&Bs[k * BN + tx * VEC + g * 16 * VEC]));
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+// ---------------------------------------------------------------------------------------------------------
+// Policies: who owns which accumulator element, how operand tiles are laid out, how one tile is multiplied.
+// A tile: logical [k][row] (k < KC, row < 128); B tile: logical [k][cand].  a_index / b_index give the
+// physical element offset inside the 8 KB tile (and inside the [128][128] residual / workspace block rows).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T> struct FmaPolicy {
+    using Elem = T;
+    static constexpr int VEC = Geo<T>::VEC, KC = Geo<T>::KC, CH = Geo<T>::CH;
+    static constexpr int RI = 8, CJ = 8, CV = VEC;   // rows x candidates per thread, candidates per vector store
+    static constexpr bool kSwizzled = false;
+    int ty, tx, part;
+    bool leader;
+    __device__ explicit FmaPolicy(int tid) {
+        const int lane = tid & 31, warp = tid >> 5;
+        part = warp >> 1;
+        ty = part * 4 + (lane >> 3);
+        tx = (warp & 1) * 8 + (lane & 7);
+        leader = (lane >> 3) == 0;
     }
+    __device__ __forceinline__ int row_of(int i) const { return ty * VEC + (i / VEC) * (16 * VEC) + (i % VEC); }
+    __device__ __forceinline__ int cand_of(int j) const { return tx * VEC + (j / VEC) * (16 * VEC) + (j % VEC); }
+    __host__ __device__ static __forceinline__ int a_index(int k, int r) { return k * BM + r; }
+    __host__ __device__ static __forceinline__ int b_index(int k, int c) { return k * BN + c; }
+    // sum over the lanes that hold the same candidates but different rows
+    __device__ __forceinline__ double reduce_rows(double v) const {
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        return v;
+    }
+    // acc += A (x) B over one tile; DIAG marks tile kc of the diagonal GEMM (dense here)
+    template <bool DIAG>
+    __device__ __forceinline__ void mma_tile(T (&acc)[RI][CJ], const T* __restrict__ As, const T* __restrict__ Bs,
+                                             int /*kc*/) const {
+        using V = typename VecOf<T>::type;
+        constexpr int NV = 8 / VEC;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            T a[8], b[8];
+#pragma unroll
+            for (int g = 0; g < NV; ++g) {
+                unpack_vec(&a[g * VEC], *reinterpret_cast<const V*>(&As[k * BM + ty * VEC + g * 16 * VEC]));
+                unpack_vec(&b[g * VEC], *reinterpret_cast<const V*>(&Bs[k * BN + tx * VEC + g * 16 * VEC]));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+    }
+};
+
+// fp64 tensor-shaped MMA: D(8x8) += A(8x4) * B(4x8); a = A[lane/4][lane%4], b = B[lane%4][lane/4],
+// c0/c1 = C[lane/4][2*(lane%4) + 0/1]
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
 }
 
-template <typename T> constexpr size_t sweep_smem_bytes(int d) {
-    return (size_t)2 * STAGES * TILE_BYTES + (size_t)BM * BN * sizeof(T) + (size_t)d * BN * sizeof(double) + 128;
+struct DmmaPolicy {
+    using Elem = double;
+    static constexpr int VEC = 2, KC = 8, CH = 16;
+    static constexpr int RI = 4, CJ = 16, CV = 2;
+    static constexpr bool kSwizzled = true;
+    int lane, rg, cg, part;
+    int aoff[RI], boff[CJ / 2];   // fragment element offsets inside a tile for k = lane%4 (k+4: add 4*128)
+    bool leader;
+    __device__ explicit DmmaPolicy(int tid) {
+        lane = tid & 31;
+        const int warp = tid >> 5;
+        rg = warp >> 1;   // row atoms rg, rg+4, rg+8, rg+12 (8 rows each): balanced triangular work
+        cg = warp & 1;    // candidates 64*cg .. 64*cg+63
+        part = rg;
+        leader = (lane >> 2) == 0;
+        const int kq = lane & 3, q8 = lane >> 2;
+#pragma unroll
+        for (int i = 0; i < RI; ++i) aoff[i] = a_index(kq, 8 * (rg + 4 * i) + q8);
+#pragma unroll
+        for (int jj = 0; jj < CJ / 2; ++jj) boff[jj] = b_index(kq, 64 * cg + 8 * jj + q8);
+    }
+    __device__ __forceinline__ int row_of(int i) const { return 8 * (rg + 4 * i) + (lane >> 2); }
+    __device__ __forceinline__ int cand_of(int j) const { return 64 * cg + 8 * (j >> 1) + 2 * (lane & 3) + (j & 1); }
+    // XOR swizzle on the 128-wide axis keyed by k%4: the 4 x 8 fragment gather of a half-warp hits 32 banks
+    __host__ __device__ static __forceinline__ int a_index(int k, int r) { return k * BM + (r ^ (4 * (k & 3))); }
+    __host__ __device__ static __forceinline__ int b_index(int k, int c) { return k * BN + (c ^ (4 * (k & 3))); }
+    __device__ __forceinline__ double reduce_rows(double v) const {
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        return v;
+    }
+    // DIAG: inv(L_II) is lower triangular, so row atom (rg+4i) only needs the k tiles kc <= its own index
+    template <bool DIAG>
+    __device__ __forceinline__ void mma_tile(double (&acc)[RI][CJ], const double* __restrict__ As,
+                                             const double* __restrict__ Bs, int kc) const {
+#pragma unroll
+        for (int s = 0; s < KC / 4; ++s) {
+            double a[RI], b[CJ / 2];
+#pragma unroll
+            for (int jj = 0; jj < CJ / 2; ++jj) b[jj] = Bs[boff[jj] + s * 4 * BN];
+#pragma unroll
+            for (int i = 0; i < RI; ++i) a[i] = As[aoff[i] + s * 4 * BM];
+#pragma unroll
+            for (int i = 0; i < RI; ++i) {
+                if (DIAG && rg + 4 * i < kc) continue;   // warp-uniform
+#pragma unroll
+                for (int jj = 0; jj < CJ / 2; ++jj) dmma_m8n8k4(acc[i][2 * jj], acc[i][2 * jj + 1], a[i], b[jj]);
+            }
+        }
+    }
+};
+
+template <class P> constexpr size_t sweep_smem_bytes(int d) {
+    return (size_t)2 * STAGES * TILE_BYTES + (size_t)BM * BN * sizeof(typename P::Elem) +
+           (size_t)d * BN * sizeof(double) + 192;
 }
 
-template <typename T, int KIND>
-__global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
-    using G = Geo<T>;
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+
+template <class P, int KIND>
+__global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
+    using T = typename P::Elem;
     using V = typename VecOf<T>::type;
-    constexpr int VEC = G::VEC, KC = G::KC, CH = G::CH, NV = 8 / VEC;
+    constexpr int KC = P::KC, CH = P::CH, RI = P::RI, CJ = P::CJ, CV = P::CV;
     constexpr int TE = TILE_BYTES / sizeof(T);  // elements per operand tile
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -130,24 +231,67 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
     double* const partS = reinterpret_cast<double*>(rs_raw + 52 * 1024);  // aliases Rs: [4][BN]
     double* const xs_s = reinterpret_cast<double*>(rs_raw + (size_t)BM * BN * sizeof(T));  // [d][BN] candidates / l
     unsigned char* const tail = reinterpret_cast<unsigned char*>(xs_s + (size_t)p.d * BN);
-    uint64_t* const full = reinterpret_cast<uint64_t*>(tail);           // [STAGES]
-    uint64_t* const xbar = full + STAGES;
-    MinLoc* const red = reinterpret_cast<MinLoc*>(tail + 64);           // [4]
+    uint64_t* const full = reinterpret_cast<uint64_t*>(tail);           // [STAGES] producer -> consumers
+    uint64_t* const empty = full + STAGES;                              // [STAGES] consumers -> producer
+    uint64_t* const xbar = empty + STAGES;                              // block row of X/l + alpha landed
+    uint64_t* const vbar = xbar + 1;                                    // V_I published to the workspace
+    MinLoc* const red = reinterpret_cast<MinLoc*>(tail + 128);          // [4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wy = warp >> 1;
-    const int ty = wy * 4 + (lane >> 3);
-    const int tx = (warp & 1) * 8 + (lane & 7);
     const int n_pad = p.n_blocks * BM;
     const T* const Lt = reinterpret_cast<const T*>(p.Lt);
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NT / 32);
+        }
         mbar_init(xbar, 1);
+        mbar_init(vbar, 1);
         fence_mbar_init();
     }
     __syncthreads();
 
+    if (warp >= NT / 32) {
+        // =============================== TMA producer (one lane) =========================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+        if (warp != NT / 32 || lane != 0) return;
+        uint32_t g = 0, vphase = 0;
+        for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            const T* const Vt =
+                reinterpret_cast<const T*>(p.Vws) + (p.slot_per_tile ? tile : (long long)blockIdx.x) * n_pad * BN;
+            for (int I = 0; I < p.n_blocks; ++I) {
+                const int T_gemm = I * CH, T_all = T_gemm + CH;
+                const T* const a_row = Lt + (long long)CH * I * (I + 1) / 2 * TE;
+                for (int t = 0; t < T_all; ++t, ++g) {
+                    const uint32_t stage = g % STAGES;
+                    mbar_wait(&empty[stage], ((g / STAGES) & 1u) ^ 1u);
+                    if (t < T_gemm) {
+                        // J order: even rows 0..I-1, odd rows I-2..0 then I-1 (zig-zag: the V slices read last by one
+                        // block row are read first by the next, so they are still in L2; V_{I-1} always comes last)
+                        const int jpos = t / CH, c = t - jpos * CH;
+                        const int J = (I & 1) ? (jpos < I - 1 ? I - 2 - jpos : I - 1) : jpos;
+                        if (J == I - 1 && c == 0) {   // first touch of V_{I-1}: wait until the consumers published it
+                            mbar_wait(vbar, vphase);
+                            vphase ^= 1u;
+                        }
+                        const int tt = J * CH + c;
+                        mbar_arrive_expect_tx(&full[stage], 2 * TILE_BYTES);
+                        bulk_g2s(stA + stage * TE, a_row + (long long)tt * TE, TILE_BYTES, &full[stage]);
+                        bulk_g2s(stB + stage * TE, Vt + (long long)tt * TE, TILE_BYTES, &full[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&full[stage], TILE_BYTES);
+                        bulk_g2s(stA + stage * TE, a_row + (long long)t * TE, TILE_BYTES, &full[stage]);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================================== compute warps ==================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
+    const P pol(tid);
     uint32_t gcount = 0;   // operand tiles consumed so far (selects ring stage and barrier parity)
     uint32_t xphase = 0;
     MinLoc best;
@@ -163,18 +307,6 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             mbar_arrive_expect_tx(xbar, bytes);
             bulk_g2s(xrow, p.Xt + (long long)I * (p.d + 1) * BM, bytes, xbar);
         };
-        auto issue = [&](int I, int t, uint32_t gc) {
-            const uint32_t stage = gc % STAGES;
-            const T* a_src = Lt + ((long long)CH * I * (I + 1) / 2 + t) * TE;
-            if (t < I * CH) {
-                mbar_arrive_expect_tx(&full[stage], 2 * TILE_BYTES);
-                bulk_g2s(stA + stage * TE, a_src, TILE_BYTES, &full[stage]);
-                bulk_g2s(stB + stage * TE, Vt + (long long)t * TE, TILE_BYTES, &full[stage]);
-            } else {
-                mbar_arrive_expect_tx(&full[stage], TILE_BYTES);
-                bulk_g2s(stA + stage * TE, a_src, TILE_BYTES, &full[stage]);
-            }
-        };
 
         if (tid == 0) issue_xrow(0);
         // stage this tile's candidates, scaled like sklearn does (X / length_scale), dimension-major
@@ -185,126 +317,123 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
             xs_s[q * BN + c] = __ddiv_rn(v, p.ls[q]);
         }
         double mean_c = 0.0, ss_c = 0.0;  // per-candidate accumulators, threads 0..BN-1
-        __syncthreads();
+        consumer_sync();
 
         for (int I = 0; I < p.n_blocks; ++I) {
-            const int T_gemm = I * CH, T_all = T_gemm + CH;
-            if (tid == 0) {
-                const int pre = T_all < STAGES ? T_all : STAGES;
-                for (int t = 0; t < pre; ++t) issue(I, t, gcount + t);
-            }
+            const int T_gemm = I * CH;
 
             // ---- kernel tile K*[block row I, this tile's candidates] and its share of the mean --------
-            T acc[8][8];
+            T acc[RI][CJ];
             mbar_wait(xbar, xphase);
             xphase ^= 1;
             {
-                double d2[8][8];
+                double d2[RI][CJ];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < RI; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) d2[i][j] = 0.0;
+                    for (int j = 0; j < CJ; ++j) d2[i][j] = 0.0;
                 for (int q = 0; q < p.d; ++q) {
-                    double xr[8], xc[8];
+                    double xr[RI], xc[CJ];
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        xr[s] = xrow[q * BM + owned<T>(ty, s)];
-                        xc[s] = xs_s[q * BN + owned<T>(tx, s)];
-                    }
+                    for (int i = 0; i < RI; ++i) xr[i] = xrow[q * BM + pol.row_of(i)];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    for (int j = 0; j < CJ; ++j) xc[j] = xs_s[q * BN + pol.cand_of(j)];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                    for (int i = 0; i < RI; ++i)
+#pragma unroll
+                        for (int j = 0; j < CJ; ++j) {
                             const double df = __dadd_rn(xc[j], -xr[i]);
                             d2[i][j] = __dadd_rn(d2[i][j], __dmul_rn(df, df));  // cdist order, unfused
                         }
                 }
-                double mp[8];
+                double mp[CJ];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) mp[j] = 0.0;
+                for (int j = 0; j < CJ; ++j) mp[j] = 0.0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = owned<T>(ty, i);
+                for (int i = 0; i < RI; ++i) {
+                    const int row = pol.row_of(i);
                     const bool live = I * BM + row < p.n;
                     const double a_i = xrow[p.d * BM + row];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < CJ; ++j) {
                         const double kv = live ? __dmul_rn(p.amp, base_kernel<KIND>(d2[i][j])) : 0.0;
                         acc[i][j] = static_cast<T>(kv);
                         mp[j] = fma(kv, a_i, mp[j]);
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    mp[j] += __shfl_xor_sync(0xffffffffu, mp[j], 8);
-                    mp[j] += __shfl_xor_sync(0xffffffffu, mp[j], 16);
-                }
-                if ((lane >> 3) == 0) {
+                for (int j = 0; j < CJ; ++j) mp[j] = pol.reduce_rows(mp[j]);
+                if (pol.leader) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) partM[wy * BN + owned<T>(tx, j)] = mp[j];
+                    for (int j = 0; j < CJ; ++j) partM[pol.part * BN + pol.cand_of(j)] = mp[j];
                 }
             }
-            __syncthreads();
+            consumer_sync();
             if (tid < BN) mean_c += ((partM[tid] + partM[BN + tid]) + partM[2 * BN + tid]) + partM[3 * BN + tid];
-            __syncthreads();  // xrow / partM consumed: Rs may be overwritten from here on
+            consumer_sync();  // xrow / partM consumed: Rs may be overwritten from here on
 
             // ---- R_I = K*_I - sum_J L_IJ V_J, then V_I = inv(L_II) R_I ------------------------------------
-            for (int t = 0; t < T_all; ++t) {
-                if (t == T_gemm) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-#pragma unroll
-                        for (int g = 0; g < NV; ++g)
-                            *reinterpret_cast<V*>(&Rs[owned<T>(ty, i) * BN + tx * VEC + g * 16 * VEC]) =
-                                pack_vec(&acc[i][g * VEC]);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[i][j] = static_cast<T>(0);
-                    }
-                    __syncthreads();
-                }
+            for (int t = 0; t < T_gemm; ++t, ++gcount) {
                 const uint32_t stage = gcount % STAGES;
                 mbar_wait(&full[stage], (gcount / STAGES) & 1u);
-                const T* Bs = t < T_gemm ? stB + stage * TE : Rs + (t - T_gemm) * KC * BN;
-                mma_chunk<T>(acc, stA + stage * TE, Bs, ty, tx);
-                __syncthreads();  // every warp is done with this stage (and with this slice of Rs)
-                if (tid == 0 && t + STAGES < T_all) issue(I, t + STAGES, gcount + STAGES);
-                ++gcount;
+                pol.template mma_tile<false>(acc, stA + stage * TE, stB + stage * TE, -1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage
+            }
+            // the residual tile becomes the B operand of the diagonal GEMM
+#pragma unroll
+            for (int i = 0; i < RI; ++i) {
+                const int row = pol.row_of(i);
+#pragma unroll
+                for (int jv = 0; jv < CJ / CV; ++jv)
+                    *reinterpret_cast<V*>(&Rs[P::b_index(row, pol.cand_of(jv * CV))]) = pack_vec(&acc[i][jv * CV]);
+#pragma unroll
+                for (int j = 0; j < CJ; ++j) acc[i][j] = static_cast<T>(0);
+            }
+            consumer_sync();
+            for (int kc = 0; kc < CH; ++kc, ++gcount) {
+                const uint32_t stage = gcount % STAGES;
+                mbar_wait(&full[stage], (gcount / STAGES) & 1u);
+                pol.template mma_tile<true>(acc, stA + stage * TE, Rs + kc * KC * BN, kc);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
             }
 
             // ---- V_I: publish to the workspace, fold into sum v^2 --------------------------------------------
-            if (tid == 0 && I + 1 < p.n_blocks) issue_xrow(I + 1);
             {
                 const bool publish = (I + 1 < p.n_blocks) || p.slot_per_tile;
                 T* const Vrow = Vt + (long long)I * BM * BN;
-                double sq[8];
+                double sq[CJ];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) sq[j] = 0.0;
+                for (int j = 0; j < CJ; ++j) sq[j] = 0.0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < RI; ++i) {
                     if (publish) {
+                        const int row = pol.row_of(i);
 #pragma unroll
-                        for (int g = 0; g < NV; ++g)
-                            *reinterpret_cast<V*>(&Vrow[owned<T>(ty, i) * BN + tx * VEC + g * 16 * VEC]) =
-                                pack_vec(&acc[i][g * VEC]);
+                        for (int jv = 0; jv < CJ / CV; ++jv)
+                            *reinterpret_cast<V*>(&Vrow[P::b_index(row, pol.cand_of(jv * CV))]) =
+                                pack_vec(&acc[i][jv * CV]);
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < CJ; ++j) {
                         const double v = static_cast<double>(acc[i][j]);
                         sq[j] = fma(v, v, sq[j]);
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 8);
-                    sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 16);
-                }
-                if ((lane >> 3) == 0) {
+                for (int j = 0; j < CJ; ++j) sq[j] = pol.reduce_rows(sq[j]);
+                if (pol.leader) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) partS[wy * BN + owned<T>(tx, j)] = sq[j];
+                    for (int j = 0; j < CJ; ++j) partS[pol.part * BN + pol.cand_of(j)] = sq[j];
                 }
-                fence_proxy_async();  // V stores (generic proxy) before the bulk loads of the next block row
+                fence_proxy_async();  // V stores (generic proxy) before the producer's bulk loads of them
             }
-            __syncthreads();
+            consumer_sync();   // every warp finished the diagonal GEMM (Rs reads) and published its part of V_I
+            if (tid == 0 && I + 1 < p.n_blocks) {
+                mbar_arrive(vbar);       // producer may now load V_I
+                issue_xrow(I + 1);       // lands in the (now free) Rs region
+            }
             if (tid < BN) ss_c += ((partS[tid] + partS[BN + tid]) + partS[2 * BN + tid]) + partS[3 * BN + tid];
         }
 
@@ -332,13 +461,13 @@ __global__ void __launch_bounds__(NT, 1) sweep_kernel(const SweepParams p) {
                 mine = minloc_warp_reduce(mine);
                 if (lane == 0) red[warp] = mine;
             }
-            __syncthreads();
+            consumer_sync();
             if (tid == 0) {
                 for (int w = 0; w < BN / 32; ++w)
                     if (minloc_better(red[w], best)) best = red[w];
             }
         }
-        __syncthreads();  // xs_s, part buffers and red are reused by the next tile
+        consumer_sync();  // xs_s, part buffers and red are reused by the next tile
     }
     if (tid == 0 && p.partials != nullptr) p.partials[blockIdx.x] = best;
 }
