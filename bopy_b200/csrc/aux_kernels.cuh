@@ -27,30 +27,36 @@ __global__ void dinv_kernel(const double* __restrict__ L, int n, double* Dinv) {
     }
 }
 
-// Operand tile (I, Jc): logical [k][row] = -L[I*BM+row][Jc*KC+k] below the diagonal block, Dinv[I][row][.] on it;
-// stored at the policy's physical index (XOR-swizzled for the DMMA engine).
-template <class P>
+// Operand tile t of block row I: t < I*CHG is the off-diagonal tile [k][row] = -L[I*BM+row][t*KCG+k] in the GEMM
+// policy's element type and physical layout; the CHD tiles after it hold Dinv[I][row][.] in the diagonal policy's.
+template <class E>
 __global__ void pack_tiles_kernel(const double* __restrict__ L, int n, const double* __restrict__ Dinv,
-                                  typename P::Elem* out) {
-    using T = typename P::Elem;
-    constexpr int KC = P::KC, CH = P::CH, TE = TILE_BYTES / sizeof(T);
-    const int I = blockIdx.y, Jc = blockIdx.x;
-    if (Jc >= (I + 1) * CH) return;
-    __shared__ double tmp[KC][BM + 1];
+                                  unsigned char* out) {
+    using PG = typename E::PG;
+    using PD = typename E::PD;
+    constexpr int KMAX = PG::KC > PD::KC ? PG::KC : PD::KC;
+    const int I = blockIdx.y, t = blockIdx.x;
+    if (t >= I * E::CHG + E::CHD) return;
+    const bool offdiag = t < I * E::CHG;
+    const int KC = offdiag ? PG::KC : PD::KC;
+    __shared__ double tmp[KMAX][BM + 1];
     for (int e = threadIdx.x; e < BM * KC; e += blockDim.x) {
         const int r = e / KC, k = e - r * KC;
         double v;
-        if (Jc < I * CH)
-            v = -L_at(L, n, I * BM + r, Jc * KC + k);
+        if (offdiag)
+            v = -L_at(L, n, I * BM + r, t * PG::KC + k);
         else
-            v = Dinv[((size_t)I * BM + r) * BM + (Jc - I * CH) * KC + k];
+            v = Dinv[((size_t)I * BM + r) * BM + (t - I * E::CHG) * PD::KC + k];
         tmp[k][r] = v;
     }
     __syncthreads();
-    T* dst = out + ((size_t)CH * I * (I + 1) / 2 + Jc) * TE;
+    unsigned char* dst = out + (E::row_base(I) + t) * (long long)TILE_BYTES;
     for (int e = threadIdx.x; e < BM * KC; e += blockDim.x) {
         const int k = e / BM, r = e - k * BM;
-        dst[P::a_index(k, r)] = static_cast<T>(tmp[k][r]);
+        if (offdiag)
+            reinterpret_cast<typename PG::Elem*>(dst)[PG::a_index(k, r)] = static_cast<typename PG::Elem>(tmp[k][r]);
+        else
+            reinterpret_cast<typename PD::Elem*>(dst)[PD::a_index(k, r)] = static_cast<typename PD::Elem>(tmp[k][r]);
     }
 }
 
@@ -68,10 +74,11 @@ __global__ void pack_x_kernel(const double* __restrict__ X, const double* __rest
 }
 
 // cov[a][b] = (k(x_a, x_b) - sum_i V[i,a] V[i,b]) * y_std^2   ($SK/_gpr.py:466-469); V in the sweep's tile layout
-template <class P, int KIND>
-__global__ void cov_kernel(const typename P::Elem* __restrict__ Vws, int n_pad, int n, const double* __restrict__ Xs,
+template <class E, int KIND>
+__global__ void cov_kernel(const typename E::TG* __restrict__ Vws, int n_pad, int n, const double* __restrict__ Xs,
                            long long m, int d, LsParam ls, double amp, double kss, double y_var, double* cov) {
-    using T = typename P::Elem;
+    using T = typename E::TG;
+    using P = typename E::PG;   // V is published in the GEMM policy's B layout
     const long long a = (long long)blockIdx.y * blockDim.y + threadIdx.y;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= m || b >= m) return;

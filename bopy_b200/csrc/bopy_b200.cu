@@ -60,34 +60,30 @@ struct bopy_gp {
 
 namespace {
 
-long long packed_tiles(const bopy_gp* gp) {
-    const long long ch = gp->dtype == BOPY_F64 ? Geo<double>::CH : Geo<float>::CH;
-    return ch * gp->n_blocks * (gp->n_blocks + 1) / 2;
-}
 
-template <class P, int KIND> int launch_sweep_t(const SweepParams& p, int grid, cudaStream_t st) {
-    const size_t smem = sweep_smem_bytes<P>(p.d);
-    CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<P, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sweep_kernel<P, KIND><<<grid, NT_ALL, smem, st>>>(p);
+template <class E, int KIND> int launch_sweep_t(const SweepParams& p, int grid, cudaStream_t st) {
+    const size_t smem = sweep_smem_bytes<E>(p.d);
+    CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<E, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sweep_kernel<E, KIND><<<grid, NT_ALL, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     return BOPY_OK;
 }
 
-template <class P> int launch_sweep_k(int kernel, const SweepParams& p, int grid, cudaStream_t st) {
+template <class E> int launch_sweep_k(int kernel, const SweepParams& p, int grid, cudaStream_t st) {
     switch (kernel) {
-        case BOPY_KERNEL_RBF: return launch_sweep_t<P, K_RBF>(p, grid, st);
-        case BOPY_KERNEL_MATERN12: return launch_sweep_t<P, K_M12>(p, grid, st);
-        case BOPY_KERNEL_MATERN32: return launch_sweep_t<P, K_M32>(p, grid, st);
-        case BOPY_KERNEL_MATERN52: return launch_sweep_t<P, K_M52>(p, grid, st);
+        case BOPY_KERNEL_RBF: return launch_sweep_t<E, K_RBF>(p, grid, st);
+        case BOPY_KERNEL_MATERN12: return launch_sweep_t<E, K_M12>(p, grid, st);
+        case BOPY_KERNEL_MATERN32: return launch_sweep_t<E, K_M32>(p, grid, st);
+        case BOPY_KERNEL_MATERN52: return launch_sweep_t<E, K_M52>(p, grid, st);
     }
     return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
 }
 
 template <class P> int launch_cov_k(const bopy_gp* gp, const void* Vws, const double* Xs, long long m,
-                                    const LsParam& ls, double* cov, cudaStream_t st) {
+                                    const LsParam& ls, double* cov, cudaStream_t st) {   // P: an Engine
     dim3 block(16, 16), grid((unsigned)((m + 15) / 16), (unsigned)((m + 15) / 16));
     const double kss = gp->amp + gp->noise, yv = gp->y_std * gp->y_std;
-    const typename P::Elem* V = reinterpret_cast<const typename P::Elem*>(Vws);
+    const typename P::TG* V = reinterpret_cast<const typename P::TG*>(Vws);
     switch (gp->kernel) {
         case BOPY_KERNEL_RBF:
             cov_kernel<P, K_RBF><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
@@ -106,11 +102,17 @@ template <class P> int launch_cov_k(const bopy_gp* gp, const void* Vws, const do
     return BOPY_OK;
 }
 
-// engine selection: fp64 -> DMMA warp tiles (or FMA thread tiles on request), fp32 -> FMA thread tiles
+// engine selection: f64 -> DMMA warp tiles (FMA thread tiles on request, for A/B runs); f32 -> mixed engine
 template <class F> int dispatch_engine(const bopy_gp* gp, F&& f) {
-    if (gp->dtype == BOPY_F32) return f(FmaPolicy<float>(0));
-    if (gp->fma64) return f(FmaPolicy<double>(0));
-    return f(DmmaPolicy(0));
+    if (gp->dtype == BOPY_F32) return f(EngineMixed());
+    if (gp->fma64) return f(EngineF64Fma());
+    return f(EngineF64());
+}
+
+long long packed_tiles(const bopy_gp* gp) {
+    long long n = 0;
+    dispatch_engine(gp, [&](auto e) { n = decltype(e)::total_tiles(gp->n_blocks); return 0; });
+    return n;
 }
 
 int check_ready(const bopy_gp* gp) {
@@ -251,10 +253,10 @@ int bopy_gp_set_state(bopy_gp* gp, const double* X_dev, const double* L_dev, con
     const int n = (int)gp->n;
     dinv_kernel<<<gp->n_blocks, BM, 0, st>>>(L_dev, n, gp->Dinv);
     CUDA_TRY(cudaGetLastError());
-    dispatch_engine(gp, [&](auto pol) {
-        using P = decltype(pol);
-        dim3 grid(gp->n_blocks * P::CH, gp->n_blocks);
-        pack_tiles_kernel<P><<<grid, 256, 0, st>>>(L_dev, n, gp->Dinv, reinterpret_cast<typename P::Elem*>(gp->Lt));
+    dispatch_engine(gp, [&](auto e) {
+        using E = decltype(e);
+        dim3 grid((gp->n_blocks - 1) * E::CHG + E::CHD, gp->n_blocks);
+        pack_tiles_kernel<E><<<grid, 256, 0, st>>>(L_dev, n, gp->Dinv, reinterpret_cast<unsigned char*>(gp->Lt));
         return BOPY_OK;
     });
     CUDA_TRY(cudaGetLastError());

@@ -32,7 +32,7 @@ constexpr int NT_ALL = NT + 128;  // 8 compute warps + one producer warpgroup (r
 constexpr int REGS_COMPUTE = 232, REGS_PRODUCER = 40;  // setmaxnreg: 8*32*232 + 4*32*40 <= 65536
 
 struct SweepParams {
-    const void* Lt;     // packed factor tiles, tile (I, Jc) at ((CH*I*(I+1)/2 + Jc) * tile elements)
+    const void* Lt;     // packed factor tiles (TILE_BYTES each), tile t of block row I at Engine::row_base(I) + t
     const double* Xt;   // [n_blocks][d+1][BM]: X/l (dimension-major) then alpha, zero padded
     void* Vws;          // [slots][n_pad][BN] solve workspace (policy tile layout)
     const double* Xs;   // candidates (m, d) row-major
@@ -207,39 +207,76 @@ struct DmmaPolicy {
     }
 };
 
-template <class P> constexpr size_t sweep_smem_bytes(int d) {
-    return (size_t)2 * STAGES * TILE_BYTES + (size_t)BM * BN * sizeof(typename P::Elem) +
+// ---------------------------------------------------------------------------------------------------------
+// Engine = (policy of the off-diagonal GEMM, policy of the diagonal GEMM).
+//   Engine<DmmaPolicy, DmmaPolicy>          fp64 everywhere                                   (dtype f64)
+//   Engine<FmaPolicy<double>, FmaPolicy<double>>  fp64 on the FMA pipe (A/B comparison only)
+//   Engine<FmaPolicy<float>, DmmaPolicy>    "mixed": fp32 FFMA for the n^2/2 off-diagonal work, fp64 DMMA for the
+//                                           diagonal solve; L_IJ and V are stored in fp32, inv(L_II) in fp64, and
+//                                           the fp32 rounding residual of K* is carried in shared memory so the
+//                                           residual tile enters the diagonal solve with fp64 accuracy (dtype f32)
+// All operand tiles are TILE_BYTES; block row I holds I*CHG off-diagonal tiles followed by CHD diagonal tiles.
+// ---------------------------------------------------------------------------------------------------------
+template <class PG_, class PD_> struct Engine {
+    using PG = PG_;
+    using PD = PD_;
+    using TG = typename PG::Elem;
+    using TD = typename PD::Elem;
+    static constexpr bool kMixed = sizeof(TG) != sizeof(TD);
+    static constexpr int CHG = PG::CH, CHD = PD::CH;
+    __host__ __device__ static long long row_base(int I) {   // tiles stored before block row I
+        return (long long)CHG * I * (I - 1) / 2 + (long long)CHD * I;
+    }
+    __host__ __device__ static long long total_tiles(int n_blocks) { return row_base(n_blocks); }
+};
+using EngineF64 = Engine<DmmaPolicy, DmmaPolicy>;
+using EngineF64Fma = Engine<FmaPolicy<double>, FmaPolicy<double>>;
+using EngineMixed = Engine<FmaPolicy<float>, DmmaPolicy>;
+
+template <class E> constexpr size_t sweep_smem_bytes(int d) {
+    return (size_t)2 * STAGES * TILE_BYTES + (size_t)BM * BN * sizeof(typename E::TD) +
            (size_t)d * BN * sizeof(double) + 192;
 }
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
-template <class P, int KIND>
+// store CV consecutive candidates of one row (converted to the destination element type)
+__device__ __forceinline__ void store_cands(double* dst, const double* v, int) { *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]); }
+__device__ __forceinline__ void store_cands(float* dst, const float* v, int) { *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void store_cands(float* dst, const double* v, int) {
+    *reinterpret_cast<float2*>(dst) = make_float2(static_cast<float>(v[0]), static_cast<float>(v[1]));
+}
+
+template <class E, int KIND>
 __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
-    using T = typename P::Elem;
-    using V = typename VecOf<T>::type;
-    constexpr int KC = P::KC, CH = P::CH, RI = P::RI, CJ = P::CJ, CV = P::CV;
-    constexpr int TE = TILE_BYTES / sizeof(T);  // elements per operand tile
+    using PG = typename E::PG;
+    using PD = typename E::PD;
+    using TG = typename E::TG;
+    using TD = typename E::TD;
+    constexpr int CHG = E::CHG, CHD = E::CHD;
+    constexpr int TEG = TILE_BYTES / sizeof(TG), TED = TILE_BYTES / sizeof(TD);  // elements per operand tile
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    T* const stA = reinterpret_cast<T*>(smem_raw);
-    T* const stB = reinterpret_cast<T*>(smem_raw + STAGES * TILE_BYTES);
+    unsigned char* const stA = smem_raw;                                 // [STAGES] A tiles (L_IJ or inv(L_II))
+    unsigned char* const stB = smem_raw + STAGES * TILE_BYTES;           // [STAGES] B tiles (V_J)
     unsigned char* const rs_raw = smem_raw + 2 * STAGES * TILE_BYTES;
-    T* const Rs = reinterpret_cast<T*>(rs_raw);                       // [BM][BN] residual tile (B operand of the diagonal GEMM)
-    double* const xrow = reinterpret_cast<double*>(rs_raw);             // aliases Rs: [(d+1)][BM] X/l block row + alpha
-    double* const partM = reinterpret_cast<double*>(rs_raw + 48 * 1024);  // aliases Rs: [4][BN]
-    double* const partS = reinterpret_cast<double*>(rs_raw + 52 * 1024);  // aliases Rs: [4][BN]
-    double* const xs_s = reinterpret_cast<double*>(rs_raw + (size_t)BM * BN * sizeof(T));  // [d][BN] candidates / l
+    TD* const Rs = reinterpret_cast<TD*>(rs_raw);                        // [BM][BN] residual tile (B operand of the diagonal GEMM)
+    double* const xrow = reinterpret_cast<double*>(rs_raw);              // aliases Rs: [(d+1)][BM] X/l block row + alpha
+    double* const partM = reinterpret_cast<double*>(rs_raw + 48 * 1024); // aliases Rs: [4][BN]
+    double* const partS = reinterpret_cast<double*>(rs_raw + 52 * 1024); // aliases Rs: [4][BN]
+    float* const kloS = reinterpret_cast<float*>(rs_raw + 64 * 1024);    // aliases Rs (mixed only): [BM][BN] fp32 residual of K*
+    double* const xs_s = reinterpret_cast<double*>(rs_raw + (size_t)BM * BN * sizeof(TD));  // [d][BN] candidates / l
     unsigned char* const tail = reinterpret_cast<unsigned char*>(xs_s + (size_t)p.d * BN);
-    uint64_t* const full = reinterpret_cast<uint64_t*>(tail);           // [STAGES] producer -> consumers
-    uint64_t* const empty = full + STAGES;                              // [STAGES] consumers -> producer
-    uint64_t* const xbar = empty + STAGES;                              // block row of X/l + alpha landed
-    uint64_t* const vbar = xbar + 1;                                    // V_I published to the workspace
-    MinLoc* const red = reinterpret_cast<MinLoc*>(tail + 128);          // [4]
+    uint64_t* const full = reinterpret_cast<uint64_t*>(tail);            // [STAGES] producer -> consumers
+    uint64_t* const empty = full + STAGES;                               // [STAGES] consumers -> producer
+    uint64_t* const xbar = empty + STAGES;                               // block row of X/l + alpha landed
+    uint64_t* const vbar = xbar + 1;                                     // V_I published to the workspace
+    MinLoc* const red = reinterpret_cast<MinLoc*>(tail + 128);           // [4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_pad = p.n_blocks * BM;
-    const T* const Lt = reinterpret_cast<const T*>(p.Lt);
+    const unsigned char* const Lt = reinterpret_cast<const unsigned char*>(p.Lt);
+    const long long slot_bytes = (long long)n_pad * BN * sizeof(TG);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -258,30 +295,30 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
         if (warp != NT / 32 || lane != 0) return;
         uint32_t g = 0, vphase = 0;
         for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            const T* const Vt =
-                reinterpret_cast<const T*>(p.Vws) + (p.slot_per_tile ? tile : (long long)blockIdx.x) * n_pad * BN;
+            const unsigned char* const Vt =
+                reinterpret_cast<const unsigned char*>(p.Vws) + (p.slot_per_tile ? tile : (long long)blockIdx.x) * slot_bytes;
             for (int I = 0; I < p.n_blocks; ++I) {
-                const int T_gemm = I * CH, T_all = T_gemm + CH;
-                const T* const a_row = Lt + (long long)CH * I * (I + 1) / 2 * TE;
+                const int T_gemm = I * CHG, T_all = T_gemm + CHD;
+                const unsigned char* const a_row = Lt + E::row_base(I) * TILE_BYTES;
                 for (int t = 0; t < T_all; ++t, ++g) {
                     const uint32_t stage = g % STAGES;
                     mbar_wait(&empty[stage], ((g / STAGES) & 1u) ^ 1u);
                     if (t < T_gemm) {
                         // J order: even rows 0..I-1, odd rows I-2..0 then I-1 (zig-zag: the V slices read last by one
                         // block row are read first by the next, so they are still in L2; V_{I-1} always comes last)
-                        const int jpos = t / CH, c = t - jpos * CH;
+                        const int jpos = t / CHG, c = t - jpos * CHG;
                         const int J = (I & 1) ? (jpos < I - 1 ? I - 2 - jpos : I - 1) : jpos;
                         if (J == I - 1 && c == 0) {   // first touch of V_{I-1}: wait until the consumers published it
                             mbar_wait(vbar, vphase);
                             vphase ^= 1u;
                         }
-                        const int tt = J * CH + c;
+                        const long long tt = (long long)J * CHG + c;
                         mbar_arrive_expect_tx(&full[stage], 2 * TILE_BYTES);
-                        bulk_g2s(stA + stage * TE, a_row + (long long)tt * TE, TILE_BYTES, &full[stage]);
-                        bulk_g2s(stB + stage * TE, Vt + (long long)tt * TE, TILE_BYTES, &full[stage]);
+                        bulk_g2s(stA + stage * TILE_BYTES, a_row + tt * TILE_BYTES, TILE_BYTES, &full[stage]);
+                        bulk_g2s(stB + stage * TILE_BYTES, Vt + tt * TILE_BYTES, TILE_BYTES, &full[stage]);
                     } else {
                         mbar_arrive_expect_tx(&full[stage], TILE_BYTES);
-                        bulk_g2s(stA + stage * TE, a_row + (long long)t * TE, TILE_BYTES, &full[stage]);
+                        bulk_g2s(stA + stage * TILE_BYTES, a_row + (long long)t * TILE_BYTES, TILE_BYTES, &full[stage]);
                     }
                 }
             }
@@ -291,7 +328,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
 
     // ===================================== compute warps ==================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
-    const P pol(tid);
+    const PG pg(tid);
+    const PD pd(tid);
     uint32_t gcount = 0;   // operand tiles consumed so far (selects ring stage and barrier parity)
     uint32_t xphase = 0;
     MinLoc best;
@@ -300,7 +338,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
 
     for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const long long c0 = tile * BN;
-        T* const Vt = reinterpret_cast<T*>(p.Vws) + (p.slot_per_tile ? tile : (long long)blockIdx.x) * n_pad * BN;
+        TG* const Vt = reinterpret_cast<TG*>(reinterpret_cast<unsigned char*>(p.Vws) +
+                                             (p.slot_per_tile ? tile : (long long)blockIdx.x) * slot_bytes);
 
         auto issue_xrow = [&](int I) {
             const uint32_t bytes = (uint32_t)(p.d + 1) * BM * sizeof(double);
@@ -320,112 +359,149 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
         consumer_sync();
 
         for (int I = 0; I < p.n_blocks; ++I) {
-            const int T_gemm = I * CH;
+            const int T_gemm = I * CHG;
 
             // ---- kernel tile K*[block row I, this tile's candidates] and its share of the mean --------
-            T acc[RI][CJ];
+            TG acc[PG::RI][PG::CJ];
             mbar_wait(xbar, xphase);
             xphase ^= 1;
             {
-                double d2[RI][CJ];
+                double d2[PG::RI][PG::CJ];
 #pragma unroll
-                for (int i = 0; i < RI; ++i)
+                for (int i = 0; i < PG::RI; ++i)
 #pragma unroll
-                    for (int j = 0; j < CJ; ++j) d2[i][j] = 0.0;
+                    for (int j = 0; j < PG::CJ; ++j) d2[i][j] = 0.0;
                 for (int q = 0; q < p.d; ++q) {
-                    double xr[RI], xc[CJ];
+                    double xr[PG::RI], xc[PG::CJ];
 #pragma unroll
-                    for (int i = 0; i < RI; ++i) xr[i] = xrow[q * BM + pol.row_of(i)];
+                    for (int i = 0; i < PG::RI; ++i) xr[i] = xrow[q * BM + pg.row_of(i)];
 #pragma unroll
-                    for (int j = 0; j < CJ; ++j) xc[j] = xs_s[q * BN + pol.cand_of(j)];
+                    for (int j = 0; j < PG::CJ; ++j) xc[j] = xs_s[q * BN + pg.cand_of(j)];
 #pragma unroll
-                    for (int i = 0; i < RI; ++i)
+                    for (int i = 0; i < PG::RI; ++i)
 #pragma unroll
-                        for (int j = 0; j < CJ; ++j) {
+                        for (int j = 0; j < PG::CJ; ++j) {
                             const double df = __dadd_rn(xc[j], -xr[i]);
                             d2[i][j] = __dadd_rn(d2[i][j], __dmul_rn(df, df));  // cdist order, unfused
                         }
                 }
-                double mp[CJ];
+                double mp[PG::CJ];
 #pragma unroll
-                for (int j = 0; j < CJ; ++j) mp[j] = 0.0;
+                for (int j = 0; j < PG::CJ; ++j) mp[j] = 0.0;
 #pragma unroll
-                for (int i = 0; i < RI; ++i) {
-                    const int row = pol.row_of(i);
+                for (int i = 0; i < PG::RI; ++i) {
+                    const int row = pg.row_of(i);
                     const bool live = I * BM + row < p.n;
                     const double a_i = xrow[p.d * BM + row];
+                    float lo[PG::CJ];
 #pragma unroll
-                    for (int j = 0; j < CJ; ++j) {
+                    for (int j = 0; j < PG::CJ; ++j) {
                         const double kv = live ? __dmul_rn(p.amp, base_kernel<KIND>(d2[i][j])) : 0.0;
-                        acc[i][j] = static_cast<T>(kv);
+                        acc[i][j] = static_cast<TG>(kv);
+                        if constexpr (E::kMixed) lo[j] = static_cast<float>(kv - static_cast<double>(acc[i][j]));
                         mp[j] = fma(kv, a_i, mp[j]);
+                    }
+                    if constexpr (E::kMixed) {
+#pragma unroll
+                        for (int jv = 0; jv < PG::CJ / 4; ++jv)
+                            *reinterpret_cast<float4*>(&kloS[row * BN + pg.cand_of(jv * 4)]) =
+                                make_float4(lo[jv * 4], lo[jv * 4 + 1], lo[jv * 4 + 2], lo[jv * 4 + 3]);
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < CJ; ++j) mp[j] = pol.reduce_rows(mp[j]);
-                if (pol.leader) {
+                for (int j = 0; j < PG::CJ; ++j) mp[j] = pg.reduce_rows(mp[j]);
+                if (pg.leader) {
 #pragma unroll
-                    for (int j = 0; j < CJ; ++j) partM[pol.part * BN + pol.cand_of(j)] = mp[j];
+                    for (int j = 0; j < PG::CJ; ++j) partM[pg.part * BN + pg.cand_of(j)] = mp[j];
                 }
             }
             consumer_sync();
             if (tid < BN) mean_c += ((partM[tid] + partM[BN + tid]) + partM[2 * BN + tid]) + partM[3 * BN + tid];
             consumer_sync();  // xrow / partM consumed: Rs may be overwritten from here on
 
-            // ---- R_I = K*_I - sum_J L_IJ V_J, then V_I = inv(L_II) R_I ------------------------------------
+            // ---- R_I = K*_I - sum_J L_IJ V_J ---------------------------------------------------------------
             for (int t = 0; t < T_gemm; ++t, ++gcount) {
                 const uint32_t stage = gcount % STAGES;
                 mbar_wait(&full[stage], (gcount / STAGES) & 1u);
-                pol.template mma_tile<false>(acc, stA + stage * TE, stB + stage * TE, -1);
+                pg.template mma_tile<false>(acc, reinterpret_cast<const TG*>(stA + stage * TILE_BYTES),
+                                            reinterpret_cast<const TG*>(stB + stage * TILE_BYTES), -1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage
             }
-            // the residual tile becomes the B operand of the diagonal GEMM
+
+            // ---- the residual tile becomes the B operand of the diagonal GEMM (in the diagonal policy's layout) ----
+            if constexpr (E::kMixed) {
+                float lo[PG::RI][PG::CJ];
 #pragma unroll
-            for (int i = 0; i < RI; ++i) {
-                const int row = pol.row_of(i);
+                for (int i = 0; i < PG::RI; ++i)
 #pragma unroll
-                for (int jv = 0; jv < CJ / CV; ++jv)
-                    *reinterpret_cast<V*>(&Rs[P::b_index(row, pol.cand_of(jv * CV))]) = pack_vec(&acc[i][jv * CV]);
+                    for (int jv = 0; jv < PG::CJ / 4; ++jv) {
+                        const float4 v = *reinterpret_cast<const float4*>(&kloS[pg.row_of(i) * BN + pg.cand_of(jv * 4)]);
+                        lo[i][jv * 4] = v.x, lo[i][jv * 4 + 1] = v.y, lo[i][jv * 4 + 2] = v.z, lo[i][jv * 4 + 3] = v.w;
+                    }
+                consumer_sync();   // every thread holds its part of kloS: the region may be overwritten by Rs
 #pragma unroll
-                for (int j = 0; j < CJ; ++j) acc[i][j] = static_cast<T>(0);
+                for (int i = 0; i < PG::RI; ++i) {
+                    const int row = pg.row_of(i);
+#pragma unroll
+                    for (int jv = 0; jv < PG::CJ / 2; ++jv)
+                        *reinterpret_cast<double2*>(&Rs[PD::b_index(row, pg.cand_of(jv * 2))]) =
+                            make_double2(static_cast<double>(acc[i][jv * 2]) + static_cast<double>(lo[i][jv * 2]),
+                                         static_cast<double>(acc[i][jv * 2 + 1]) + static_cast<double>(lo[i][jv * 2 + 1]));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < PG::RI; ++i) {
+                    const int row = pg.row_of(i);
+#pragma unroll
+                    for (int jv = 0; jv < PG::CJ / PG::CV; ++jv)
+                        store_cands(reinterpret_cast<TG*>(Rs) + PD::b_index(row, pg.cand_of(jv * PG::CV)),
+                                    &acc[i][jv * PG::CV], 0);
+                }
             }
             consumer_sync();
-            for (int kc = 0; kc < CH; ++kc, ++gcount) {
+
+            // ---- V_I = inv(L_II) R_I ------------------------------------------------------------------------------
+            TD accd[PD::RI][PD::CJ];
+#pragma unroll
+            for (int i = 0; i < PD::RI; ++i)
+#pragma unroll
+                for (int j = 0; j < PD::CJ; ++j) accd[i][j] = static_cast<TD>(0);
+            for (int kc = 0; kc < CHD; ++kc, ++gcount) {
                 const uint32_t stage = gcount % STAGES;
                 mbar_wait(&full[stage], (gcount / STAGES) & 1u);
-                pol.template mma_tile<true>(acc, stA + stage * TE, Rs + kc * KC * BN, kc);
+                pd.template mma_tile<true>(accd, reinterpret_cast<const TD*>(stA + stage * TILE_BYTES),
+                                           Rs + kc * PD::KC * BN, kc);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
             }
 
-            // ---- V_I: publish to the workspace, fold into sum v^2 --------------------------------------------
+            // ---- V_I: publish to the workspace (GEMM policy's B layout), fold into sum v^2 -------------------------
             {
                 const bool publish = (I + 1 < p.n_blocks) || p.slot_per_tile;
-                T* const Vrow = Vt + (long long)I * BM * BN;
-                double sq[CJ];
+                TG* const Vrow = Vt + (long long)I * BM * BN;
+                double sq[PD::CJ];
 #pragma unroll
-                for (int j = 0; j < CJ; ++j) sq[j] = 0.0;
+                for (int j = 0; j < PD::CJ; ++j) sq[j] = 0.0;
 #pragma unroll
-                for (int i = 0; i < RI; ++i) {
+                for (int i = 0; i < PD::RI; ++i) {
                     if (publish) {
-                        const int row = pol.row_of(i);
+                        const int row = pd.row_of(i);
 #pragma unroll
-                        for (int jv = 0; jv < CJ / CV; ++jv)
-                            *reinterpret_cast<V*>(&Vrow[P::b_index(row, pol.cand_of(jv * CV))]) =
-                                pack_vec(&acc[i][jv * CV]);
+                        for (int jv = 0; jv < PD::CJ / PD::CV; ++jv)
+                            store_cands(&Vrow[PG::b_index(row, pd.cand_of(jv * PD::CV))], &accd[i][jv * PD::CV], 0);
                     }
 #pragma unroll
-                    for (int j = 0; j < CJ; ++j) {
-                        const double v = static_cast<double>(acc[i][j]);
+                    for (int j = 0; j < PD::CJ; ++j) {
+                        const double v = static_cast<double>(accd[i][j]);
                         sq[j] = fma(v, v, sq[j]);
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < CJ; ++j) sq[j] = pol.reduce_rows(sq[j]);
-                if (pol.leader) {
+                for (int j = 0; j < PD::CJ; ++j) sq[j] = pd.reduce_rows(sq[j]);
+                if (pd.leader) {
 #pragma unroll
-                    for (int j = 0; j < CJ; ++j) partS[pol.part * BN + pol.cand_of(j)] = sq[j];
+                    for (int j = 0; j < PD::CJ; ++j) partS[pd.part * BN + pd.cand_of(j)] = sq[j];
                 }
                 fence_proxy_async();  // V stores (generic proxy) before the producer's bulk loads of them
             }

@@ -162,7 +162,8 @@ def test_full_size_c4_properties():
     a = out["acq"].cpu().numpy()
     var = out["var"].cpu().numpy()
     pv = prior_var(st)
-    assert np.isfinite(a).all() and (a <= 0).all()                     # EI is a negated expectation of a positive part
+    # EI is a negated expectation of a positive part: <= 0 up to rounding of the two cancelling terms
+    assert np.isfinite(a).all() and (a <= 1e-12 * np.abs(a).max()).all()
     assert (var > 0).all() and (var <= pv * (1 + 1e-12)).all()          # 0 < posterior var <= prior var
     assert int(out["min_idx"].item()) == int(np.argmin(a))
     # the first 1024 candidates ARE the golden candidate set (same generator, same seed)
