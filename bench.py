@@ -281,10 +281,12 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel (sweep_kernel): FP64/FP32 FMA pipe
-    peak_name = "fp64_fma" if args.dtype == "f64" else "fp32_fma"
-    peak = _native.measure_peak(peak_name)
+    # roofline of the dominant kernel (sweep_kernel): the FP64 pipe (DFMA and DMMA share it on B200; the larger
+    # of the two measured rates is the denominator) or, for the fp32 mode, the FP32 FMA pipe
     peaks_all = {k: _native.measure_peak(k) for k in ("fp64_fma", "fp32_fma", "fp64_mma")}
+    peak = max(peaks_all["fp64_fma"], peaks_all["fp64_mma"]) if args.dtype == "f64" else peaks_all["fp32_fma"]
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    nominal = sm_count * (64 if args.dtype == "f64" else 128) * 2 * 1.965e9 / 1e12
     F = flops_per_candidate(n, d)
     achieved = F * m / (kernel_ms * 1e-3) / 1e12
     measured = {}
@@ -296,10 +298,12 @@ def run_b200(args):
     hbm_peak = measured.get("hbm_gbs", 6650.0)
     algo_bytes = m * d * 8 + 16
     roofline = {
-        "bound": "fp64_fma" if args.dtype == "f64" else "fp32_fma", "kernel": "sweep_kernel",
+        "bound": "fp64 pipe (DMMA)" if args.dtype == "f64" else "fp32 FMA pipe (fp64 DMMA for the diagonal solve)",
+        "kernel": "sweep_kernel",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "peak_source": "bopy_measure_peak: register-resident FMA loop measured live on this GPU (MEASURED_PEAKS.json "
-                       "holds only HBM and bf16 peaks; the path is FP-pipe bound, SURVEY.md section 8d)",
+        "peak_source": "bopy_measure_peak: register-resident DFMA / DMMA / FFMA loops measured live on this GPU "
+                       "(MEASURED_PEAKS.json holds only HBM and bf16 peaks; the path is FP-pipe bound, SURVEY.md 8d)",
+        "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
         "flops_per_candidate": F, "candidates_per_launch": m, "kernel_ms": kernel_ms,
         "traffic": None,
         "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (kernel_ms * 1e-3) / 1e9,

@@ -166,26 +166,25 @@ template <typename T> __global__ void peak_fma_kernel(T* out, int iters, T x, T 
     if (s == static_cast<T>(-1.2345)) out[0] = s;
 }
 
-// mma.sync m8n8k4 f64 (DMMA): 256 MACs per warp instruction
-__global__ void peak_dmma_kernel(double* out, int iters, double x, double y) {
-    double c[8][2];
+// mma.sync m8n8k4 f64 (DMMA): 256 MACs per warp instruction; 32 independent accumulator pairs per warp,
+// the same instruction-level parallelism the sweep kernel's 32 x 64 warp tile has
+__global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, int iters, double x, double y) {
+    double c[32][2];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 32; ++k) {
         c[k][0] = threadIdx.x + k;
         c[k][1] = threadIdx.x - k;
     }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                             : "+d"(c[k][0]), "+d"(c[k][1])
-                             : "d"(x), "d"(y));
+        for (int k = 0; k < 32; ++k)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[k][0]), "+d"(c[k][1])
+                         : "d"(x), "d"(y));
     }
     double s = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+    for (int k = 0; k < 32; ++k) s += c[k][0] + c[k][1];
     if (s == -1.2345) out[0] = s;
 }
 

@@ -380,9 +380,10 @@ int bopy_measure_peak(int what, double* tflops_out) {
             peak_fma_kernel<float><<<grid, block>>>(reinterpret_cast<float*>(sink), iters, 1.0000001f, 1e-9f);
             flops = 2.0 * grid * block * (double)iters * 64;
         } else if (what == BOPY_PEAK_FP64_MMA) {
-            const int iters = 512;
-            peak_dmma_kernel<<<grid, block>>>(reinterpret_cast<double*>(sink), iters, 1.0000001, 1e-9);
-            flops = 2.0 * grid * (block / 32) * (double)iters * 32 * 256;
+            const int iters = 2048;
+            const int g2 = prop.multiProcessorCount * 2;   // 16 warps per SM, 32 independent DMMAs each
+            peak_dmma_kernel<<<g2, block>>>(reinterpret_cast<double*>(sink), iters, 1.0000001, 1e-9);
+            flops = 2.0 * g2 * (block / 32) * (double)iters * 32 * 256;
         } else {
             cudaFree(sink);
             return fail(BOPY_ERR_BAD_ARG, "unknown peak id %d", what);

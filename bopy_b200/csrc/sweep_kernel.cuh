@@ -212,9 +212,9 @@ struct DmmaPolicy {
 //   Engine<DmmaPolicy, DmmaPolicy>          fp64 everywhere                                   (dtype f64)
 //   Engine<FmaPolicy<double>, FmaPolicy<double>>  fp64 on the FMA pipe (A/B comparison only)
 //   Engine<FmaPolicy<float>, DmmaPolicy>    "mixed": fp32 FFMA for the n^2/2 off-diagonal work, fp64 DMMA for the
-//                                           diagonal solve; L_IJ and V are stored in fp32, inv(L_II) in fp64, and
-//                                           the fp32 rounding residual of K* is carried in shared memory so the
-//                                           residual tile enters the diagonal solve with fp64 accuracy (dtype f32)
+//                                           diagonal solve; L_IJ and V are stored in fp32, inv(L_II) in fp64; the
+//                                           residual tile lives in shared memory in fp64 (seeded with the fp64 K*),
+//                                           fp32 partial sums span one 128-column block of L only   (dtype f32)
 // All operand tiles are TILE_BYTES; block row I holds I*CHG off-diagonal tiles followed by CHD diagonal tiles.
 // ---------------------------------------------------------------------------------------------------------
 template <class PG_, class PD_> struct Engine {
@@ -254,7 +254,6 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
     using TG = typename E::TG;
     using TD = typename E::TD;
     constexpr int CHG = E::CHG, CHD = E::CHD;
-    constexpr int TEG = TILE_BYTES / sizeof(TG), TED = TILE_BYTES / sizeof(TD);  // elements per operand tile
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* const stA = smem_raw;                                 // [STAGES] A tiles (L_IJ or inv(L_II))
@@ -264,7 +263,6 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
     double* const xrow = reinterpret_cast<double*>(rs_raw);              // aliases Rs: [(d+1)][BM] X/l block row + alpha
     double* const partM = reinterpret_cast<double*>(rs_raw + 48 * 1024); // aliases Rs: [4][BN]
     double* const partS = reinterpret_cast<double*>(rs_raw + 52 * 1024); // aliases Rs: [4][BN]
-    float* const kloS = reinterpret_cast<float*>(rs_raw + 64 * 1024);    // aliases Rs (mixed only): [BM][BN] fp32 residual of K*
     double* const xs_s = reinterpret_cast<double*>(rs_raw + (size_t)BM * BN * sizeof(TD));  // [d][BN] candidates / l
     unsigned char* const tail = reinterpret_cast<unsigned char*>(xs_s + (size_t)p.d * BN);
     uint64_t* const full = reinterpret_cast<uint64_t*>(tail);            // [STAGES] producer -> consumers
@@ -393,19 +391,12 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
                     const int row = pg.row_of(i);
                     const bool live = I * BM + row < p.n;
                     const double a_i = xrow[p.d * BM + row];
-                    float lo[PG::CJ];
 #pragma unroll
                     for (int j = 0; j < PG::CJ; ++j) {
                         const double kv = live ? __dmul_rn(p.amp, base_kernel<KIND>(d2[i][j])) : 0.0;
-                        acc[i][j] = static_cast<TG>(kv);
-                        if constexpr (E::kMixed) lo[j] = static_cast<float>(kv - static_cast<double>(acc[i][j]));
+                        d2[i][j] = kv;   // mixed engine: K* stays fp64 until it seeds the residual tile
+                        acc[i][j] = E::kMixed ? static_cast<TG>(0) : static_cast<TG>(kv);
                         mp[j] = fma(kv, a_i, mp[j]);
-                    }
-                    if constexpr (E::kMixed) {
-#pragma unroll
-                        for (int jv = 0; jv < PG::CJ / 4; ++jv)
-                            *reinterpret_cast<float4*>(&kloS[row * BN + pg.cand_of(jv * 4)]) =
-                                make_float4(lo[jv * 4], lo[jv * 4 + 1], lo[jv * 4 + 2], lo[jv * 4 + 3]);
                     }
                 }
 #pragma unroll
@@ -414,10 +405,22 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
 #pragma unroll
                     for (int j = 0; j < PG::CJ; ++j) partM[pg.part * BN + pg.cand_of(j)] = mp[j];
                 }
+                consumer_sync();
+                if (tid < BN) mean_c += ((partM[tid] + partM[BN + tid]) + partM[2 * BN + tid]) + partM[3 * BN + tid];
+                consumer_sync();  // xrow / partM consumed: Rs may be overwritten from here on
+                if constexpr (E::kMixed) {
+                    // fp64 residual tile R lives in shared memory (diagonal policy's B layout); every thread owns the
+                    // same elements throughout, so the read-modify-write flushes below need no barrier
+#pragma unroll
+                    for (int i = 0; i < PG::RI; ++i) {
+                        const int row = pg.row_of(i);
+#pragma unroll
+                        for (int jv = 0; jv < PG::CJ / 2; ++jv)
+                            *reinterpret_cast<double2*>(&Rs[PD::b_index(row, pg.cand_of(jv * 2))]) =
+                                make_double2(d2[i][jv * 2], d2[i][jv * 2 + 1]);
+                    }
+                }
             }
-            consumer_sync();
-            if (tid < BN) mean_c += ((partM[tid] + partM[BN + tid]) + partM[2 * BN + tid]) + partM[3 * BN + tid];
-            consumer_sync();  // xrow / partM consumed: Rs may be overwritten from here on
 
             // ---- R_I = K*_I - sum_J L_IJ V_J ---------------------------------------------------------------
             for (int t = 0; t < T_gemm; ++t, ++gcount) {
@@ -427,29 +430,28 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
                                             reinterpret_cast<const TG*>(stB + stage * TILE_BYTES), -1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage
+                if constexpr (E::kMixed) {
+                    // fp32 partial sums cover one 128-column block of L only; they are folded into the fp64 tile
+                    if ((t + 1) % CHG == 0) {
+#pragma unroll
+                        for (int i = 0; i < PG::RI; ++i) {
+                            const int row = pg.row_of(i);
+#pragma unroll
+                            for (int jv = 0; jv < PG::CJ / 2; ++jv) {
+                                double2* const dst = reinterpret_cast<double2*>(&Rs[PD::b_index(row, pg.cand_of(jv * 2))]);
+                                double2 r = *dst;
+                                r.x += static_cast<double>(acc[i][jv * 2]);
+                                r.y += static_cast<double>(acc[i][jv * 2 + 1]);
+                                *dst = r;
+                                acc[i][jv * 2] = acc[i][jv * 2 + 1] = static_cast<TG>(0);
+                            }
+                        }
+                    }
+                }
             }
 
             // ---- the residual tile becomes the B operand of the diagonal GEMM (in the diagonal policy's layout) ----
-            if constexpr (E::kMixed) {
-                float lo[PG::RI][PG::CJ];
-#pragma unroll
-                for (int i = 0; i < PG::RI; ++i)
-#pragma unroll
-                    for (int jv = 0; jv < PG::CJ / 4; ++jv) {
-                        const float4 v = *reinterpret_cast<const float4*>(&kloS[pg.row_of(i) * BN + pg.cand_of(jv * 4)]);
-                        lo[i][jv * 4] = v.x, lo[i][jv * 4 + 1] = v.y, lo[i][jv * 4 + 2] = v.z, lo[i][jv * 4 + 3] = v.w;
-                    }
-                consumer_sync();   // every thread holds its part of kloS: the region may be overwritten by Rs
-#pragma unroll
-                for (int i = 0; i < PG::RI; ++i) {
-                    const int row = pg.row_of(i);
-#pragma unroll
-                    for (int jv = 0; jv < PG::CJ / 2; ++jv)
-                        *reinterpret_cast<double2*>(&Rs[PD::b_index(row, pg.cand_of(jv * 2))]) =
-                            make_double2(static_cast<double>(acc[i][jv * 2]) + static_cast<double>(lo[i][jv * 2]),
-                                         static_cast<double>(acc[i][jv * 2 + 1]) + static_cast<double>(lo[i][jv * 2 + 1]));
-                }
-            } else {
+            if constexpr (!E::kMixed) {
 #pragma unroll
                 for (int i = 0; i < PG::RI; ++i) {
                     const int row = pg.row_of(i);

