@@ -124,6 +124,12 @@ def host_info():
     return cores, model
 
 
+def all_host_threads():
+    """Context manager: let BLAS/OpenMP use every host core (torchrun exports OMP_NUM_THREADS=1)."""
+    from threadpoolctl import threadpool_limits
+    return threadpool_limits(limits=host_info()[0])
+
+
 def time_reference_path(gp, eta, lowers, uppers, budget_s, chunk=64, base_index=0, max_candidates=1 << 17):
     """bopy's call sequence on the host: chunks of `chunk` candidates until `budget_s` seconds are used."""
     from oracle import gp_oracle as O
@@ -132,7 +138,7 @@ def time_reference_path(gp, eta, lowers, uppers, budget_s, chunk=64, base_index=
     best = (np.inf, -1)
     done = 0
     t0 = time.perf_counter()
-    with np.errstate(invalid="ignore", divide="ignore"):
+    with np.errstate(invalid="ignore", divide="ignore"), all_host_threads():
         while done < max_candidates and time.perf_counter() - t0 < budget_s:
             a = R.ei(gp, xs[done:done + chunk], eta)
             i = int(np.argmin(a))
