@@ -13,7 +13,7 @@ from .exceptions import NativeLibraryError
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libbopy_b200.so")
 ABI_VERSION = 1
 
-OK, ERR_BAD_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_READY = 0, -1, -2, -3, -4
+OK, ERR_BAD_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_READY, ERR_NOT_POSITIVE_DEFINITE = 0, -1, -2, -3, -4, -5
 F64, F32 = 0, 1
 KERNEL_IDS = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3}
 ACQ_IDS = {None: -1, "none": -1, "lcb": 0, "ei": 1, "poi": 2}
@@ -27,6 +27,8 @@ _SIGNATURES = {
     "bopy_gp_destroy": (None, [c_void_p]),
     "bopy_gp_set_state": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_double,
                                   c_double, c_double, c_double, c_void_p]),
+    "bopy_gp_fit": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_double, c_double, c_double,
+                            c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "bopy_gp_posterior_acq": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_double, c_void_p, c_void_p,
                                       c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "bopy_gp_predict_diag": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -76,6 +78,9 @@ def load():
 def check(status, what):
     if status != OK:
         msg = load().bopy_last_error().decode("utf-8", "replace")
+        if status == ERR_NOT_POSITIVE_DEFINITE:
+            import numpy as np
+            raise np.linalg.LinAlgError(msg)   # what scipy's cholesky raises inside sklearn's fit
         raise NativeLibraryError(f"{what} failed with status {status}: {msg}")
 
 
@@ -159,6 +164,25 @@ class NativeGP:
                                              float(amplitude), float(noise_level), float(y_mean), float(y_std),
                                              _stream(self.device)), "bopy_gp_set_state")
         # the library packed private copies and synchronised: nothing needs to stay alive
+
+    def fit(self, X, y_normalised, length_scale, amplitude=1.0, noise_level=0.0, alpha_reg=1e-10, y_mean=0.0,
+            y_std=1.0, want_factor=False):
+        """Fixed-hyper-parameter fit on the device (Gram + Cholesky + alpha) and state installation.
+
+        Returns (alpha (n,) device tensor, L (n, n) device tensor or None)."""
+        import numpy as np
+        torch = require_cuda()
+        Xd = self._dev64(X, (self.n, self.d))
+        yd = self._dev64(y_normalised, (self.n,))
+        ls = np.atleast_1d(np.asarray(length_scale, dtype=np.float64))
+        ls_c = (c_double * len(ls))(*ls.tolist())
+        alpha = torch.empty(self.n, dtype=torch.float64, device=self.device)
+        L = torch.empty((self.n, self.n), dtype=torch.float64, device=self.device) if want_factor else None
+        with torch.cuda.device(self.device):
+            check(self.lib.bopy_gp_fit(self._handle, _ptr(Xd), _ptr(yd), ls_c, len(ls), float(amplitude),
+                                       float(noise_level), float(alpha_reg), float(y_mean), float(y_std), _ptr(L),
+                                       _ptr(alpha), _stream(self.device)), "bopy_gp_fit")
+        return alpha, L
 
     def candidates(self, x):
         """(m, d) fp64 device tensor from numpy / torch input."""

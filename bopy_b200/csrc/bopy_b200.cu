@@ -13,6 +13,7 @@
 
 #include "aux_kernels.cuh"
 #include "common.cuh"
+#include "fit_kernels.cuh"
 #include "sweep_kernel.cuh"
 
 using namespace bopy;
@@ -226,20 +227,22 @@ void bopy_gp_destroy(bopy_gp* gp) {
     delete gp;
 }
 
-int bopy_gp_set_state(bopy_gp* gp, const double* X_dev, const double* L_dev, const double* alpha_dev,
-                      const double* length_scale_host, int n_ls, double amplitude, double noise_level,
-                      double y_mean, double y_std, void* stream) {
-    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
-    if (X_dev == nullptr || L_dev == nullptr || alpha_dev == nullptr || length_scale_host == nullptr)
-        return fail(BOPY_ERR_BAD_ARG, "X_dev, L_dev, alpha_dev and length_scale_host must be non-NULL");
+}  // extern "C"
+
+namespace {
+
+int check_hyper(const bopy_gp* gp, const double* length_scale_host, int n_ls, double amplitude, double noise_level) {
+    if (length_scale_host == nullptr) return fail(BOPY_ERR_BAD_ARG, "length_scale_host is NULL");
     if (n_ls != 1 && n_ls != gp->d) return fail(BOPY_ERR_BAD_ARG, "n_ls must be 1 or d = %d (got %d)", gp->d, n_ls);
     for (int q = 0; q < n_ls; ++q)
         if (!(length_scale_host[q] > 0.0)) return fail(BOPY_ERR_BAD_ARG, "length_scale[%d] must be positive", q);
     if (!(amplitude > 0.0)) return fail(BOPY_ERR_BAD_ARG, "amplitude must be positive");
     if (!(noise_level >= 0.0)) return fail(BOPY_ERR_BAD_ARG, "noise_level must be non-negative");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(cudaSetDevice(gp->device));
-    gp->ready = false;
+    return BOPY_OK;
+}
+
+LsParam store_hyper(bopy_gp* gp, const double* length_scale_host, int n_ls, double amplitude, double noise_level,
+                    double y_mean, double y_std) {
     LsParam ls;
     for (int q = 0; q < MAX_D; ++q) ls.v[q] = 1.0;
     for (int q = 0; q < gp->d; ++q) {
@@ -250,9 +253,13 @@ int bopy_gp_set_state(bopy_gp* gp, const double* X_dev, const double* L_dev, con
     gp->noise = noise_level;
     gp->y_mean = y_mean;
     gp->y_std = y_std;
+    return ls;
+}
+
+// pack (L, Dinv, X, alpha) into the sweep layout; gp->Dinv must already hold the inverted diagonal blocks
+int pack_state(bopy_gp* gp, const double* X_dev, const double* L_dev, const double* alpha_dev, const LsParam& ls,
+               cudaStream_t st) {
     const int n = (int)gp->n;
-    dinv_kernel<<<gp->n_blocks, BM, 0, st>>>(L_dev, n, gp->Dinv);
-    CUDA_TRY(cudaGetLastError());
     dispatch_engine(gp, [&](auto e) {
         using E = decltype(e);
         dim3 grid((gp->n_blocks - 1) * E::CHG + E::CHD, gp->n_blocks);
@@ -262,7 +269,109 @@ int bopy_gp_set_state(bopy_gp* gp, const double* X_dev, const double* L_dev, con
     CUDA_TRY(cudaGetLastError());
     pack_x_kernel<<<gp->n_blocks, BM, 0, st>>>(X_dev, alpha_dev, n, gp->d, ls, gp->Xt);
     CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
+template <int KIND> void launch_gram(const bopy_gp* gp, const double* X, const LsParam& ls, double diag, double* A,
+                                     cudaStream_t st) {
+    dim3 block(32, 8), grid((unsigned)((gp->n + 31) / 32), (unsigned)((gp->n + 7) / 8));
+    gram_kernel<KIND><<<grid, block, 0, st>>>(X, (int)gp->n, gp->d, ls, gp->amp, diag, A);
+}
+
+}  // namespace
+
+extern "C" {
+
+int bopy_gp_set_state(bopy_gp* gp, const double* X_dev, const double* L_dev, const double* alpha_dev,
+                      const double* length_scale_host, int n_ls, double amplitude, double noise_level,
+                      double y_mean, double y_std, void* stream) {
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    if (X_dev == nullptr || L_dev == nullptr || alpha_dev == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "X_dev, L_dev and alpha_dev must be non-NULL");
+    int rc = check_hyper(gp, length_scale_host, n_ls, amplitude, noise_level);
+    if (rc != BOPY_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    gp->ready = false;
+    const LsParam ls = store_hyper(gp, length_scale_host, n_ls, amplitude, noise_level, y_mean, y_std);
+    dinv_kernel<<<gp->n_blocks, BM, 0, st>>>(L_dev, (int)gp->n, gp->Dinv);
+    CUDA_TRY(cudaGetLastError());
+    rc = pack_state(gp, X_dev, L_dev, alpha_dev, ls, st);
+    if (rc != BOPY_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(st));
+    gp->ready = true;
+    return BOPY_OK;
+}
+
+int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const double* length_scale_host, int n_ls,
+                double amplitude, double noise_level, double alpha_reg, double y_mean, double y_std,
+                double* L_out_dev, double* alpha_out_dev, void* stream) {
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    if (X_dev == nullptr || yn_dev == nullptr) return fail(BOPY_ERR_BAD_ARG, "X_dev and yn_dev must be non-NULL");
+    if (!(alpha_reg >= 0.0)) return fail(BOPY_ERR_BAD_ARG, "alpha_reg must be non-negative");
+    int rc = check_hyper(gp, length_scale_host, n_ls, amplitude, noise_level);
+    if (rc != BOPY_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    gp->ready = false;
+    const LsParam ls = store_hyper(gp, length_scale_host, n_ls, amplitude, noise_level, y_mean, y_std);
+    const int n = (int)gp->n, nb = gp->n_blocks;
+    // scratch: the working matrix (unless the caller wants L), z (n_pad), alpha (n), status
+    double* A = L_out_dev;
+    double *scratch = nullptr, *Aown = nullptr;
+    int* status = nullptr;
+    if (A == nullptr) {
+        CUDA_TRY(cudaMalloc(&Aown, (size_t)n * n * sizeof(double)));
+        A = Aown;
+    }
+    cudaError_t e = cudaMalloc(&scratch, ((size_t)gp->n_pad + n) * sizeof(double) + 16);
+    if (e != cudaSuccess) {
+        cudaFree(Aown);
+        return fail(BOPY_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    double* z = scratch;
+    double* alpha = alpha_out_dev != nullptr ? alpha_out_dev : scratch + gp->n_pad;
+    status = reinterpret_cast<int*>(scratch + gp->n_pad + n);
+    auto cleanup = [&]() {
+        cudaFree(Aown);
+        cudaFree(scratch);
+    };
+    cudaMemsetAsync(status, 0, sizeof(int), st);
+    if (L_out_dev != nullptr) cudaMemsetAsync(L_out_dev, 0, (size_t)n * n * sizeof(double), st);  // zero upper triangle
+    const double diag = (amplitude + noise_level) + alpha_reg;   // kernel_(X) diagonal, then += alpha
+    switch (gp->kernel) {
+        case BOPY_KERNEL_RBF: launch_gram<K_RBF>(gp, X_dev, ls, diag, A, st); break;
+        case BOPY_KERNEL_MATERN12: launch_gram<K_M12>(gp, X_dev, ls, diag, A, st); break;
+        case BOPY_KERNEL_MATERN32: launch_gram<K_M32>(gp, X_dev, ls, diag, A, st); break;
+        default: launch_gram<K_M52>(gp, X_dev, ls, diag, A, st); break;
+    }
+    const size_t chol_smem = (size_t)BM * (BM + 1) * sizeof(double);
+    cudaFuncSetAttribute(chol_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem);
+    for (int J = 0; J < nb; ++J) {
+        chol_block_kernel<<<1, BM, chol_smem, st>>>(A, n, J, gp->Dinv, status);
+        const int below = nb - J - 1;
+        if (below > 0) {
+            gemm_nt_kernel<<<below, NT, 0, st>>>(A, n, J, gp->Dinv, 0);
+            gemm_nt_kernel<<<below * (below + 1) / 2, NT, 0, st>>>(A, n, J, gp->Dinv, 1);
+        }
+    }
+    solve_alpha_kernel<<<1, 1024, 0, st>>>(A, n, nb, gp->Dinv, yn_dev, z, alpha);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        rc = pack_state(gp, X_dev, A, alpha, ls, st);
+    } else {
+        rc = fail(BOPY_ERR_CUDA, "fit kernels failed to launch: %s", cudaGetErrorString(e));
+    }
+    int host_status = 0;
+    if (rc == BOPY_OK) e = cudaMemcpyAsync(&host_status, status, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (rc == BOPY_OK && e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cleanup();
+    if (rc != BOPY_OK) return rc;
+    if (e != cudaSuccess) return fail(BOPY_ERR_CUDA, "bopy_gp_fit failed: %s", cudaGetErrorString(e));
+    if (host_status != 0)
+        return fail(BOPY_ERR_NOT_POSITIVE_DEFINITE,
+                    "K + alpha I is not positive definite (non-positive pivot in block column %d); increase alpha",
+                    host_status - 1);
     gp->ready = true;
     return BOPY_OK;
 }

@@ -61,22 +61,90 @@ class B200GPSurrogate(Surrogate):
         kernel tile, the mean and the variance reduction in fp64 and solves in fp32.
     device : int | str | torch.device | None
         CUDA device (default: current).
+    device_fit : 'auto' | bool
+        Where the fit runs.  With fixed hyper-parameters (`gp.optimizer is None`) the Gram matrix, the Cholesky
+        factorisation and alpha_ are computed on the device (`bopy_gp_fit`) and nothing n x n crosses PCIe;
+        otherwise scikit-learn optimises the hyper-parameters on the host exactly as the reference does and the
+        fitted state is uploaded.  'auto' picks the device fit whenever it applies.
     """
 
-    def __init__(self, gp, dtype: str = "f64", device=None):
+    def __init__(self, gp, dtype: str = "f64", device=None, device_fit="auto"):
         super().__init__()
         if dtype not in ("f64", "f32"):
             raise ValueError("dtype must be 'f64' or 'f32'")
         self.gp = gp
         self.dtype = dtype
         self.device = device
+        self.device_fit = device_fit
         self.native = None          # _native.NativeGP once fitted
         self.kernel_spec = None
+        self.fitted_on_device = False
 
-    # -- fit: host (scikit-learn), then upload ---------------------------------------------------
+    # -- fit ---------------------------------------------------------------------------------------
     def _fit(self, x: np.ndarray, y: np.ndarray) -> None:
-        self.gp.fit(x, y)
-        self.load_fitted_state()
+        if self._device_fit_applies():
+            self._fit_on_device(x, y)
+        else:
+            self.gp.fit(x, y)          # host fit incl. hyper-parameter optimisation, bopy/surrogate.py:87-88
+            self.load_fitted_state()
+
+    def _device_fit_applies(self) -> bool:
+        if self.device_fit is False:
+            return False
+        fixed = getattr(self.gp, "optimizer", None) is None
+        scalar_alpha = np.ndim(self.gp.alpha) == 0
+        if self.device_fit is True and not (fixed and scalar_alpha):
+            raise ValueError("device_fit=True needs gp.optimizer=None (fixed hyper-parameters) and a scalar alpha")
+        return fixed and scalar_alpha
+
+    def _native_for(self, n: int, d: int, kernel: str):
+        if (self.native is None or self.native.n != n or self.native.d != d or self.native.kernel != kernel):
+            if self.native is not None:
+                self.native.close()
+            self.native = _native.NativeGP(n, d, kernel=kernel, dtype=self.dtype, device=self.device)
+        return self.native
+
+    def _fit_on_device(self, x: np.ndarray, y: np.ndarray) -> None:
+        """gp.fit(x, y) with optimizer=None, restated: $SK/_gpr.py:275-285 on the host (O(n)), :349-367 on the GPU."""
+        from sklearn.base import clone
+        from sklearn.gaussian_process.kernels import RBF, ConstantKernel
+        gp = self.gp
+        kernel = gp.kernel if gp.kernel is not None else \
+            ConstantKernel(1.0, constant_value_bounds="fixed") * RBF(1.0, length_scale_bounds="fixed")
+        kernel_ = clone(kernel)
+        spec = flatten_sklearn_kernel(kernel_)
+        X = np.ascontiguousarray(x, dtype=np.float64)
+        yv = np.asarray(y, dtype=np.float64)
+        if gp.normalize_y:
+            y_mean = np.mean(yv, axis=0)
+            y_std = np.std(yv, axis=0)
+            if y_std < 10 * np.finfo(np.float64).eps:   # sklearn's _handle_zeros_in_scale
+                y_std = 1.0
+            yn = (yv - y_mean) / y_std
+        else:
+            y_mean, y_std, yn = 0.0, 1.0, yv
+        n, d = X.shape
+        native = self._native_for(n, d, spec.kernel)
+        alpha, _ = native.fit(X, yn, spec.length_scale, amplitude=spec.amplitude, noise_level=spec.noise_level,
+                              alpha_reg=float(gp.alpha), y_mean=float(y_mean), y_std=float(y_std))
+        # leave the scikit-learn object in the state its own fit would leave (minus the n x n factor, which stays
+        # on the device; `export_factor()` fetches it)
+        gp.kernel_ = kernel_
+        gp.X_train_ = np.copy(X) if gp.copy_X_train else X
+        gp.y_train_ = np.copy(yn) if gp.copy_X_train else yn
+        gp._y_train_mean, gp._y_train_std = y_mean, y_std
+        gp.alpha_ = alpha.cpu().numpy()
+        self.kernel_spec = spec
+        self.fitted_on_device = True
+
+    def export_factor(self) -> np.ndarray:
+        """The lower Cholesky factor L_ (n, n) as numpy: refits on the device with the factor exported."""
+        spec, gp = self.kernel_spec, self.gp
+        _, L = self.native.fit(gp.X_train_, gp.y_train_, spec.length_scale, amplitude=spec.amplitude,
+                               noise_level=spec.noise_level, alpha_reg=float(gp.alpha),
+                               y_mean=float(np.ravel(gp._y_train_mean)[0]), y_std=float(np.ravel(gp._y_train_std)[0]),
+                               want_factor=True)
+        return np.tril(L.cpu().numpy())
 
     def load_fitted_state(self) -> None:
         """(Re)install the state of `self.gp` -- X_train_, L_, alpha_, kernel_, y mean/std -- on the device."""
@@ -86,15 +154,11 @@ class B200GPSurrogate(Surrogate):
         n, d = X.shape
         if np.ndim(gp.alpha_) != 1:
             raise ValueError("multi-target GPs are not supported")
-        if (self.native is None or self.native.n != n or self.native.d != d
-                or self.native.kernel != spec.kernel):
-            if self.native is not None:
-                self.native.close()
-            self.native = _native.NativeGP(n, d, kernel=spec.kernel, dtype=self.dtype, device=self.device)
-        self.native.set_state(
+        self._native_for(n, d, spec.kernel).set_state(
             X, gp.L_, gp.alpha_, spec.length_scale, amplitude=spec.amplitude, noise_level=spec.noise_level,
             y_mean=float(np.ravel(gp._y_train_mean)[0]), y_std=float(np.ravel(gp._y_train_std)[0]))
         self.kernel_spec = spec
+        self.fitted_on_device = False
 
     # -- the reference contract --------------------------------------------------------------------
     def _predict(self, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:

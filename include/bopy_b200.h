@@ -8,6 +8,7 @@
  *
  *   bopy_gp_set_state      <- state left by ScipyGPSurrogate._fit     bopy/surrogate.py:87-88
  *                             ($SK/_gpr.py:349-367: X_train_, L_, alpha_, kernel_, y mean/std)
+ *   bopy_gp_fit            <- ScipyGPSurrogate._fit itself for fixed hyper-parameters (gp.fit with optimizer=None)
  *   bopy_gp_predict_cov    <- ScipyGPSurrogate._predict                bopy/surrogate.py:90-91
  *                             ($SK/_gpr.py:446-473, return_cov branch)
  *   bopy_gp_predict_diag   <- np.diag(sigma) as every acquisition uses it   bopy/acquisition.py:84-85,100-101,124-125
@@ -47,7 +48,8 @@ enum bopy_status {
     BOPY_ERR_BAD_ARG = -1,
     BOPY_ERR_CUDA = -2,
     BOPY_ERR_UNSUPPORTED = -3,
-    BOPY_ERR_NOT_READY = -4
+    BOPY_ERR_NOT_READY = -4,
+    BOPY_ERR_NOT_POSITIVE_DEFINITE = -5
 };
 
 enum bopy_dtype { BOPY_F64 = 0, BOPY_F32 = 1 };
@@ -79,6 +81,19 @@ void bopy_gp_destroy(bopy_gp* gp);
 int bopy_gp_set_state(bopy_gp* gp, const double* X_dev, const double* L_dev, const double* alpha_dev,
                       const double* length_scale_host, int n_ls, double amplitude, double noise_level,
                       double y_mean, double y_std, void* stream);
+
+/*
+ * Fit with FIXED hyper-parameters entirely on the device and install the state:
+ *   K = k(X, X) + (noise_level + alpha_reg) I;  L = cholesky(K);  alpha = K^-1 yn      ($SK/_gpr.py:349-367)
+ * X_dev (n,d) and yn_dev (n,) are device fp64; yn is the target vector AFTER the caller's normalisation
+ * ((y - y_mean) / y_std, $SK/_gpr.py:275-285: an O(n) host step kept in Python so it is bit-identical).
+ * L_out_dev (n,n row-major; only the lower triangle is meaningful) and alpha_out_dev (n,) receive the factor
+ * and the weights when non-NULL.  Returns BOPY_ERR_NOT_POSITIVE_DEFINITE if a pivot is not positive.
+ * Synchronises the stream before returning.  Replaces bopy_gp_set_state for this handle.
+ */
+int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const double* length_scale_host, int n_ls,
+                double amplitude, double noise_level, double alpha_reg, double y_mean, double y_std,
+                double* L_out_dev, double* alpha_out_dev, void* stream);
 
 /*
  * The fused sweep.  For candidates Xs_dev (m,d) row-major fp64 computes posterior mean and variance

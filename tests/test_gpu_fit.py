@@ -1,0 +1,109 @@
+"""Fixed-hyper-parameter fit on the device (bopy_gp_fit: Gram + blocked Cholesky + alpha_) against scikit-learn's
+fit ($SK/_gpr.py:349-367) and the golden vectors of the unmodified reference.  -m gpu."""
+import numpy as np
+import pytest
+from sklearn.gaussian_process import GaussianProcessRegressor
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, WhiteKernel
+
+from conftest import golden_names, golden_state
+from parity_util import check_mean, check_var
+
+from bopy_b200.acquisition import EI
+from bopy_b200.surrogate import B200GPSurrogate
+
+pytestmark = pytest.mark.gpu
+
+
+def sklearn_kernel(st):
+    k = st.kernel
+    base = RBF(k.length_scale) if k.kind == "rbf" else Matern(k.length_scale, nu=k.nu)
+    kern = ConstantKernel(k.amplitude) * base
+    return kern + WhiteKernel(k.noise_level) if k.noise_level > 0 else kern
+
+
+def device_fitted(name, dtype="f64"):
+    g, st = golden_state(name)
+    gp = GaussianProcessRegressor(kernel=sklearn_kernel(st), alpha=float(g["alpha_reg"]),
+                                  normalize_y=bool(g["normalize_y"]), optimizer=None)
+    sur = B200GPSurrogate(gp, dtype=dtype, device_fit=True)
+    sur.fit(g["X"], g["y"])
+    assert sur.fitted_on_device
+    return g, st, sur
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n != "edge_alpha0_nan"])
+def test_device_fit_reproduces_the_reference_posterior(name):
+    g, st, sur = device_fitted(name)
+    mean, var = sur.predict_diag(g["Xs"])
+    err, bound = check_mean(mean, g["mean"], st, "f64")
+    assert (err <= bound).all(), f"mean: worst {np.max(err / bound):.3g}x the bound"
+    err, bound = check_var(var, g["var"], st, "f64")
+    assert (err <= bound).all(), f"var: worst {np.max(err / bound):.3g}x the bound"
+    ei = EI(sur)
+    ei.fit(g["X"], g["y"])
+    idx, _ = ei.argmin(g["Xs"])
+    ref = g["ei"]
+    assert idx == int(g["argmin_ei"]) or abs(ref[idx] - ref.min()) <= 1e-9 * max(np.ptp(ref), abs(ref.min()))
+    # the scikit-learn object is left as its own fit would leave it (minus the factor)
+    assert np.array_equal(sur.gp.X_train_, g["X"]) and sur.gp.alpha_.shape == (len(g["X"]),)
+    assert float(np.ravel(sur.gp._y_train_std)[0]) == pytest.approx(st.y_std, rel=1e-15)
+
+
+@pytest.mark.parametrize("name", ["c3_branin_n256", "ragged_n333_d4_opt", "c4_hartmann6_n2048", "ard_amp_white"])
+def test_device_cholesky_factor_and_weights(name):
+    g, st, sur = device_fitted(name)
+    L = sur.export_factor()
+    n = len(g["X"])
+    assert L.shape == (n, n) and np.array_equal(L, np.tril(L))
+    # same factor as LAPACK's up to rounding: compare through the matrix it factors (backward error) and directly
+    K = st.L @ st.L.T
+    assert np.max(np.abs(L @ L.T - K)) <= 1e-13 * np.max(np.abs(K)) * n ** 0.5
+    assert np.max(np.abs(L - st.L)) <= 1e-9 * np.max(np.abs(st.L))
+    # alpha_ is ill-conditioned (cond(K) ~ 1e8): compare its action on the kernel rows, which is what predict uses
+    from oracle import gp_oracle as O
+    Kt = O.kernel_cross(st.kernel, g["Xs"][:64], st.X_train)
+    np.testing.assert_allclose(Kt @ sur.gp.alpha_, Kt @ st.alpha, rtol=1e-9, atol=1e-9)
+
+
+def test_device_fit_is_used_by_default_only_for_fixed_hyper_parameters():
+    x = np.linspace(0, 1, 12).reshape(-1, 1)
+    y = np.sin(6 * x).ravel()
+    fixed = B200GPSurrogate(GaussianProcessRegressor(kernel=RBF(0.3), alpha=1e-8, optimizer=None))
+    fixed.fit(x, y)
+    assert fixed.fitted_on_device
+    tuned = B200GPSurrogate(GaussianProcessRegressor(kernel=RBF(0.3), alpha=1e-8))
+    tuned.fit(x, y)
+    assert not tuned.fitted_on_device
+    with pytest.raises(ValueError, match="device_fit=True needs"):
+        B200GPSurrogate(GaussianProcessRegressor(kernel=RBF(0.3)), device_fit=True).fit(x, y)
+    # same predictions from both routes when the hyper-parameters coincide
+    host = B200GPSurrogate(GaussianProcessRegressor(kernel=RBF(0.3), alpha=1e-8, optimizer=None), device_fit=False)
+    host.fit(x, y)
+    grid = np.linspace(0, 1, 101).reshape(-1, 1)
+    m1, v1 = fixed.predict_diag(grid)
+    m2, v2 = host.predict_diag(grid)
+    np.testing.assert_allclose(m1, m2, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(v1, v2, rtol=1e-6, atol=1e-11)
+
+
+def test_not_positive_definite_raises_like_scipy():
+    x = np.array([[0.1], [0.1], [0.7]])           # duplicate row, alpha = 0 -> singular Gram matrix
+    y = np.array([1.0, 1.0, 2.0])
+    sur = B200GPSurrogate(GaussianProcessRegressor(kernel=RBF(0.3), alpha=0.0, optimizer=None))
+    with pytest.raises(np.linalg.LinAlgError, match="not positive definite"):
+        sur.fit(x, y)
+
+
+def test_refit_chain_like_kriging_believer():
+    """Fantasise-and-refit (bopy/acquisition.py:188-197) with every refit on the device."""
+    from bopy_b200.acquisition import LCB, KriggingBeliever
+    from bopy_b200.bounds import Bound, Bounds
+    from bopy_b200.optimizer import CandidateSweepOptimizer, SequentialBatchOptimizer
+    g, st, sur = device_fitted("c3_branin_n256")
+    bounds = Bounds([Bound(-5.0, 10.0), Bound(0.0, 15.0)])
+    kb = KriggingBeliever(LCB(sur))
+    kb.fit(g["X"], g["y"])
+    opt = SequentialBatchOptimizer(kb, bounds, CandidateSweepOptimizer(kb, bounds, n_candidates=1 << 14, seed=5), batch_size=3)
+    res = opt.optimize()
+    assert res.x_min.shape == (3, 2) and len(sur.x) == 256 and sur.fitted_on_device
+    assert len({tuple(np.round(p, 6)) for p in res.x_min}) == 3
