@@ -36,6 +36,12 @@ def test_device_fit_reproduces_the_reference_posterior(name):
     g, st, sur = device_fitted(name)
     mean, var = sur.predict_diag(g["Xs"])
     err, bound = check_mean(mean, g["mean"], st, "f64")
+    # two backward-stable Cholesky factorisations of K agree in the weights only up to eps * cond(K): the fit
+    # parity bound carries that term (it exceeds the 1e-9 convention only for cond(K) > 1e9, i.e. alpha_reg <= 1e-10
+    # with candidates on training points)
+    if st.L.shape[0] <= 2048:
+        s = np.linalg.svd(st.L, compute_uv=False)
+        bound = bound + 1e-2 * np.finfo(np.float64).eps * (s[0] / s[-1]) ** 2 * st.y_std
     assert (err <= bound).all(), f"mean: worst {np.max(err / bound):.3g}x the bound"
     err, bound = check_var(var, g["var"], st, "f64")
     assert (err <= bound).all(), f"var: worst {np.max(err / bound):.3g}x the bound"
