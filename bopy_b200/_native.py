@@ -35,6 +35,11 @@ _SIGNATURES = {
     "bopy_acq_eval": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p]),
     "bopy_acq_argmin": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                                 c_void_p]),
+    "bopy_acq_segment_argmin": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_int64, c_int64,
+                                        c_void_p, c_void_p, c_void_p]),
+    "bopy_candidates_around": (c_int, [c_uint64, c_void_p, c_int64, c_int, c_int, POINTER(c_double), POINTER(c_double),
+                                       POINTER(c_double), c_void_p, c_void_p]),
+    "bopy_gather_rows": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "bopy_acq_from_moments": (c_int, [c_int, c_double, c_double, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                       c_void_p, c_void_p, c_void_p]),
     "bopy_gp_predict_cov": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -210,6 +215,20 @@ class NativeGP:
         out.update(mean=mean, var=var, acq=acqv, min_val=minv, min_idx=mini)
         return out
 
+    def segment_argmin(self, Xs, seg_len, acq, eta=0.0, kappa=2.0, index_base=0):
+        """Per-segment arg-min of the acquisition over consecutive segments of `seg_len` rows of Xs (one launch).
+        Returns (values (nseg,), indices (nseg,)) device tensors."""
+        torch = require_cuda()
+        m = Xs.shape[0]
+        nseg = (m + seg_len - 1) // seg_len
+        vals = torch.empty(nseg, dtype=torch.float64, device=self.device)
+        idxs = torch.empty(nseg, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.bopy_acq_segment_argmin(self._handle, ACQ_IDS[acq], float(eta), float(kappa), _ptr(Xs), m,
+                                                   int(seg_len), int(index_base), _ptr(vals), _ptr(idxs),
+                                                   _stream(self.device)), "bopy_acq_segment_argmin")
+        return vals, idxs
+
     def predict_cov(self, Xs):
         torch = require_cuda()
         m = Xs.shape[0]
@@ -254,6 +273,33 @@ def candidates_uniform(seed, index_base, m, lowers, uppers, device=None):
     with torch.cuda.device(dev):
         check(lib.bopy_candidates_uniform(int(seed), int(index_base), int(m), d, lo, hi, _ptr(out), _stream(dev)),
               "bopy_candidates_uniform")
+    return out
+
+
+def candidates_around(seed, starts, P, halfwidth, lowers, uppers):
+    """(S*P, d) device tensor: P points around each of the S starts (row s*P is the start itself)."""
+    torch = require_cuda()
+    lib = load()
+    S, d = starts.shape
+    out = torch.empty((S * int(P), d), dtype=torch.float64, device=starts.device)
+    hw = (c_double * d)(*[float(v) for v in halfwidth])
+    lo = (c_double * d)(*[float(v) for v in lowers])
+    hi = (c_double * d)(*[float(v) for v in uppers])
+    with torch.cuda.device(starts.device):
+        check(lib.bopy_candidates_around(int(seed), _ptr(starts), S, int(P), d, hw, lo, hi, _ptr(out),
+                                         _stream(starts.device)), "bopy_candidates_around")
+    return out
+
+
+def gather_rows(xs, idx, index_base=0):
+    """xs[idx - index_base] as a new (S, d) device tensor."""
+    torch = require_cuda()
+    lib = load()
+    S, d = idx.shape[0], xs.shape[1]
+    out = torch.empty((S, d), dtype=torch.float64, device=xs.device)
+    with torch.cuda.device(xs.device):
+        check(lib.bopy_gather_rows(_ptr(xs), xs.shape[0], d, _ptr(idx), S, int(index_base), _ptr(out),
+                                   _stream(xs.device)), "bopy_gather_rows")
     return out
 
 

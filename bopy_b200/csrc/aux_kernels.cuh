@@ -125,6 +125,22 @@ __global__ void moments_kernel(int acq, double eta, double kappa, const double* 
     }
 }
 
+// segment s = tile records [s*tiles_per_seg, (s+1)*tiles_per_seg): its arg-min under np.argmin's ordering
+__global__ void segment_minloc_kernel(const MinLoc* __restrict__ tile_records, long long ntiles, int tiles_per_seg,
+                                      long long nseg, double* val_out, long long* idx_out) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    MinLoc v;
+    v.val = 0.0;
+    v.idx = -1;
+    for (int t = 0; t < tiles_per_seg; ++t) {
+        const long long g = s * tiles_per_seg + t;
+        if (g < ntiles && minloc_better(tile_records[g], v)) v = tile_records[g];
+    }
+    val_out[s] = v.val;
+    idx_out[s] = v.idx;
+}
+
 struct BoxParam {
     double lo[MAX_D], hi[MAX_D];
 };
@@ -147,6 +163,41 @@ __global__ void candidates_kernel(unsigned long long seed, long long index_base,
         const double u = __dmul_rn((double)(z >> 11), 1.0 / 9007199254740992.0);
         out[e] = __dadd_rn(box.lo[j], __dmul_rn(u, __dadd_rn(box.hi[j], -box.lo[j])));
     }
+}
+
+// local candidate clouds for multi-start refinement: row s*P + p is start s itself for p == 0 (the incumbent), else
+// start s + (2u - 1) * halfwidth, clipped to the box; u from the same counter-based generator
+__global__ void candidates_around_kernel(unsigned long long seed, const double* __restrict__ starts, long long S,
+                                         int P, int d, BoxParam half, BoxParam box, double* out) {
+    const long long total = S * P * (long long)d;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / d;             // output row
+        const int j = (int)(e - i * d);
+        const long long s = i / P;
+        const int pidx = (int)(i - s * P);
+        const double c = starts[s * d + j];
+        double x = c;
+        if (pidx != 0) {
+            const unsigned long long ctr = (unsigned long long)i * (unsigned long long)d + j + 1ULL;
+            const unsigned long long z = splitmix64(seed + 0x9E3779B97F4A7C15ULL * ctr);
+            const double u = __dmul_rn((double)(z >> 11), 1.0 / 9007199254740992.0);
+            x = __dadd_rn(c, __dmul_rn(__dadd_rn(__dmul_rn(2.0, u), -1.0), half.lo[j]));
+            x = fmin(fmax(x, box.lo[j]), box.hi[j]);
+        }
+        out[e] = x;
+    }
+}
+
+// out[s][:] = xs[idx[s] - index_base][:]
+__global__ void gather_rows_kernel(const double* __restrict__ xs, const long long* __restrict__ idx, long long S, int d,
+                                   long long index_base, long long m, double* out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S * d) return;
+    const long long s = e / d;
+    const int j = (int)(e - s * d);
+    const long long r = idx[s] - index_base;
+    out[e] = (r >= 0 && r < m) ? xs[r * d + j] : __longlong_as_double(0x7ff8000000000000LL);
 }
 
 // ---- register-resident peak microbenchmarks ---------------------------------------------------------

@@ -125,7 +125,7 @@ int check_ready(const bopy_gp* gp) {
 // the one place the sweep is launched from
 int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, double kappa, double* mean_out,
               double* var_out, double* acq_out, long long index_base, double* min_val, long long* min_idx,
-              void* Vws, int slot_per_tile, cudaStream_t st) {
+              void* Vws, int slot_per_tile, cudaStream_t st, MinLoc* tile_records = nullptr) {
     SweepParams p;
     std::memset(&p, 0, sizeof(p));
     p.Lt = gp->Lt;
@@ -153,6 +153,7 @@ int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, d
     p.index_base = index_base;
     const bool want_min = (min_val != nullptr || min_idx != nullptr);
     p.partials = want_min ? gp->partials : nullptr;
+    p.tile_records = tile_records;
     const int grid = (int)std::min<long long>(p.ntiles, gp->sm_count);
     int rc = dispatch_engine(gp, [&](auto pol) { return launch_sweep_k<decltype(pol)>(gp->kernel, p, grid, st); });
     if (rc != BOPY_OK) return rc;
@@ -408,6 +409,66 @@ int bopy_acq_argmin(bopy_gp* gp, int acq, double eta, double kappa, const double
     if (min_val_out == nullptr || min_idx_out == nullptr) return fail(BOPY_ERR_BAD_ARG, "min outputs are NULL");
     return bopy_gp_posterior_acq(gp, Xs_dev, m, acq, eta, kappa, nullptr, nullptr, nullptr, index_base, min_val_out,
                                  min_idx_out, stream);
+}
+
+int bopy_acq_segment_argmin(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
+                            int64_t seg_len, int64_t index_base, double* seg_val_out, int64_t* seg_idx_out,
+                            void* stream) {
+    int rc = check_ready(gp);
+    if (rc != BOPY_OK) return rc;
+    if (Xs_dev == nullptr || seg_val_out == nullptr || seg_idx_out == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "Xs_dev / seg_val_out / seg_idx_out is NULL");
+    if (m < 1) return fail(BOPY_ERR_BAD_ARG, "m must be >= 1 (got %lld)", (long long)m);
+    if (acq < BOPY_ACQ_LCB || acq > BOPY_ACQ_POI) return fail(BOPY_ERR_BAD_ARG, "unknown acquisition id %d", acq);
+    if (seg_len < BN || seg_len % BN != 0)
+        return fail(BOPY_ERR_BAD_ARG, "seg_len must be a positive multiple of %d (got %lld)", BN, (long long)seg_len);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    const long long ntiles = (m + BN - 1) / BN, nseg = (m + seg_len - 1) / seg_len;
+    MinLoc* records = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&records), (size_t)ntiles * sizeof(MinLoc), st));
+    rc = run_sweep(gp, Xs_dev, m, acq, eta, kappa, nullptr, nullptr, nullptr, index_base, nullptr, nullptr, gp->Vws, 0,
+                   st, records);
+    if (rc == BOPY_OK) {
+        segment_minloc_kernel<<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(
+            records, ntiles, (int)(seg_len / BN), nseg, seg_val_out, reinterpret_cast<long long*>(seg_idx_out));
+        if (cudaGetLastError() != cudaSuccess) rc = fail(BOPY_ERR_CUDA, "segment_minloc_kernel failed to launch");
+    }
+    cudaFreeAsync(records, st);
+    return rc;
+}
+
+int bopy_candidates_around(uint64_t seed, const double* starts_dev, int64_t S, int P, int d,
+                           const double* halfwidth_host, const double* lowers_host, const double* uppers_host,
+                           double* out_dev, void* stream) {
+    if (starts_dev == nullptr || halfwidth_host == nullptr || lowers_host == nullptr || uppers_host == nullptr ||
+        out_dev == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "starts/halfwidth/lowers/uppers/out must be non-NULL");
+    if (S < 1 || P < 1 || d < 1 || d > MAX_D) return fail(BOPY_ERR_BAD_ARG, "need S >= 1, P >= 1, 1 <= d <= %d", MAX_D);
+    BoxParam half, box;
+    for (int q = 0; q < MAX_D; ++q) {
+        half.lo[q] = half.hi[q] = q < d ? halfwidth_host[q] : 0.0;
+        box.lo[q] = q < d ? lowers_host[q] : 0.0;
+        box.hi[q] = q < d ? uppers_host[q] : 1.0;
+    }
+    const long long total = (long long)S * P * d;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    candidates_around_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(seed, starts_dev, S, P, d, half, box,
+                                                                               out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
+int bopy_gather_rows(const double* Xs_dev, int64_t m, int d, const int64_t* idx_dev, int64_t S, int64_t index_base,
+                     double* out_dev, void* stream) {
+    if (Xs_dev == nullptr || idx_dev == nullptr || out_dev == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "Xs_dev / idx_dev / out_dev is NULL");
+    if (m < 1 || S < 1 || d < 1) return fail(BOPY_ERR_BAD_ARG, "need m, S, d >= 1");
+    const long long total = (long long)S * d;
+    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        Xs_dev, reinterpret_cast<const long long*>(idx_dev), S, d, index_base, m, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
 }
 
 int bopy_acq_from_moments(int acq, double eta, double kappa, const double* mean_dev, const double* var_dev,

@@ -48,6 +48,7 @@ struct SweepParams {
     double* acq_out;
     long long index_base;
     MinLoc* partials;   // [gridDim.x] or nullptr when no arg-min is wanted
+    MinLoc* tile_records;  // [ntiles] per-tile arg-min records (for segmented arg-min) or nullptr
 };
 
 // base kernel as sklearn evaluates it from the squared scaled distance
@@ -534,15 +535,18 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
                 }
             }
         }
-        if (p.partials != nullptr) {
+        if (p.partials != nullptr || p.tile_records != nullptr) {
             if (warp < BN / 32) {
                 mine = minloc_warp_reduce(mine);
                 if (lane == 0) red[warp] = mine;
             }
             consumer_sync();
             if (tid == 0) {
-                for (int w = 0; w < BN / 32; ++w)
-                    if (minloc_better(red[w], best)) best = red[w];
+                MinLoc tbest = red[0];
+                for (int w = 1; w < BN / 32; ++w)
+                    if (minloc_better(red[w], tbest)) tbest = red[w];
+                if (p.tile_records != nullptr) p.tile_records[tile] = tbest;
+                if (minloc_better(tbest, best)) best = tbest;
             }
         }
         consumer_sync();  // xs_s, part buffers and red are reused by the next tile

@@ -105,6 +105,111 @@ class CandidateSweepOptimizer(Optimizer):
         return np.array([x]), np.array([val])
 
 
+class MultiStartOptimizer(Optimizer):
+    """Batched multi-start minimisation of the acquisition: all starts advance together, one launch per round.
+
+    1. A global sweep of `n_candidates` counter-based candidates is cut into `n_starts` segments; the fused
+       segmented argmin returns the best point of every segment: `n_starts` stratified starts.
+    2. `rounds` times: a cloud of `points_per_start` points is drawn around every start in a box of half-width
+       `shrink**k * initial_halfwidth * (upper - lower)` (clipped to the bounds, the start itself is point 0), all
+       clouds are swept in ONE launch, and each start moves to the best point of its own cloud.
+    3. The best start wins (`np.argmin` ordering).  `local_minima()` returns all refined starts of the last call.
+
+    Everything between the first candidate and the final (x, value) stays on the device.  With a process group the
+    starts are sharded over the ranks and one min-loc all-gather picks the winner.
+    Needs a B200-native surrogate behind an LCB / EI / POI acquisition.
+    """
+
+    def __init__(self, acquisition_function: AcquisitionFunction, bounds: Bounds, n_starts: int = 256,
+                 n_candidates: int = 1 << 20, rounds: int = 6, points_per_start: int = 256, shrink: float = 0.5,
+                 initial_halfwidth: Optional[float] = None, seed: int = 0, process_group=None,
+                 distributed: bool = False):
+        super().__init__(acquisition_function, bounds)
+        if n_starts < 1 or rounds < 0:
+            raise ValueError("`n_starts` must be positive and `rounds` non-negative.")
+        if points_per_start % 128 != 0 or points_per_start < 128:
+            raise ValueError("`points_per_start` must be a positive multiple of 128.")
+        self.n_starts = int(n_starts)
+        seg = max(128, (int(n_candidates) // self.n_starts) // 128 * 128)
+        self.segment = seg                       # candidates per start in the global sweep (multiple of 128)
+        self.n_candidates = seg * self.n_starts
+        self.rounds = int(rounds)
+        self.points_per_start = int(points_per_start)
+        self.shrink = float(shrink)
+        self.initial_halfwidth = initial_halfwidth
+        self.seed = int(seed)
+        self.process_group = process_group
+        self.distributed = distributed or process_group is not None
+        self._calls = 0
+        self._last = None
+
+    def _inner(self):
+        acq = self.acquisition_function
+        while hasattr(acq, "base_acquisition"):
+            acq = acq.base_acquisition
+        sur = acq.surrogate
+        if not (hasattr(acq, "kind") and hasattr(sur, "acquisition_segment_argmin")):
+            raise TypeError("MultiStartOptimizer needs an LCB / EI / POI acquisition on a B200GPSurrogate")
+        return acq, sur
+
+    def local_minima(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(x (n_starts_local, d), values (n_starts_local,)) of the refined starts of the last `optimize()`."""
+        if self._last is None:
+            raise RuntimeError("call optimize() first")
+        return self._last
+
+    def _optimize(self) -> Tuple[np.ndarray, np.ndarray]:
+        import torch
+
+        from .distributed import all_reduce_minloc, shard_range
+        acq, sur = self._inner()
+        args = acq.native_args()
+        lo = np.asarray(self.bounds.lowers, dtype=np.float64)
+        hi = np.asarray(self.bounds.uppers, dtype=np.float64)
+        d = len(lo)
+        seed = self.seed + 104729 * self._calls
+        self._calls += 1
+        rank, world = 0, 1
+        if self.distributed:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(self.process_group), dist.get_world_size(self.process_group)
+        s0, s1 = shard_range(self.n_starts, rank, world)      # this rank's starts
+        value, index, x_best = 0.0, -1, None
+        if s1 > s0:
+            base = s0 * self.segment
+            xs = _native.candidates_uniform(seed, base, (s1 - s0) * self.segment, lo, hi)
+            vals, idxs = sur.acquisition_segment_argmin(acq.kind, xs, self.segment, index_base=base, **args)
+            starts = _native.gather_rows(xs, idxs, index_base=base)
+            del xs
+            # a start owns ~1/n_starts of the box: begin with a cloud of that size
+            frac = self.initial_halfwidth if self.initial_halfwidth is not None else \
+                min(0.5, 0.5 * (1.0 / self.n_starts) ** (1.0 / d) * 2.0)
+            half = (hi - lo) * frac
+            P = self.points_per_start
+            for k in range(self.rounds):
+                cloud = _native.candidates_around(seed + 1 + k + 1000 * rank, starts, P, half, lo, hi)
+                vals, idxs = sur.acquisition_segment_argmin(acq.kind, cloud, P, **args)
+                starts = _native.gather_rows(cloud, idxs)
+                half = half * self.shrink
+            v = vals.cpu().numpy()
+            self._last = (starts.cpu().numpy(), v)
+            j = int(np.argmin(v))
+            value, index, x_best = float(v[j]), s0 + j, self._last[0][j]
+        if world > 1:
+            value, index = all_reduce_minloc(value, index, group=self.process_group)
+            owner = next(r for r in range(world) if shard_range(self.n_starts, r, world)[0] <= index
+                         < shard_range(self.n_starts, r, world)[1])
+            import torch.distributed as dist
+            buf = torch.as_tensor(x_best if rank == owner else np.zeros(d), dtype=torch.float64)
+            if dist.get_backend(self.process_group) != "gloo":
+                buf = buf.cuda()
+            dist.broadcast(buf, src=dist.get_global_rank(self.process_group, owner) if self.process_group is not None
+                           else owner, group=self.process_group)
+            x_best = buf.cpu().numpy()
+        return np.array([x_best]), np.array([value])
+
+
 class DirectOptimizer(Optimizer):
     """DIRECT global optimiser, one acquisition probe per call (bopy/optimizer.py:70-107).
 

@@ -187,5 +187,13 @@ class B200GPSurrogate(Surrogate):
         return int(out["min_idx"].item()), float(out["min_val"].item())
 
 
+    def acquisition_segment_argmin(self, kind: str, xs, seg_len: int, eta: float = 0.0, kappa: float = 2.0,
+                                   index_base: int = 0):
+        """Per-segment fused argmin over consecutive segments of `seg_len` rows (a multiple of 128) of the device
+        tensor / array `xs`: (values (nseg,), indices (nseg,)) as device tensors.  One launch for all segments."""
+        return self.native.segment_argmin(self.native.candidates(xs), seg_len, kind, eta=eta, kappa=kappa,
+                                          index_base=index_base)
+
+
 # Drop-in name: code written against the reference keeps working and runs on the B200.
 ScipyGPSurrogate = B200GPSurrogate

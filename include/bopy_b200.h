@@ -114,6 +114,23 @@ int bopy_acq_eval(bopy_gp* gp, int acq, double eta, double kappa, const double* 
 int bopy_acq_argmin(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
                     int64_t index_base, double* min_val_out, int64_t* min_idx_out, void* stream);
 
+/* Segmented arg-min: the m candidates are cut into consecutive segments of seg_len (a multiple of 128) and the
+ * fused sweep returns one (value, index) per segment: seg_val_out / seg_idx_out (ceil(m / seg_len),).  This is the
+ * batched multi-start primitive: one segment per start, all starts in one launch. */
+int bopy_acq_segment_argmin(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
+                            int64_t seg_len, int64_t index_base, double* seg_val_out, int64_t* seg_idx_out,
+                            void* stream);
+
+/* Local candidate clouds around S starts (S,d): out_dev (S*P, d); row s*P is the start itself, the other P-1 rows
+ * are start + U(-halfwidth, halfwidth) clipped to [lowers, uppers] (counter-based, seed). */
+int bopy_candidates_around(uint64_t seed, const double* starts_dev, int64_t S, int P, int d,
+                           const double* halfwidth_host, const double* lowers_host, const double* uppers_host,
+                           double* out_dev, void* stream);
+
+/* out_dev[s] = Xs_dev[idx_dev[s] - index_base] for s < S (rows of d doubles). */
+int bopy_gather_rows(const double* Xs_dev, int64_t m, int d, const int64_t* idx_dev, int64_t S, int64_t index_base,
+                     double* out_dev, void* stream);
+
 /* The acquisition epilogue alone, on posterior moments already on the device (mean_dev, var_dev (m,) fp64):
  * the same device code as the fused sweep's epilogue.  Serves surrogates that are not B200-native (a
  * user-defined Surrogate subclass whose predict() ran elsewhere); intended for small m. */

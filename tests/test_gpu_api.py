@@ -228,3 +228,66 @@ def test_bayes_opt_finds_the_forrester_minimum(dtype):
     assert res.f_opt < -5.9 and abs(res.x_opt[0, 0] - 0.757249) < 0.02       # global minimum -6.0207 at 0.7572
     assert rec.events[0] == "on_initial_design_end" and rec.events[-1] == "on_bo_end"
     assert rec.events.count("on_trial_end") == 12 and rec.events.count("on_acquisition_optimized") == 12
+
+
+class TestMultiStart:
+    def test_segment_argmin_matches_numpy(self):
+        from bopy_b200 import _native
+        from conftest import golden_state
+        from test_gpu_parity import native_for
+        g, st = golden_state("c3_branin_n256")
+        gp = native_for(st, "f64")
+        xs = _native.candidates_uniform(5, 0, 128 * 37 + 11, [-5.0, 0.0], [10.0, 15.0])
+        eta = float(g["eta"])
+        a = gp.sweep(xs, acq="ei", eta=eta, want_acq=True)["acq"].cpu().numpy()
+        for seg in (128, 384, 1280):
+            vals, idxs = gp.segment_argmin(xs, seg, "ei", eta=eta, index_base=7000)
+            vals, idxs = vals.cpu().numpy(), idxs.cpu().numpy()
+            nseg = -(-len(a) // seg)
+            assert vals.shape == (nseg,)
+            for s in range(nseg):
+                chunk = a[s * seg:(s + 1) * seg]
+                assert idxs[s] - 7000 == s * seg + int(np.argmin(chunk)) and vals[s] == chunk.min()
+        rows = _native.gather_rows(xs, torch_as(idxs, xs.device), index_base=7000).cpu().numpy()
+        assert np.array_equal(rows, xs.cpu().numpy()[idxs - 7000])
+
+    def test_candidate_clouds(self):
+        from bopy_b200 import _native
+        import torch
+        starts = torch.tensor([[0.1, 0.9], [0.5, 0.5], [1.0, 0.0]], dtype=torch.float64, device="cuda")
+        cloud = _native.candidates_around(3, starts, 256, [0.05, 0.2], [0.0, 0.0], [1.0, 1.0]).cpu().numpy()
+        assert cloud.shape == (768, 2)
+        for s in range(3):
+            block = cloud[s * 256:(s + 1) * 256]
+            assert np.array_equal(block[0], starts[s].cpu().numpy())          # the incumbent is point 0
+            assert (block >= 0).all() and (block <= 1).all()
+            assert (np.abs(block - starts[s].cpu().numpy()) <= np.array([0.05, 0.2]) + 1e-15).all()
+            assert block[:, 0].std() > 0.01
+
+    def test_multi_start_optimizer_beats_the_plain_sweep(self):
+        from bopy_b200.benchmark_functions import branin
+        from bopy_b200.optimizer import MultiStartOptimizer
+        lo, hi = np.array([-5.0, 0.0]), np.array([10.0, 15.0])
+        X = lo + np.random.default_rng(3).random((40, 2)) * (hi - lo)
+        y = branin(X)
+        sur = ScipyGPSurrogate(GaussianProcessRegressor(kernel=ConstantKernel(1.0) * RBF([3.0, 3.0]), alpha=1e-6,
+                                                        normalize_y=True, optimizer=None))
+        sur.fit(X, y)
+        acq = LCB(sur, kappa=1.0)
+        acq.fit(X, y)
+        bounds = Bounds([Bound(-5.0, 10.0), Bound(0.0, 15.0)])
+        plain = CandidateSweepOptimizer(acq, bounds, n_candidates=1 << 14, seed=11).optimize()
+        ms = MultiStartOptimizer(acq, bounds, n_starts=64, n_candidates=1 << 14, rounds=8, seed=11)
+        res = ms.optimize()
+        assert res.x_min.shape == (1, 2) and res.f_min.shape == (1,)
+        assert res.f_min[0] <= plain.f_min[0] + 1e-12
+        assert abs(acq(res.x_min)[0] - res.f_min[0]) <= 1e-10 * max(1.0, abs(res.f_min[0]))
+        xs, vs = ms.local_minima()
+        assert xs.shape == (64, 2) and vs.shape == (64,) and vs.min() == res.f_min[0]
+        dense = acq(np.stack(np.meshgrid(np.linspace(-5, 10, 301), np.linspace(0, 15, 301)), -1).reshape(-1, 2))
+        assert res.f_min[0] <= dense.min() + 1e-6 * np.ptp(dense)            # at least as good as a 300 x 300 grid
+
+
+def torch_as(a, device):
+    import torch
+    return torch.as_tensor(a, dtype=torch.int64, device=device)
