@@ -29,6 +29,8 @@ _SIGNATURES = {
                                   c_double, c_double, c_double, c_void_p]),
     "bopy_gp_fit": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_double, c_double, c_double,
                             c_double, c_double, c_void_p, c_void_p, c_void_p]),
+    "bopy_gp_lml": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_double, c_double, c_double,
+                            POINTER(c_double), POINTER(c_double), c_void_p]),
     "bopy_gp_posterior_acq": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_double, c_void_p, c_void_p,
                                       c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "bopy_gp_predict_diag": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -188,6 +190,23 @@ class NativeGP:
                                        float(noise_level), float(alpha_reg), float(y_mean), float(y_std), _ptr(L),
                                        _ptr(alpha), _stream(self.device)), "bopy_gp_fit")
         return alpha, L
+
+    def lml(self, X, y_normalised, length_scale, amplitude=1.0, noise_level=0.0, alpha_reg=1e-10, want_grad=True):
+        """Log marginal likelihood (and gradient w.r.t. [log amplitude, log length_scale..., log noise_level]) on the
+        device.  X / y_normalised may be device tensors (no copy).  Raises numpy.linalg.LinAlgError if K is not PD."""
+        import numpy as np
+        torch = require_cuda()
+        Xd = self._dev64(X, (self.n, self.d))
+        yd = self._dev64(y_normalised, (self.n,))
+        ls = np.atleast_1d(np.asarray(length_scale, dtype=np.float64))
+        ls_c = (c_double * len(ls))(*ls.tolist())
+        value = c_double()
+        grad = (c_double * (len(ls) + 2))() if want_grad else None
+        with torch.cuda.device(self.device):
+            check(self.lib.bopy_gp_lml(self._handle, _ptr(Xd), _ptr(yd), ls_c, len(ls), float(amplitude),
+                                       float(noise_level), float(alpha_reg), byref(value), grad, _stream(self.device)),
+                  "bopy_gp_lml")
+        return value.value, (np.array(grad[:]) if want_grad else None)
 
     def candidates(self, x):
         """(m, d) fp64 device tensor from numpy / torch input."""

@@ -273,10 +273,34 @@ int pack_state(bopy_gp* gp, const double* X_dev, const double* L_dev, const doub
     return BOPY_OK;
 }
 
-template <int KIND> void launch_gram(const bopy_gp* gp, const double* X, const LsParam& ls, double diag, double* A,
-                                     cudaStream_t st) {
-    dim3 block(32, 8), grid((unsigned)((gp->n + 31) / 32), (unsigned)((gp->n + 7) / 8));
-    gram_kernel<KIND><<<grid, block, 0, st>>>(X, (int)gp->n, gp->d, ls, gp->amp, diag, A);
+template <int KIND> void launch_gram_t(const bopy_gp* gp, const double* X, const LsParam& ls, double amp, double diag,
+                                       double* A, int ld, int n_fill, cudaStream_t st) {
+    dim3 block(32, 8), grid((unsigned)((n_fill + 31) / 32), (unsigned)((n_fill + 7) / 8));
+    gram_kernel<KIND><<<grid, block, 0, st>>>(X, (int)gp->n, gp->d, ls, amp, diag, A, ld, n_fill);
+}
+
+void launch_gram(const bopy_gp* gp, const double* X, const LsParam& ls, double amp, double diag, double* A, int ld,
+                 int n_fill, cudaStream_t st) {
+    switch (gp->kernel) {
+        case BOPY_KERNEL_RBF: launch_gram_t<K_RBF>(gp, X, ls, amp, diag, A, ld, n_fill, st); break;
+        case BOPY_KERNEL_MATERN12: launch_gram_t<K_M12>(gp, X, ls, amp, diag, A, ld, n_fill, st); break;
+        case BOPY_KERNEL_MATERN32: launch_gram_t<K_M32>(gp, X, ls, amp, diag, A, ld, n_fill, st); break;
+        default: launch_gram_t<K_M52>(gp, X, ls, amp, diag, A, ld, n_fill, st); break;
+    }
+}
+
+// in-place blocked Cholesky of the lower triangle of A (n x n, leading dimension ld); Dinv receives inv(L_JJ)
+void launch_cholesky(double* A, int n, int ld, int nb, double* Dinv, int* status, cudaStream_t st) {
+    const size_t chol_smem = (size_t)BM * (BM + 1) * sizeof(double);
+    cudaFuncSetAttribute(chol_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem);
+    for (int J = 0; J < nb; ++J) {
+        chol_block_kernel<<<1, BM, chol_smem, st>>>(A, n, ld, J, Dinv, status);
+        const int below = nb - J - 1;
+        if (below > 0) {
+            gemm_nt_kernel<<<below, NT, 0, st>>>(A, n, ld, J, Dinv, 0);
+            gemm_nt_kernel<<<below * (below + 1) / 2, NT, 0, st>>>(A, n, ld, J, Dinv, 1);
+        }
+    }
 }
 
 }  // namespace
@@ -340,23 +364,9 @@ int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const do
     cudaMemsetAsync(status, 0, sizeof(int), st);
     if (L_out_dev != nullptr) cudaMemsetAsync(L_out_dev, 0, (size_t)n * n * sizeof(double), st);  // zero upper triangle
     const double diag = (amplitude + noise_level) + alpha_reg;   // kernel_(X) diagonal, then += alpha
-    switch (gp->kernel) {
-        case BOPY_KERNEL_RBF: launch_gram<K_RBF>(gp, X_dev, ls, diag, A, st); break;
-        case BOPY_KERNEL_MATERN12: launch_gram<K_M12>(gp, X_dev, ls, diag, A, st); break;
-        case BOPY_KERNEL_MATERN32: launch_gram<K_M32>(gp, X_dev, ls, diag, A, st); break;
-        default: launch_gram<K_M52>(gp, X_dev, ls, diag, A, st); break;
-    }
-    const size_t chol_smem = (size_t)BM * (BM + 1) * sizeof(double);
-    cudaFuncSetAttribute(chol_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem);
-    for (int J = 0; J < nb; ++J) {
-        chol_block_kernel<<<1, BM, chol_smem, st>>>(A, n, J, gp->Dinv, status);
-        const int below = nb - J - 1;
-        if (below > 0) {
-            gemm_nt_kernel<<<below, NT, 0, st>>>(A, n, J, gp->Dinv, 0);
-            gemm_nt_kernel<<<below * (below + 1) / 2, NT, 0, st>>>(A, n, J, gp->Dinv, 1);
-        }
-    }
-    solve_alpha_kernel<<<1, 1024, 0, st>>>(A, n, nb, gp->Dinv, yn_dev, z, alpha);
+    launch_gram(gp, X_dev, ls, gp->amp, diag, A, n, n, st);
+    launch_cholesky(A, n, n, nb, gp->Dinv, status, st);
+    solve_alpha_kernel<<<1, 1024, 0, st>>>(A, n, n, nb, gp->Dinv, yn_dev, z, alpha);
     e = cudaGetLastError();
     if (e == cudaSuccess) {
         rc = pack_state(gp, X_dev, A, alpha, ls, st);
@@ -374,6 +384,83 @@ int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const do
                     "K + alpha I is not positive definite (non-positive pivot in block column %d); increase alpha",
                     host_status - 1);
     gp->ready = true;
+    return BOPY_OK;
+}
+
+int bopy_gp_lml(bopy_gp* gp, const double* X_dev, const double* yn_dev, const double* length_scale_host, int n_ls,
+                double amplitude, double noise_level, double alpha_reg, double* lml_out_host, double* grad_out_host,
+                void* stream) {
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    if (X_dev == nullptr || yn_dev == nullptr || lml_out_host == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "X_dev, yn_dev and lml_out_host must be non-NULL");
+    if (!(alpha_reg >= 0.0)) return fail(BOPY_ERR_BAD_ARG, "alpha_reg must be non-negative");
+    int rc = check_hyper(gp, length_scale_host, n_ls, amplitude, noise_level);
+    if (rc != BOPY_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    LsParam ls;
+    for (int q = 0; q < MAX_D; ++q) ls.v[q] = q < gp->d ? length_scale_host[n_ls == 1 ? 0 : q] : 1.0;
+    const int n = (int)gp->n, nb = gp->n_blocks, np = gp->n_pad;
+    const bool want_grad = grad_out_host != nullptr;
+    const int gx = (n + 15) / 16;
+    // one pooled allocation: A (np^2), W (np^2, gradient only), Dinv, z, alpha, scalars, partials, status
+    const size_t mat = (size_t)np * np;
+    const size_t n_part = want_grad ? (size_t)gx * gx * LML_NG : 0;
+    const size_t doubles = mat * (want_grad ? 2 : 1) + (size_t)nb * BM * BM + 2 * (size_t)np + 64 + n_part + 2;
+    double* buf = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&buf), doubles * sizeof(double), st));
+    double* A = buf;
+    double* W = want_grad ? A + mat : nullptr;
+    double* Dinv = A + mat * (want_grad ? 2 : 1);
+    double* z = Dinv + (size_t)nb * BM * BM;
+    double* alpha = z + np;
+    double* scal = alpha + np;            // [0] lml, [1..] gradient
+    double* partial = scal + 64;
+    int* status = reinterpret_cast<int*>(partial + n_part);
+    cudaMemsetAsync(A, 0, mat * (want_grad ? 2 : 1) * sizeof(double), st);
+    cudaMemsetAsync(alpha, 0, (size_t)np * sizeof(double), st);
+    cudaMemsetAsync(status, 0, sizeof(int), st);
+    launch_gram(gp, X_dev, ls, amplitude, (amplitude + noise_level) + alpha_reg, A, np, np, st);
+    launch_cholesky(A, n, np, nb, Dinv, status, st);
+    solve_alpha_kernel<<<1, 1024, 0, st>>>(A, n, np, nb, Dinv, yn_dev, z, alpha);
+    lml_value_kernel<<<1, 1024, 0, st>>>(A, n, np, yn_dev, alpha, scal);
+    if (want_grad) {
+        copy_diag_blocks_kernel<<<nb, 256, 0, st>>>(Dinv, W, np);
+        for (int delta = 1; delta < nb; ++delta) {               // W = L^-1, one block diagonal at a time
+            tile_gemm_kernel<<<nb - delta, NT, 0, st>>>(0, nb, delta, A, W, Dinv, nullptr, np);
+            tile_gemm_kernel<<<nb - delta, NT, 0, st>>>(1, nb, delta, A, W, Dinv, nullptr, np);
+        }
+        tile_gemm_kernel<<<nb * (nb + 1) / 2, NT, 0, st>>>(2, nb, 0, A, W, Dinv, A, np);   // K^-1 (lower) over L
+        dim3 block(16, 16), grid(gx, gx);
+        switch (gp->kernel) {
+            case BOPY_KERNEL_RBF:
+                lml_grad_kernel<K_RBF><<<grid, block, 0, st>>>(X_dev, n, gp->d, n_ls, ls, amplitude, noise_level, alpha, A, np, partial);
+                break;
+            case BOPY_KERNEL_MATERN12:
+                lml_grad_kernel<K_M12><<<grid, block, 0, st>>>(X_dev, n, gp->d, n_ls, ls, amplitude, noise_level, alpha, A, np, partial);
+                break;
+            case BOPY_KERNEL_MATERN32:
+                lml_grad_kernel<K_M32><<<grid, block, 0, st>>>(X_dev, n, gp->d, n_ls, ls, amplitude, noise_level, alpha, A, np, partial);
+                break;
+            default:
+                lml_grad_kernel<K_M52><<<grid, block, 0, st>>>(X_dev, n, gp->d, n_ls, ls, amplitude, noise_level, alpha, A, np, partial);
+                break;
+        }
+        lml_grad_finalize_kernel<<<1, 256, 0, st>>>(partial, gx, gx, n_ls + 2, scal + 1);
+    }
+    cudaError_t e = cudaGetLastError();
+    double host[1 + LML_NG];
+    int host_status = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host, scal, sizeof(double) * (1 + (want_grad ? n_ls + 2 : 0)), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&host_status, status, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(buf, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(BOPY_ERR_CUDA, "bopy_gp_lml failed: %s", cudaGetErrorString(e));
+    if (host_status != 0)
+        return fail(BOPY_ERR_NOT_POSITIVE_DEFINITE, "K + alpha I is not positive definite (block column %d)", host_status - 1);
+    *lml_out_host = host[0];
+    if (want_grad)
+        for (int q = 0; q < n_ls + 2; ++q) grad_out_host[q] = host[1 + q];
     return BOPY_OK;
 }
 

@@ -18,13 +18,18 @@
 
 namespace bopy {
 
-// lower triangle of K + (noise + alpha) I, row-major n x n (the strict upper triangle is left untouched)
+// lower triangle of K + (noise + alpha) I, row-major with leading dimension ld >= n (the strict upper triangle is
+// left untouched); rows n..n_fill-1 get a unit diagonal (identity padding for the blocked algorithms)
 template <int KIND>
 __global__ void gram_kernel(const double* __restrict__ X, int n, int d, LsParam ls, double amp, double diag_value,
-                            double* __restrict__ A) {
+                            double* __restrict__ A, int ld, int n_fill) {
     const int i = blockIdx.y * blockDim.y + threadIdx.y;   // row
     const int j = blockIdx.x * blockDim.x + threadIdx.x;   // column
-    if (i >= n || j > i) return;
+    if (i >= n) {
+        if (i < n_fill && j == i) A[(size_t)i * ld + j] = 1.0;
+        return;
+    }
+    if (j > i) return;
     double v = diag_value;
     if (i != j) {
         double d2 = 0.0;
@@ -34,19 +39,19 @@ __global__ void gram_kernel(const double* __restrict__ X, int n, int d, LsParam 
         }
         v = __dmul_rn(amp, base_kernel<KIND>(d2));
     }
-    A[(size_t)i * n + j] = v;
+    A[(size_t)i * ld + j] = v;
 }
 
 // In-place Cholesky of the diagonal block J (identity padded beyond n) + its inverse.  One CTA, 128 threads.
 // status[0] is set to J+1 if a non-positive pivot is met (matrix not positive definite).
-__global__ void __launch_bounds__(BM) chol_block_kernel(double* A, int n, int J, double* Dinv, int* status) {
+__global__ void __launch_bounds__(BM) chol_block_kernel(double* A, int n, int ld, int J, double* Dinv, int* status) {
     extern __shared__ double sm[];          // [BM][BM+1]
     const int t = threadIdx.x, base = J * BM;
     constexpr int LD = BM + 1;
     for (int r = 0; r < BM; ++r) {          // thread t owns column t
         const int gr = base + r, gc = base + t;
         double v = (r == t) ? 1.0 : 0.0;
-        if (gr < n && gc < n && t <= r) v = A[(size_t)gr * n + gc];
+        if (gr < n && gc < n && t <= r) v = A[(size_t)gr * ld + gc];
         sm[r * LD + t] = (t <= r) ? v : 0.0;
     }
     __syncthreads();
@@ -70,7 +75,7 @@ __global__ void __launch_bounds__(BM) chol_block_kernel(double* A, int n, int J,
     }
     for (int r = 0; r < BM; ++r) {
         const int gr = base + r, gc = base + t;
-        if (gr < n && gc < n && t <= r) A[(size_t)gr * n + gc] = sm[r * LD + t];
+        if (gr < n && gc < n && t <= r) A[(size_t)gr * ld + gc] = sm[r * LD + t];
     }
     // Dinv_J = inv(L_JJ): forward substitution, column t per thread (same recurrence as dinv_kernel)
     double* D = Dinv + (size_t)J * BM * BM;
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(BM) chol_block_kernel(double* A, int n, int J,
 //   mode 0 (panel):    tile I in (J, nb):   A = Amat[I][J] (input), B = Dinv_J, C = Amat[I][J] (in place), beta 0
 //   mode 1 (trailing): tiles I >= K > J:    A = Amat[I][J], B = Amat[K][J], C = Amat[I][K], beta 1, sign -1
 // Rows / columns beyond n are treated as zero on load and skipped on store.
-__global__ void __launch_bounds__(NT) gemm_nt_kernel(double* Amat, int n, int J, const double* Dinv, int mode) {
+__global__ void __launch_bounds__(NT) gemm_nt_kernel(double* Amat, int n, int ld, int J, const double* Dinv, int mode) {
     __shared__ __align__(16) double As[2][DmmaPolicy::KC * BM];
     __shared__ __align__(16) double Bs[2][DmmaPolicy::KC * BN];
     int I, K;
@@ -107,9 +112,9 @@ __global__ void __launch_bounds__(NT) gemm_nt_kernel(double* Amat, int n, int J,
     }
     const int tid = threadIdx.x;
     const DmmaPolicy pol(tid);
-    const double* Ablk = Amat + (size_t)I * BM * n + (size_t)J * BM;             // A[r][k], ld n
-    const double* Bblk = mode == 0 ? Dinv + (size_t)J * BM * BM : Amat + (size_t)K * BM * n + (size_t)J * BM;
-    const int ldb = mode == 0 ? BM : n;
+    const double* Ablk = Amat + (size_t)I * BM * ld + (size_t)J * BM;            // A[r][k]
+    const double* Bblk = mode == 0 ? Dinv + (size_t)J * BM * BM : Amat + (size_t)K * BM * ld + (size_t)J * BM;
+    const int ldb = mode == 0 ? BM : ld;
     const int rowsA = n - I * BM, rowsB = mode == 0 ? BM : n - K * BM, colsK = n - J * BM;   // valid extents
     // global -> register staging: 128 rows x 8 k per chunk, 4 doubles per thread per operand
     const int lr = tid >> 1, lk = (tid & 1) * 4;
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(NT) gemm_nt_kernel(double* Amat, int n, int J,
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int k = kc * DmmaPolicy::KC + lk + e;
-            ra[e] = (lr < rowsA && k < colsK) ? Ablk[(size_t)lr * n + k] : 0.0;
+            ra[e] = (lr < rowsA && k < colsK) ? Ablk[(size_t)lr * ld + k] : 0.0;
             rb[e] = (lr < rowsB && (mode == 0 || k < colsK)) ? Bblk[(size_t)lr * ldb + k] : 0.0;
         }
     };
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(NT) gemm_nt_kernel(double* Amat, int n, int J,
         if (kc + 1 < NCH) store_chunk((kc + 1) & 1);
         __syncthreads();
     }
-    double* Cblk = Amat + (size_t)I * BM * n + (size_t)K * BM;
+    double* Cblk = Amat + (size_t)I * BM * ld + (size_t)K * BM;
     const int colsC = n - K * BM;
 #pragma unroll
     for (int i = 0; i < DmmaPolicy::RI; ++i) {
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(NT) gemm_nt_kernel(double* Amat, int n, int J,
         for (int j = 0; j < DmmaPolicy::CJ; ++j) {
             const int c = pol.cand_of(j);
             if (c >= colsC || c >= BM) continue;
-            double* dst = &Cblk[(size_t)r * n + c];
+            double* dst = &Cblk[(size_t)r * ld + c];
             if (mode == 0)
                 *dst = acc[i][j];
             else if (I != K || c <= r)       // diagonal tiles: lower triangle only
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(NT) gemm_nt_kernel(double* Amat, int n, int J,
 }
 
 // alpha = L^-T (L^-1 y) with the inverted diagonal blocks; one CTA walks the block rows.  z is a scratch (n_pad).
-__global__ void __launch_bounds__(1024) solve_alpha_kernel(const double* __restrict__ L, int n, int nb,
+__global__ void __launch_bounds__(1024) solve_alpha_kernel(const double* __restrict__ L, int n, int ld, int nb,
                                                            const double* __restrict__ Dinv,
                                                            const double* __restrict__ y, double* z, double* alpha) {
     __shared__ double rhs[BM];
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(1024) solve_alpha_kernel(const double* __restr
             const int gr = I * BM + r;
             double s = 0.0;
             if (gr < n)
-                for (int k = lane; k < I * BM; k += 32) s = fma(L[(size_t)gr * n + k], z[k], s);
+                for (int k = lane; k < I * BM; k += 32) s = fma(L[(size_t)gr * ld + k], z[k], s);
 #pragma unroll
             for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
             if (lane == 0) rhs[r] = gr < n ? y[gr] - s : 0.0;
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(1024) solve_alpha_kernel(const double* __restr
             const int gc = I * BM + tid;
             double s = 0.0;
             if (gc < n)
-                for (int k = (I + 1) * BM; k < n; ++k) s = fma(L[(size_t)k * n + gc], alpha[k], s);
+                for (int k = (I + 1) * BM; k < n; ++k) s = fma(L[(size_t)k * ld + gc], alpha[k], s);
             rhs[tid] = z[I * BM + tid] - s;
         }
         __syncthreads();
@@ -202,6 +207,210 @@ __global__ void __launch_bounds__(1024) solve_alpha_kernel(const double* __restr
             double s = 0.0;
             for (int k = tid; k < BM; ++k) s = fma(Dinv[((size_t)I * BM + k) * BM + tid], rhs[k], s);
             if (I * BM + tid < n) alpha[I * BM + tid] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================================
+// Log marginal likelihood and its gradient w.r.t. the log hyper-parameters ($SK/_gpr.py:541-656), SURVEY 8(f) rank 4
+// =====================================================================================================
+
+// out[0] = -0.5 y.alpha - sum log L_ii - n/2 log(2 pi)
+__global__ void __launch_bounds__(1024) lml_value_kernel(const double* __restrict__ L, int n, int ld,
+                                                         const double* __restrict__ y, const double* __restrict__ alpha,
+                                                         double* out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += -0.5 * y[i] * alpha[i] - log(L[(size_t)i * ld + i]);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        out[0] = t - 0.5 * n * 1.8378770664093453;   // log(2 pi)
+    }
+}
+
+// W diagonal blocks = Dinv (the rest of W is zero-filled by the caller)
+__global__ void copy_diag_blocks_kernel(const double* __restrict__ Dinv, double* W, int ld) {
+    const int I = blockIdx.x;
+    for (int e = threadIdx.x; e < BM * BM; e += blockDim.x) {
+        const int r = e / BM, c = e - r * BM;
+        W[((size_t)I * BM + r) * ld + (size_t)I * BM + c] = Dinv[(size_t)I * BM * BM + e];
+    }
+}
+
+// One 128 x 128 output tile C(I,J) = scale * sum_{kb in [kb0,kb1)} Aop(I,kb) * Bop(kb,J), fp64 DMMA, on padded
+// (multiple-of-128, zero/identity filled) matrices, so no bounds checks.  Jobs:
+//   0  TRTRI off-diagonal sum   T_IJ = sum_{K=J}^{I-1} L_IK W_KJ          I = J + delta        -> W_IJ
+//   1  TRTRI scale              W_IJ = -Dinv_I T_IJ                        (in place)
+//   2  K^-1 = W^T W             Kinv_IJ = sum_{K=I}^{nb-1} W_KI^T W_KJ     I >= J               -> out
+__global__ void __launch_bounds__(NT) tile_gemm_kernel(int job, int nb, int delta, const double* __restrict__ Lmat,
+                                                       double* W, const double* __restrict__ Dinv, double* out,
+                                                       int ld) {
+    __shared__ __align__(16) double As[2][DmmaPolicy::KC * BM];
+    __shared__ __align__(16) double Bs[2][DmmaPolicy::KC * BN];
+    int I, J, kb0, kb1;
+    if (job == 2) {
+        const int idx = blockIdx.x;   // lower-triangular tile enumeration
+        int rrow = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+        while ((rrow + 1) * (rrow + 2) / 2 <= idx) ++rrow;
+        while (rrow * (rrow + 1) / 2 > idx) --rrow;
+        I = rrow;
+        J = idx - rrow * (rrow + 1) / 2;
+        kb0 = I;
+        kb1 = nb;
+    } else {
+        J = blockIdx.x;
+        I = J + delta;
+        kb0 = job == 0 ? J : 0;
+        kb1 = job == 0 ? I : 1;
+    }
+    const int tid = threadIdx.x;
+    const DmmaPolicy pol(tid);
+    // operand element addressing: A(r,k), B(k,c) for k-block kb
+    //   job 0: A = L[I*BM+r][kb*BM+k]  (k contiguous)      B = W[kb*BM+k][J*BM+c]   (c contiguous)
+    //   job 1: A = Dinv[I][r][k]       (k contiguous)      B = W[I*BM+k][J*BM+c]    (c contiguous)
+    //   job 2: A = W[kb*BM+k][I*BM+r]  (r contiguous)      B = W[kb*BM+k][J*BM+c]   (c contiguous)
+    const int lr = tid >> 1, lk = (tid & 1) * 4;       // k-contiguous loads: row lr, 4 consecutive k
+    const int rk = tid >> 5, rx = (tid & 31) * 4;      // row-contiguous loads: k row rk, 4 consecutive x
+    double ra[4], rb[4];
+    auto load_chunk = [&](int kb, int kc) {
+        const int k0 = kc * DmmaPolicy::KC;
+        if (job == 2) {
+            const double* src = W + ((size_t)kb * BM + k0 + rk) * ld + (size_t)I * BM + rx;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ra[e] = src[e];
+        } else {
+            const double* src = job == 0 ? Lmat + ((size_t)I * BM + lr) * ld + (size_t)kb * BM + k0 + lk
+                                         : Dinv + ((size_t)I * BM + lr) * BM + k0 + lk;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ra[e] = src[e];
+        }
+        const size_t brow = job == 1 ? (size_t)I * BM : (size_t)kb * BM;
+        const double* bsrc = W + (brow + k0 + rk) * ld + (size_t)J * BM + rx;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rb[e] = bsrc[e];
+    };
+    auto store_chunk = [&](int buf) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (job == 2)
+                As[buf][DmmaPolicy::a_index(rk, rx + e)] = ra[e];
+            else
+                As[buf][DmmaPolicy::a_index(lk + e, lr)] = ra[e];
+            Bs[buf][DmmaPolicy::b_index(rk, rx + e)] = rb[e];
+        }
+    };
+    double acc[DmmaPolicy::RI][DmmaPolicy::CJ];
+#pragma unroll
+    for (int i = 0; i < DmmaPolicy::RI; ++i)
+#pragma unroll
+        for (int j = 0; j < DmmaPolicy::CJ; ++j) acc[i][j] = 0.0;
+    constexpr int NCH = BM / DmmaPolicy::KC;
+    const int total = (kb1 - kb0) * NCH;
+    load_chunk(kb0, 0);
+    store_chunk(0);
+    __syncthreads();
+    for (int it = 0; it < total; ++it) {
+        const int nx = it + 1;
+        if (nx < total) load_chunk(kb0 + nx / NCH, nx % NCH);
+        pol.mma_tile<false>(acc, As[it & 1], Bs[it & 1], -1);
+        if (nx < total) store_chunk(nx & 1);
+        __syncthreads();
+    }
+    double* C = (job == 2 ? out : W) + (size_t)I * BM * ld + (size_t)J * BM;
+    const double scale = job == 1 ? -1.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < DmmaPolicy::RI; ++i) {
+        const int r = pol.row_of(i);
+#pragma unroll
+        for (int jv = 0; jv < DmmaPolicy::CJ / 2; ++jv) {
+            const int c = pol.cand_of(2 * jv);
+            *reinterpret_cast<double2*>(&C[(size_t)r * ld + c]) =
+                make_double2(scale * acc[i][2 * jv], scale * acc[i][2 * jv + 1]);
+        }
+    }
+}
+
+constexpr int LML_NG = MAX_D + 2;   // gradient slots: [amplitude, length scales..., noise]
+
+// partial[b][g] = sum over this block's (i >= k) pairs of w_ik * dK_ik/dlog(theta_g), w = (2 - [i==k]) (a_i a_k - Kinv_ik)
+template <int KIND>
+__global__ void __launch_bounds__(256) lml_grad_kernel(const double* __restrict__ X, int n, int d, int n_ls, LsParam ls,
+                                                       double amp, double noise, const double* __restrict__ alpha,
+                                                       const double* __restrict__ Kinv, int ld, double* partial) {
+    const int i = blockIdx.y * 16 + threadIdx.y;
+    const int k = blockIdx.x * 16 + threadIdx.x;
+    double g[LML_NG];
+#pragma unroll
+    for (int q = 0; q < LML_NG; ++q) g[q] = 0.0;
+    if (blockIdx.x <= blockIdx.y && i < n && k <= i) {
+        const double w = (i == k ? 1.0 : 2.0) * (alpha[i] * alpha[k] - Kinv[(size_t)i * ld + k]);
+        if (i == k) {
+            g[0] = w * amp;                 // d(c * 1)/dlog c
+            g[1 + n_ls] = w * noise;        // d(noise * I)/dlog noise
+        } else {
+            double D[MAX_D];
+            double dsum = 0.0;
+            for (int q = 0; q < d; ++q) {
+                const double df = (X[(size_t)i * d + q] - X[(size_t)k * d + q]) / ls.v[q];
+                D[q] = df * df;
+                dsum += D[q];
+            }
+            const double kv = amp * base_kernel<KIND>(dsum);
+            g[0] = w * kv;
+            double common;                  // dK/dlog l_q = common * D_q
+            if (KIND == K_RBF) common = kv;
+            else if (KIND == K_M12) common = dsum > 0.0 ? kv / sqrt(dsum) : 0.0;
+            else if (KIND == K_M32) common = amp * 3.0 * exp(-sqrt(3.0 * dsum));
+            else {
+                const double tmp = sqrt(5.0 * dsum);
+                common = amp * (5.0 / 3.0) * (tmp + 1.0) * exp(-tmp);
+            }
+            if (n_ls == 1) g[1] = w * common * dsum;
+            else
+                for (int q = 0; q < d; ++q) g[1 + q] = w * common * D[q];
+        }
+    }
+    // block reduction (fixed order), one partial row per block
+    __shared__ double red[8][LML_NG];
+    const int tid = threadIdx.y * 16 + threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int q = 0; q < n_ls + 2; ++q) {
+        double v = g[q];
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if (lane == 0) red[warp][q] = v;
+    }
+    __syncthreads();
+    if (tid < n_ls + 2) {
+        double t = 0.0;
+        for (int w2 = 0; w2 < 8; ++w2) t += red[w2][tid];
+        partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * LML_NG + tid] = t;
+    }
+}
+
+// grad[g] = 0.5 * sum_b partial[b][g] over the lower-triangular blocks, fixed order
+__global__ void __launch_bounds__(256) lml_grad_finalize_kernel(const double* __restrict__ partial, int gx, int gy, int ng,
+                                                                double* grad) {
+    __shared__ double red[8];
+    for (int q = 0; q < ng; ++q) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < gx * gy; b += blockDim.x) {
+            const int by = b / gx, bx = b - by * gx;
+            if (bx <= by) s += partial[(size_t)b * LML_NG + q];
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += red[w];
+            grad[q] = 0.5 * t;
         }
         __syncthreads();
     }

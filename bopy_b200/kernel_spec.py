@@ -64,3 +64,24 @@ def flatten_sklearn_kernel(kernel) -> FlatKernel:
         name = "rbf"
     ls = np.atleast_1d(np.asarray(base.length_scale, dtype=np.float64)).copy()
     return FlatKernel(kernel=name, length_scale=ls, amplitude=amplitude, noise_level=noise)
+
+
+def theta_gradient(kernel, flat_grad: np.ndarray) -> np.ndarray:
+    """Re-order a device gradient [d/dlog amplitude, d/dlog length_scale..., d/dlog noise_level] into the layout of
+    `kernel.theta` (scikit-learn: the log of every NON-fixed hyper-parameter, in `kernel.hyperparameters` order)."""
+    n_ls = len(flat_grad) - 2
+    out = []
+    for hp in kernel.hyperparameters:
+        if hp.fixed:
+            continue
+        if hp.name.endswith("constant_value"):
+            out.append(flat_grad[0])             # every constant factor c_i: dK/dlog c_i = K
+        elif hp.name.endswith("length_scale"):
+            if hp.n_elements != n_ls:
+                raise UnsupportedKernelError("length_scale layout does not match the flattened kernel")
+            out.extend(flat_grad[1:1 + n_ls])
+        elif hp.name.endswith("noise_level"):
+            out.append(flat_grad[1 + n_ls])
+        else:
+            raise UnsupportedKernelError(f"no device gradient for hyper-parameter {hp.name}")
+    return np.asarray(out, dtype=np.float64)

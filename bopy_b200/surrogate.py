@@ -62,10 +62,15 @@ class B200GPSurrogate(Surrogate):
     device : int | str | torch.device | None
         CUDA device (default: current).
     device_fit : 'auto' | bool
-        Where the fit runs.  With fixed hyper-parameters (`gp.optimizer is None`) the Gram matrix, the Cholesky
-        factorisation and alpha_ are computed on the device (`bopy_gp_fit`) and nothing n x n crosses PCIe;
-        otherwise scikit-learn optimises the hyper-parameters on the host exactly as the reference does and the
-        fitted state is uploaded.  'auto' picks the device fit whenever it applies.
+        Where the fit runs.
+        'auto'  fixed hyper-parameters (`gp.optimizer is None`): Gram matrix, Cholesky factorisation and alpha_ on the
+                device (`bopy_gp_fit`), nothing n x n crosses PCIe; otherwise scikit-learn optimises the
+                hyper-parameters on the host exactly as the reference does and the fitted state is uploaded.
+        True    always on the device: with an optimizer, scikit-learn's own optimiser (L-BFGS-B, restarts) drives the
+                log marginal likelihood and its gradient evaluated by `bopy_gp_lml` -- every O(n^3) step on the GPU.
+                The optimiser path is sensitive to rounding, so the hyper-parameters can differ from the host
+                route's in the last digits (or pick another local optimum where scikit-learn's would, too).
+        False   always the host route.
     """
 
     def __init__(self, gp, dtype: str = "f64", device=None, device_fit="auto"):
@@ -93,9 +98,48 @@ class B200GPSurrogate(Surrogate):
             return False
         fixed = getattr(self.gp, "optimizer", None) is None
         scalar_alpha = np.ndim(self.gp.alpha) == 0
-        if self.device_fit is True and not (fixed and scalar_alpha):
-            raise ValueError("device_fit=True needs gp.optimizer=None (fixed hyper-parameters) and a scalar alpha")
+        if self.device_fit is True:
+            if not scalar_alpha:
+                raise ValueError("device_fit=True needs a scalar alpha")
+            return True
         return fixed and scalar_alpha
+
+    def _optimise_on_device(self, kernel_, native, Xd, yd):
+        """$SK/_gpr.py:299-344 with the objective on the device: maximise the log marginal likelihood over theta."""
+        from operator import itemgetter
+
+        from sklearn.utils import check_random_state
+
+        from .kernel_spec import theta_gradient
+        gp = self.gp
+        alpha_reg = float(gp.alpha)
+
+        def obj_func(theta, eval_gradient=True):
+            k = kernel_.clone_with_theta(theta)
+            flat = flatten_sklearn_kernel(k)
+            try:
+                lml, grad = native.lml(Xd, yd, flat.length_scale, amplitude=flat.amplitude,
+                                       noise_level=flat.noise_level, alpha_reg=alpha_reg, want_grad=eval_gradient)
+            except np.linalg.LinAlgError:       # scikit-learn: -inf likelihood, zero gradient
+                return (np.inf, np.zeros_like(theta)) if eval_gradient else np.inf
+            if eval_gradient:
+                return -lml, -theta_gradient(k, grad)
+            return -lml
+
+        gp._rng = check_random_state(gp.random_state)
+        optima = [gp._constrained_optimization(obj_func, kernel_.theta, kernel_.bounds)]
+        if gp.n_restarts_optimizer > 0:
+            if not np.isfinite(kernel_.bounds).all():
+                raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) requires that all bounds "
+                                 "are finite.")
+            bounds = kernel_.bounds
+            for _ in range(gp.n_restarts_optimizer):
+                theta0 = gp._rng.uniform(bounds[:, 0], bounds[:, 1])
+                optima.append(gp._constrained_optimization(obj_func, theta0, bounds))
+        values = list(map(itemgetter(1), optima))
+        kernel_.theta = optima[int(np.argmin(values))][0]
+        kernel_._check_bounds_params()
+        gp.log_marginal_likelihood_value_ = -np.min(values)
 
     def _native_for(self, n: int, d: int, kernel: str):
         if (self.native is None or self.native.n != n or self.native.d != d or self.native.kernel != kernel):
@@ -112,7 +156,7 @@ class B200GPSurrogate(Surrogate):
         kernel = gp.kernel if gp.kernel is not None else \
             ConstantKernel(1.0, constant_value_bounds="fixed") * RBF(1.0, length_scale_bounds="fixed")
         kernel_ = clone(kernel)
-        spec = flatten_sklearn_kernel(kernel_)
+        spec = flatten_sklearn_kernel(kernel_)      # raises for kernels the device does not implement
         X = np.ascontiguousarray(x, dtype=np.float64)
         yv = np.asarray(y, dtype=np.float64)
         if gp.normalize_y:
@@ -125,6 +169,10 @@ class B200GPSurrogate(Surrogate):
             y_mean, y_std, yn = 0.0, 1.0, yv
         n, d = X.shape
         native = self._native_for(n, d, spec.kernel)
+        if gp.optimizer is not None and kernel_.n_dims > 0:
+            Xd, yd = native._dev64(X, (n, d)), native._dev64(yn, (n,))
+            self._optimise_on_device(kernel_, native, Xd, yd)
+            spec = flatten_sklearn_kernel(kernel_)
         alpha, _ = native.fit(X, yn, spec.length_scale, amplitude=spec.amplitude, noise_level=spec.noise_level,
                               alpha_reg=float(gp.alpha), y_mean=float(y_mean), y_std=float(y_std))
         # leave the scikit-learn object in the state its own fit would leave (minus the n x n factor, which stays

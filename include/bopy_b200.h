@@ -96,6 +96,17 @@ int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const do
                 double* L_out_dev, double* alpha_out_dev, void* stream);
 
 /*
+ * Log marginal likelihood of the (normalised) targets under the given hyper-parameters, and optionally its gradient
+ * with respect to the LOG hyper-parameters ($SK/_gpr.py:541-656).  Does not touch the
+ * installed state.  lml_out_host: one double.  grad_out_host (nullable): n_ls + 2 doubles laid out as
+ * [d/dlog amplitude, d/dlog length_scale[0..n_ls-1], d/dlog noise_level].  Synchronous.
+ * BOPY_ERR_NOT_POSITIVE_DEFINITE if K + alpha I has a non-positive pivot (scikit-learn returns -inf there).
+ */
+int bopy_gp_lml(bopy_gp* gp, const double* X_dev, const double* yn_dev, const double* length_scale_host, int n_ls,
+                double amplitude, double noise_level, double alpha_reg, double* lml_out_host, double* grad_out_host,
+                void* stream);
+
+/*
  * The fused sweep.  For candidates Xs_dev (m,d) row-major fp64 computes posterior mean and variance
  * (diagonal only, never the m x m matrix), the acquisition `acq` (eta = min(y) for EI/POI, kappa for
  * LCB) and the argmin over the m candidates.  Every output pointer may be NULL: mean_out/var_out/

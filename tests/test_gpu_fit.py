@@ -82,8 +82,8 @@ def test_device_fit_is_used_by_default_only_for_fixed_hyper_parameters():
     tuned = B200GPSurrogate(GaussianProcessRegressor(kernel=RBF(0.3), alpha=1e-8))
     tuned.fit(x, y)
     assert not tuned.fitted_on_device
-    with pytest.raises(ValueError, match="device_fit=True needs"):
-        B200GPSurrogate(GaussianProcessRegressor(kernel=RBF(0.3)), device_fit=True).fit(x, y)
+    with pytest.raises(ValueError, match="device_fit=True needs a scalar alpha"):
+        B200GPSurrogate(GaussianProcessRegressor(kernel=RBF(0.3), alpha=np.full(12, 1e-6)), device_fit=True).fit(x, y)
     # same predictions from both routes when the hyper-parameters coincide
     host = B200GPSurrogate(GaussianProcessRegressor(kernel=RBF(0.3), alpha=1e-8, optimizer=None), device_fit=False)
     host.fit(x, y)
@@ -115,3 +115,60 @@ def test_refit_chain_like_kriging_believer():
     res = opt.optimize()
     assert res.x_min.shape == (3, 2) and len(sur.x) == 256 and sur.fitted_on_device
     assert len({tuple(np.round(p, 6)) for p in res.x_min}) == 3
+
+
+LML_KERNELS = [
+    ConstantKernel(1.7) * RBF(0.4),
+    ConstantKernel(0.6) * RBF([0.3, 0.5, 0.9]),
+    RBF([0.3, 0.5, 0.9]),
+    ConstantKernel(2.0) * Matern(0.7, nu=0.5),
+    ConstantKernel(2.0) * Matern([0.4, 0.8, 0.6], nu=1.5),
+    Matern(0.5, nu=2.5) * ConstantKernel(1.3),
+    ConstantKernel(1.1) * RBF([0.3, 0.5, 0.9]) + WhiteKernel(1e-2),
+    ConstantKernel(1.5, constant_value_bounds="fixed") * RBF(0.4),
+]
+
+
+@pytest.mark.parametrize("kernel", LML_KERNELS, ids=[str(i) for i in range(len(LML_KERNELS))])
+@pytest.mark.parametrize("n", [50, 333])
+def test_device_lml_and_gradient_match_sklearn(kernel, n):
+    """bopy_gp_lml against GaussianProcessRegressor.log_marginal_likelihood ($SK/_gpr.py:541-656)."""
+    from bopy_b200 import _native
+    from bopy_b200.kernel_spec import flatten_sklearn_kernel, theta_gradient
+    rng = np.random.default_rng(n)
+    X = rng.random((n, 3))
+    y = np.sin(4 * X[:, 0]) + X[:, 1] ** 2 - X[:, 2]
+    ref = GaussianProcessRegressor(kernel=kernel, alpha=1e-6, normalize_y=True, optimizer=None).fit(X, y)
+    theta = ref.kernel_.theta
+    lml_ref, grad_ref = ref.log_marginal_likelihood(theta, eval_gradient=True)
+    flat = flatten_sklearn_kernel(ref.kernel_)
+    gp = _native.NativeGP(n, 3, kernel=flat.kernel)
+    lml, g = gp.lml(X, ref.y_train_, flat.length_scale, amplitude=flat.amplitude, noise_level=flat.noise_level,
+                    alpha_reg=1e-6, want_grad=True)
+    assert lml == pytest.approx(lml_ref, rel=1e-10, abs=1e-8)
+    grad = theta_gradient(ref.kernel_, g)
+    assert grad.shape == grad_ref.shape
+    np.testing.assert_allclose(grad, grad_ref, rtol=1e-7, atol=1e-7 * max(1.0, np.max(np.abs(grad_ref))))
+    value_only, none = gp.lml(X, ref.y_train_, flat.length_scale, amplitude=flat.amplitude,
+                              noise_level=flat.noise_level, alpha_reg=1e-6, want_grad=False)
+    assert none is None and value_only == lml
+
+
+def test_hyper_parameter_optimisation_on_the_device():
+    rng = np.random.default_rng(5)
+    X = rng.random((300, 2))
+    y = np.sin(5 * X[:, 0]) * np.cos(3 * X[:, 1]) + 0.05 * rng.standard_normal(300)
+    kernel = ConstantKernel(1.0) * RBF([1.0, 1.0]) + WhiteKernel(1e-1)
+    host = GaussianProcessRegressor(kernel=kernel, alpha=1e-8, normalize_y=True, random_state=0).fit(X, y)
+    sur = B200GPSurrogate(GaussianProcessRegressor(kernel=kernel, alpha=1e-8, normalize_y=True, random_state=0),
+                          device_fit=True)
+    sur.fit(X, y)
+    assert sur.fitted_on_device
+    # same optimum as scikit-learn's host route (smooth, well-identified problem)
+    np.testing.assert_allclose(sur.gp.kernel_.theta, host.kernel_.theta, rtol=1e-3, atol=1e-3)
+    assert sur.gp.log_marginal_likelihood_value_ == pytest.approx(host.log_marginal_likelihood_value_, rel=1e-6)
+    grid = rng.random((200, 2))
+    mean, var = sur.predict_diag(grid)
+    h_mean, h_std = host.predict(grid, return_std=True)
+    np.testing.assert_allclose(mean, h_mean, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(np.sqrt(var), h_std, rtol=1e-3, atol=1e-5)
