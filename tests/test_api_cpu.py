@@ -218,3 +218,19 @@ def test_one_shot_batch_optimizer_logs_and_selects():
     assert res.x_min.shape == (4, 1) and res.f_min.shape == (4,)
     xs, a_xs = acq.get_evaluations()
     assert xs.shape == (101, 1) and a_xs.shape == (101,)
+
+
+def test_theta_gradient_follows_sklearn_hyperparameter_order():
+    from bopy_b200.kernel_spec import theta_gradient
+    flat = np.array([10.0, 1.0, 2.0, 3.0, 99.0])          # [amplitude, l0, l1, l2, noise]
+    k = ConstantKernel(2.0) * RBF([0.1, 0.2, 0.3]) + WhiteKernel(1e-2)
+    assert [h.name for h in k.hyperparameters] == ["k1__k1__constant_value", "k1__k2__length_scale", "k2__noise_level"]
+    assert theta_gradient(k, flat).tolist() == [10.0, 1.0, 2.0, 3.0, 99.0]
+    k = WhiteKernel(1e-2) + RBF([0.1, 0.2, 0.3]) * ConstantKernel(2.0)
+    assert theta_gradient(k, flat).tolist() == [99.0, 1.0, 2.0, 3.0, 10.0]
+    k = ConstantKernel(2.0, constant_value_bounds="fixed") * RBF([0.1, 0.2, 0.3])
+    assert theta_gradient(k, flat).tolist() == [1.0, 2.0, 3.0]                 # fixed hyper-parameters drop out
+    k = ConstantKernel(2.0) * ConstantKernel(3.0) * Matern(0.5, nu=1.5)
+    assert theta_gradient(k, np.array([10.0, 7.0, 0.0])).tolist() == [10.0, 10.0, 7.0]
+    with pytest.raises(UnsupportedKernelError):
+        theta_gradient(ConstantKernel(2.0) * RBF([0.1, 0.2]), flat)            # layout mismatch
