@@ -42,51 +42,64 @@ __global__ void gram_kernel(const double* __restrict__ X, int n, int d, LsParam 
     A[(size_t)i * ld + j] = v;
 }
 
-// In-place Cholesky of the diagonal block J (identity padded beyond n) + its inverse.  One CTA, 128 threads.
-// status[0] is set to J+1 if a non-positive pivot is met (matrix not positive definite).
-__global__ void __launch_bounds__(BM) chol_block_kernel(double* A, int n, int ld, int J, double* Dinv, int* status) {
-    extern __shared__ double sm[];          // [BM][BM+1]
-    const int t = threadIdx.x, base = J * BM;
+// In-place Cholesky of the diagonal block J (identity padded beyond n) + its inverse, all in shared memory.
+// One CTA of CHOL_NT threads.  status[0] is set to J+1 if a non-positive pivot is met (not positive definite).
+constexpr int CHOL_NT = 256;
+__global__ void __launch_bounds__(CHOL_NT) chol_block_kernel(double* A, int n, int ld, int J, double* Dinv, int* status) {
+    extern __shared__ double sm[];          // [BM][BM+1] working block, then col[BM], dg[BM]
     constexpr int LD = BM + 1;
-    for (int r = 0; r < BM; ++r) {          // thread t owns column t
-        const int gr = base + r, gc = base + t;
-        double v = (r == t) ? 1.0 : 0.0;
-        if (gr < n && gc < n && t <= r) v = A[(size_t)gr * ld + gc];
-        sm[r * LD + t] = (t <= r) ? v : 0.0;
+    double* const col = sm + BM * LD;
+    double* const dg = col + BM;
+    const int tid = threadIdx.x, base = J * BM;
+    for (int e = tid; e < BM * BM; e += CHOL_NT) {
+        const int r = e / BM, c = e - r * BM, gr = base + r, gc = base + c;
+        double v = (r == c) ? 1.0 : 0.0;
+        if (gr < n && gc < n && c <= r) v = A[(size_t)gr * ld + gc];
+        sm[r * LD + c] = (c <= r) ? v : 0.0;
     }
     __syncthreads();
+    // right-looking factorisation: column k is scaled, then the trailing lower triangle gets a rank-1 update
     for (int k = 0; k < BM; ++k) {
-        // column k: pivot, scale
         const double akk = sm[k * LD + k];
-        if (!(akk > 0.0)) {
-            if (t == 0) status[0] = J + 1;
+        if (!(akk > 0.0)) {               // uniform: every thread reads the same value
+            if (tid == 0) status[0] = J + 1;
             return;
         }
         const double lkk = sqrt(akk);
+        if (tid == 0) dg[k] = lkk;        // the diagonal is collected aside so nobody races on sm[k][k]
+        if (tid > k && tid < BM) sm[tid * LD + k] = sm[tid * LD + k] / lkk;
         __syncthreads();
-        if (t >= k) sm[t * LD + k] = (t == k) ? lkk : sm[t * LD + k] / lkk;   // thread t = row t of column k
-        __syncthreads();
-        // trailing update of the lower triangle: column t (> k), rows r >= t
-        if (t > k) {
-            const double ltk = sm[t * LD + k];
-            for (int r = t; r < BM; ++r) sm[r * LD + t] = fma(-sm[r * LD + k], ltk, sm[r * LD + t]);
+        for (int r = k + 1 + (tid >> 4); r < BM; r += CHOL_NT / 16) {
+            const double lrk = sm[r * LD + k];
+            for (int c = k + 1 + (tid & 15); c <= r; c += 16) sm[r * LD + c] = fma(-lrk, sm[c * LD + k], sm[r * LD + c]);
         }
         __syncthreads();
     }
-    for (int r = 0; r < BM; ++r) {
-        const int gr = base + r, gc = base + t;
-        if (gr < n && gc < n && t <= r) A[(size_t)gr * ld + gc] = sm[r * LD + t];
+    if (tid < BM) sm[tid * LD + tid] = dg[tid];
+    __syncthreads();
+    for (int e = tid; e < BM * BM; e += CHOL_NT) {
+        const int r = e / BM, c = e - r * BM, gr = base + r, gc = base + c;
+        if (gr < n && gc < n && c <= r) A[(size_t)gr * ld + gc] = sm[r * LD + c];
     }
-    // Dinv_J = inv(L_JJ): forward substitution, column t per thread (same recurrence as dinv_kernel)
+    __syncthreads();
+    // in-place inverse of the lower-triangular block, last column first (LAPACK trti2 order):
+    //   X[j][j] = 1 / L[j][j];  X[r][j] = -X[j][j] * sum_{k=j+1..r} X[r][k] L[k][j]   (r > j)
+    for (int j = BM - 1; j >= 0; --j) {
+        if (tid < BM) col[tid] = sm[tid * LD + j];     // column j of L, before it is overwritten
+        __syncthreads();
+        const double xjj = 1.0 / col[j];
+        if (tid == j) sm[j * LD + j] = xjj;
+        if (tid > j && tid < BM) {
+            double s = 0.0;
+            for (int k = j + 1; k <= tid; ++k) s = fma(sm[tid * LD + k], col[k], s);
+            sm[tid * LD + j] = -xjj * s;
+        }
+        __syncthreads();
+    }
     double* D = Dinv + (size_t)J * BM * BM;
-    for (int r = 0; r < BM; ++r) {
-        double x = 0.0;
-        if (r >= t) {
-            double s = (r == t) ? 1.0 : 0.0;
-            for (int k = t; k < r; ++k) s = fma(-sm[r * LD + k], D[(size_t)k * BM + t], s);
-            x = s / sm[r * LD + r];
-        }
-        D[(size_t)r * BM + t] = x;
+    for (int e = tid; e < BM * BM; e += CHOL_NT) {
+        const int r = e / BM, c = e - r * BM;
+        D[e] = (c <= r) ? sm[r * LD + c] : 0.0;
     }
 }
 
@@ -168,13 +181,17 @@ __global__ void __launch_bounds__(NT) gemm_nt_kernel(double* Amat, int n, int ld
     }
 }
 
-// alpha = L^-T (L^-1 y) with the inverted diagonal blocks; one CTA walks the block rows.  z is a scratch (n_pad).
+// alpha = L^-T (L^-1 y) with the inverted diagonal blocks; one CTA of 1024 threads walks the block rows.
+// z is a scratch vector (n_pad).  Threads are arranged as 8 k-groups x 128 columns so that every matrix access is a
+// contiguous 1 KB row segment; partial sums are combined through shared memory in a fixed order.
 __global__ void __launch_bounds__(1024) solve_alpha_kernel(const double* __restrict__ L, int n, int ld, int nb,
                                                            const double* __restrict__ Dinv,
                                                            const double* __restrict__ y, double* z, double* alpha) {
+    __shared__ double part[8][BM];
     __shared__ double rhs[BM];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    // forward: z_I = Dinv_I (y_I - sum_{J<I} L_IJ z_J)
+    const int kg = tid >> 7, c = tid & (BM - 1);
+    // forward: z_I = Dinv_I (y_I - sum_{J<I} L_IJ z_J); rows of L are contiguous in k: one warp per row
     for (int I = 0; I < nb; ++I) {
         for (int r = warp; r < BM; r += nwarp) {
             const int gr = I * BM + r;
@@ -186,27 +203,38 @@ __global__ void __launch_bounds__(1024) solve_alpha_kernel(const double* __restr
             if (lane == 0) rhs[r] = gr < n ? y[gr] - s : 0.0;
         }
         __syncthreads();
-        if (tid < BM) {
+        for (int r = warp; r < BM; r += nwarp) {      // z_I[r] = Dinv_I[r][0..r] . rhs
             double s = 0.0;
-            for (int k = 0; k <= tid; ++k) s = fma(Dinv[((size_t)I * BM + tid) * BM + k], rhs[k], s);
-            z[I * BM + tid] = s;
+            for (int k = lane; k <= r; k += 32) s = fma(Dinv[((size_t)I * BM + r) * BM + k], rhs[k], s);
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+            if (lane == 0) z[I * BM + r] = s;
         }
         __syncthreads();
     }
-    // backward: a_I = Dinv_I^T (z_I - sum_{J>I} L_JI^T a_J)
+    // backward: a_I = Dinv_I^T (z_I - sum_{J>I} L_JI^T a_J); for a fixed row k of L the 128 columns of block I are
+    // contiguous: thread (kg, c) sums rows k = kg (mod 8)
     for (int I = nb - 1; I >= 0; --I) {
-        if (tid < BM) {
-            const int gc = I * BM + tid;
-            double s = 0.0;
-            if (gc < n)
-                for (int k = (I + 1) * BM; k < n; ++k) s = fma(L[(size_t)k * ld + gc], alpha[k], s);
-            rhs[tid] = z[I * BM + tid] - s;
-        }
+        const int gc = I * BM + c;
+        double s = 0.0;
+        if (gc < n)
+            for (int k = (I + 1) * BM + kg; k < n; k += 8) s = fma(L[(size_t)k * ld + gc], alpha[k], s);
+        part[kg][c] = s;
         __syncthreads();
         if (tid < BM) {
-            double s = 0.0;
-            for (int k = tid; k < BM; ++k) s = fma(Dinv[((size_t)I * BM + k) * BM + tid], rhs[k], s);
-            if (I * BM + tid < n) alpha[I * BM + tid] = s;
+            double t = 0.0;
+            for (int g = 0; g < 8; ++g) t += part[g][tid];
+            rhs[tid] = z[I * BM + tid] - t;
+        }
+        __syncthreads();
+        s = 0.0;                                         // a_I[c] = sum_{k >= c} Dinv_I[k][c] rhs[k]
+        for (int k = c + kg; k < BM; k += 8) s = fma(Dinv[((size_t)I * BM + k) * BM + c], rhs[k], s);
+        part[kg][c] = s;
+        __syncthreads();
+        if (tid < BM) {
+            double t = 0.0;
+            for (int g = 0; g < 8; ++g) t += part[g][tid];
+            if (I * BM + tid < n) alpha[I * BM + tid] = t;
         }
         __syncthreads();
     }
