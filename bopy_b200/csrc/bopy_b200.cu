@@ -200,6 +200,13 @@ int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, 
     gp->n_blocks = (int)((n + BM - 1) / BM);
     gp->n_pad = gp->n_blocks * BM;
     gp->sm_count = prop.multiProcessorCount;
+    {   // keep stream-ordered scratch (fit / LML / segment records) in the pool instead of returning it at every sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     const char* engine = std::getenv("BOPY_B200_F64_ENGINE");
     gp->fma64 = engine != nullptr && std::strcmp(engine, "fma") == 0;
     const size_t es = elem_size(dtype);
@@ -346,20 +353,20 @@ int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const do
     double *scratch = nullptr, *Aown = nullptr;
     int* status = nullptr;
     if (A == nullptr) {
-        CUDA_TRY(cudaMalloc(&Aown, (size_t)n * n * sizeof(double)));
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&Aown), (size_t)n * n * sizeof(double), st));
         A = Aown;
     }
-    cudaError_t e = cudaMalloc(&scratch, ((size_t)gp->n_pad + n) * sizeof(double) + 16);
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&scratch), ((size_t)gp->n_pad + n) * sizeof(double) + 16, st);
     if (e != cudaSuccess) {
-        cudaFree(Aown);
+        if (Aown) cudaFreeAsync(Aown, st);
         return fail(BOPY_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
     }
     double* z = scratch;
     double* alpha = alpha_out_dev != nullptr ? alpha_out_dev : scratch + gp->n_pad;
     status = reinterpret_cast<int*>(scratch + gp->n_pad + n);
     auto cleanup = [&]() {
-        cudaFree(Aown);
-        cudaFree(scratch);
+        if (Aown) cudaFreeAsync(Aown, st);
+        cudaFreeAsync(scratch, st);
     };
     cudaMemsetAsync(status, 0, sizeof(int), st);
     if (L_out_dev != nullptr) cudaMemsetAsync(L_out_dev, 0, (size_t)n * n * sizeof(double), st);  // zero upper triangle

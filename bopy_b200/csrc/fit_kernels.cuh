@@ -69,9 +69,25 @@ __global__ void __launch_bounds__(CHOL_NT) chol_block_kernel(double* A, int n, i
         if (tid == 0) dg[k] = lkk;        // the diagonal is collected aside so nobody races on sm[k][k]
         if (tid > k && tid < BM) sm[tid * LD + k] = sm[tid * LD + k] / lkk;
         __syncthreads();
-        for (int r = k + 1 + (tid >> 4); r < BM; r += CHOL_NT / 16) {
-            const double lrk = sm[r * LD + k];
-            for (int c = k + 1 + (tid & 15); c <= r; c += 16) sm[r * LD + c] = fma(-lrk, sm[c * LD + k], sm[r * LD + c]);
+        {
+            // each thread owns the (r, c) with (r-k-1) % 16 == tid/16 and (c-k-1) % 16 == tid%16; the column values
+            // it needs are loaded once, the row loop is unrolled so the shared-memory latencies overlap
+            const int c0 = k + 1 + (tid & 15);
+            double lck[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) lck[j] = (c0 + 16 * j < BM) ? sm[(c0 + 16 * j) * LD + k] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = k + 1 + (tid >> 4) + 16 * i;
+                if (r < BM) {
+                    const double lrk = sm[r * LD + k];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = c0 + 16 * j;
+                        if (c <= r) sm[r * LD + c] = fma(-lrk, lck[j], sm[r * LD + c]);
+                    }
+                }
+            }
         }
         __syncthreads();
     }
@@ -90,9 +106,16 @@ __global__ void __launch_bounds__(CHOL_NT) chol_block_kernel(double* A, int n, i
         const double xjj = 1.0 / col[j];
         if (tid == j) sm[j * LD + j] = xjj;
         if (tid > j && tid < BM) {
-            double s = 0.0;
-            for (int k = j + 1; k <= tid; ++k) s = fma(sm[tid * LD + k], col[k], s);
-            sm[tid * LD + j] = -xjj * s;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;   // four chains: the loop is latency bound
+            int k = j + 1;
+            for (; k + 3 <= tid; k += 4) {
+                s0 = fma(sm[tid * LD + k], col[k], s0);
+                s1 = fma(sm[tid * LD + k + 1], col[k + 1], s1);
+                s2 = fma(sm[tid * LD + k + 2], col[k + 2], s2);
+                s3 = fma(sm[tid * LD + k + 3], col[k + 3], s3);
+            }
+            for (; k <= tid; ++k) s0 = fma(sm[tid * LD + k], col[k], s0);
+            sm[tid * LD + j] = -xjj * ((s0 + s1) + (s2 + s3));
         }
         __syncthreads();
     }
