@@ -243,5 +243,65 @@ class B200GPSurrogate(Surrogate):
                                           index_base=index_base)
 
 
+class GPyGPSurrogate(B200GPSurrogate):
+    """GPy `GPRegression` surrogate whose posterior is evaluated by the B200 kernels (reference:
+    bopy/surrogate.py:94-146).
+
+    Same constructor and fit flow as the reference: `gp_initializer(x, y[:, None])` builds the GPy model on the
+    first fit, `set_XY` updates it afterwards, `optimize_restarts(n_restarts)` tunes it on the host.  The fitted
+    state GPy keeps for `predict_noiseless` -- `posterior.woodbury_chol` (Cholesky factor of K + sigma^2 I),
+    `posterior.woodbury_vector` (K^-1 y), kernel variance / lengthscale, the target normalizer -- is then installed on
+    the device, and `predict` / the fused acquisitions run there (noise-free predictive variance, as
+    `predict_noiseless(full_cov=True)` returns).
+
+    GPy is not installed in the image this was written in: the attribute names above follow GPy 1.x and the class is
+    exercised in the tests with a duck-typed stand-in for the GPy model, not with GPy itself.
+    """
+
+    _KERNELS = {"rbf": "rbf", "Mat32": "matern32", "Mat52": "matern52", "Exponential": "matern12"}
+
+    def __init__(self, gp_initializer, n_restarts: int = 1, dtype: str = "f64", device=None):
+        Surrogate.__init__(self)
+        if dtype not in ("f64", "f32"):
+            raise ValueError("dtype must be 'f64' or 'f32'")
+        self.gp_initializer = gp_initializer
+        self.n_restarts = n_restarts
+        self.gp = None
+        self.dtype, self.device, self.device_fit = dtype, device, False
+        self.native, self.kernel_spec, self.fitted_on_device = None, None, False
+
+    def _fit(self, x: np.ndarray, y: np.ndarray) -> None:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", DeprecationWarning)
+            if self.gp is None:
+                self.gp = self.gp_initializer(x, y.reshape(-1, 1))
+            else:
+                self.gp.set_XY(x, y.reshape(-1, 1))
+        self.gp.optimize_restarts(self.n_restarts)
+        self.load_fitted_state()
+
+    def load_fitted_state(self) -> None:
+        from .kernel_spec import FlatKernel, UnsupportedKernelError
+        gp = self.gp
+        kern = gp.kern
+        name = getattr(kern, "name", type(kern).__name__)
+        if name not in self._KERNELS:
+            raise UnsupportedKernelError(f"GPy kernel {name!r} is not supported (rbf, Mat32, Mat52, Exponential are)")
+        spec = FlatKernel(kernel=self._KERNELS[name],
+                          length_scale=np.atleast_1d(np.asarray(kern.lengthscale, dtype=np.float64)).ravel().copy(),
+                          amplitude=float(np.ravel(kern.variance)[0]), noise_level=0.0)
+        X = np.ascontiguousarray(np.asarray(gp.X), dtype=np.float64)
+        n, d = X.shape
+        L = np.ascontiguousarray(np.asarray(gp.posterior.woodbury_chol), dtype=np.float64)
+        alpha = np.asarray(gp.posterior.woodbury_vector, dtype=np.float64).reshape(-1)
+        normalizer = getattr(gp, "normalizer", None)
+        y_mean = float(np.ravel(normalizer.mean)[0]) if normalizer is not None else 0.0
+        y_std = float(np.ravel(normalizer.std)[0]) if normalizer is not None else 1.0
+        self._native_for(n, d, spec.kernel).set_state(X, L, alpha, spec.length_scale, amplitude=spec.amplitude,
+                                                      noise_level=0.0, y_mean=y_mean, y_std=y_std)
+        self.kernel_spec = spec
+
+
 # Drop-in name: code written against the reference keeps working and runs on the B200.
 ScipyGPSurrogate = B200GPSurrogate

@@ -291,3 +291,64 @@ class TestMultiStart:
 def torch_as(a, device):
     import torch
     return torch.as_tensor(a, dtype=torch.int64, device=device)
+
+
+class FakeGPyModel:
+    """Duck-typed stand-in for GPy.models.GPRegression (GPy is not installed): exposes exactly the attributes
+    GPyGPSurrogate reads, computed with the oracle from the same definitions GPy uses."""
+
+    class _Kern:
+        name = "rbf"
+
+        def __init__(self, variance, lengthscale):
+            self.variance, self.lengthscale = np.array([variance]), np.array([lengthscale])
+
+    class _Norm:
+        def __init__(self, y):
+            self.mean, self.std = y.mean(), y.std()
+
+    class _Posterior:
+        pass
+
+    def __init__(self, x, y, variance=1.3, lengthscale=0.25, noise_var=1e-5):
+        self.kern = self._Kern(variance, lengthscale)
+        self.noise_var = noise_var
+        self.optimized = 0
+        self.set_XY(x, y)
+
+    def set_XY(self, x, y):
+        self.X, self.Y = x, y
+        self.normalizer = self._Norm(y)
+        spec = O.KernelSpec(kind="rbf", length_scale=self.kern.lengthscale, amplitude=float(self.kern.variance[0]))
+        st = O.fit_state(x, y.ravel(), spec, self.noise_var, normalize_y=True)
+        self.posterior = self._Posterior()
+        self.posterior.woodbury_chol, self.posterior.woodbury_vector = st.L, st.alpha[:, None]
+        self._state = st
+
+    def optimize_restarts(self, n):
+        self.optimized += n
+
+    def predict_noiseless(self, x, full_cov=True):
+        mean, cov = O.posterior_full(self._state, x)
+        return mean[:, None], cov
+
+
+def test_gpy_surrogate_with_a_duck_typed_model():
+    from bopy_b200.surrogate import GPyGPSurrogate
+    xx = np.linspace(0, 1, 10).reshape(-1, 1)
+    yy = forrester(xx)
+    sur = GPyGPSurrogate(gp_initializer=lambda x, y: FakeGPyModel(x, y), n_restarts=2)
+    with pytest.raises(Exception, match="must be fitted first"):
+        sur.predict(xx)
+    sur.fit(xx, yy)
+    assert sur.gp.optimized == 2 and sur.x is xx
+    grid = np.linspace(0, 1, 77).reshape(-1, 1)
+    mean, cov = sur.predict(grid)
+    ref_mean, ref_cov = sur.gp.predict_noiseless(grid, full_cov=True)
+    np.testing.assert_allclose(mean, ref_mean.ravel(), rtol=1e-9, atol=1e-9 * yy.std())
+    np.testing.assert_allclose(cov, ref_cov, rtol=1e-8, atol=1e-11 * yy.var() * 1.3)
+    sur.fit(xx[:7], yy[:7])                      # refit goes through set_XY and a new device state
+    assert sur.gp.optimized == 4 and len(sur.gp.X) == 7
+    lcb = LCB(sur)
+    lcb.fit(xx[:7], yy[:7])
+    assert lcb(grid).shape == (77,)
