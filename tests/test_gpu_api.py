@@ -352,3 +352,21 @@ def test_gpy_surrogate_with_a_duck_typed_model():
     lcb = LCB(sur)
     lcb.fit(xx[:7], yy[:7])
     assert lcb(grid).shape == (77,)
+
+
+def test_examples_run_end_to_end():
+    """BASELINE configs C1 / C2 (examples/example_1d.py, examples/example_batch_1d.py)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lines = []
+    for name in ("example_1d", "example_batch_1d"):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, "examples", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        np.random.seed(0)
+        res = mod.main(out=lines.append)
+        assert res.x_opt.shape == (1, 1) and 0.0 <= res.x_opt[0, 0] <= 1.0
+        assert res.f_opt <= -0.9                      # both find at least the Forrester local basin
+    one_d = importlib.util.spec_from_file_location("e1", os.path.join(root, "examples", "example_1d.py"))
+    assert any("optimum found" in l for l in lines) and any("batch proposed" in l for l in lines)
