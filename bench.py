@@ -200,6 +200,8 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # whatever NCCL_DEBUG level the environment asks for goes to a file: stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/bopy_b200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     n, d, m = args.n, args.d, args.candidates
