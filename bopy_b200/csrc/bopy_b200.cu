@@ -62,8 +62,9 @@ struct bopy_gp {
 namespace {
 
 
-template <class E, int KIND> int launch_sweep_t(const SweepParams& p, int grid, cudaStream_t st) {
+template <class E, int KIND> int launch_sweep_t(SweepParams p, int grid, cudaStream_t st) {
     const size_t smem = sweep_smem_bytes<E>(p.d);
+    p.xrow_separate = sweep_xrow_separate<E>(p.d) ? 1 : 0;
     CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<E, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sweep_kernel<E, KIND><<<grid, NT_ALL, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());

@@ -49,6 +49,7 @@ struct SweepParams {
     long long index_base;
     MinLoc* partials;   // [gridDim.x] or nullptr when no arg-min is wanted
     MinLoc* tile_records;  // [ntiles] per-tile arg-min records (for segmented arg-min) or nullptr
+    int xrow_separate;  // 1: the X/l block row has its own shared-memory buffer and is prefetched one row ahead
 };
 
 // base kernel as sklearn evaluates it from the squared scaled distance
@@ -166,17 +167,19 @@ struct DmmaPolicy {
     __device__ explicit DmmaPolicy(int tid) {
         lane = tid & 31;
         const int warp = tid >> 5;
-        rg = warp >> 1;   // row atoms rg, rg+4, rg+8, rg+12 (8 rows each): balanced triangular work
+        rg = warp >> 1;   // owns the 8-row atoms {rg, 7-rg, 8+rg, 15-rg}: in the triangular diagonal GEMM atom a needs
+                          // a+1 k-tiles, and each of the four sets sums to the same 34 tile-visits
         cg = warp & 1;    // candidates 64*cg .. 64*cg+63
         part = rg;
         leader = (lane >> 2) == 0;
         const int kq = lane & 3, q8 = lane >> 2;
 #pragma unroll
-        for (int i = 0; i < RI; ++i) aoff[i] = a_index(kq, 8 * (rg + 4 * i) + q8);
+        for (int i = 0; i < RI; ++i) aoff[i] = a_index(kq, 8 * atom(i) + q8);
 #pragma unroll
         for (int jj = 0; jj < CJ / 2; ++jj) boff[jj] = b_index(kq, 64 * cg + 8 * jj + q8);
     }
-    __device__ __forceinline__ int row_of(int i) const { return 8 * (rg + 4 * i) + (lane >> 2); }
+    __device__ __forceinline__ int atom(int i) const { return (i & 2) * 4 + ((i & 1) ? 7 - rg : rg); }
+    __device__ __forceinline__ int row_of(int i) const { return 8 * atom(i) + (lane >> 2); }
     __device__ __forceinline__ int cand_of(int j) const { return 64 * cg + 8 * (j >> 1) + 2 * (lane & 3) + (j & 1); }
     // XOR swizzle on the 128-wide axis keyed by k%4: the 4 x 8 fragment gather of a half-warp hits 32 banks
     __host__ __device__ static __forceinline__ int a_index(int k, int r) { return k * BM + (r ^ (4 * (k & 3))); }
@@ -187,7 +190,7 @@ struct DmmaPolicy {
         v += __shfl_xor_sync(0xffffffffu, v, 16);
         return v;
     }
-    // DIAG: inv(L_II) is lower triangular, so row atom (rg+4i) only needs the k tiles kc <= its own index
+    // DIAG: inv(L_II) is lower triangular, so row atom a only needs the k tiles kc <= a
     template <bool DIAG>
     __device__ __forceinline__ void mma_tile(double (&acc)[RI][CJ], const double* __restrict__ As,
                                              const double* __restrict__ Bs, int kc) const {
@@ -200,7 +203,7 @@ struct DmmaPolicy {
             for (int i = 0; i < RI; ++i) a[i] = As[aoff[i] + s * 4 * BM];
 #pragma unroll
             for (int i = 0; i < RI; ++i) {
-                if (DIAG && rg + 4 * i < kc) continue;   // warp-uniform
+                if (DIAG && atom(i) < kc) continue;   // warp-uniform
 #pragma unroll
                 for (int jj = 0; jj < CJ / 2; ++jj) dmma_m8n8k4(acc[i][2 * jj], acc[i][2 * jj + 1], a[i], b[jj]);
             }
@@ -234,9 +237,17 @@ using EngineF64 = Engine<DmmaPolicy, DmmaPolicy>;
 using EngineF64Fma = Engine<FmaPolicy<double>, FmaPolicy<double>>;
 using EngineMixed = Engine<FmaPolicy<float>, DmmaPolicy>;
 
-template <class E> constexpr size_t sweep_smem_bytes(int d) {
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+template <class E> constexpr size_t sweep_smem_base(int d) {
     return (size_t)2 * STAGES * TILE_BYTES + (size_t)BM * BN * sizeof(typename E::TD) +
            (size_t)d * BN * sizeof(double) + 192;
+}
+// the block row of X/l + alpha gets a buffer of its own (prefetched a row ahead) whenever shared memory allows
+template <class E> constexpr bool sweep_xrow_separate(int d) {
+    return sweep_smem_base<E>(d) + (size_t)(d + 1) * BM * sizeof(double) <= SMEM_LIMIT;
+}
+template <class E> constexpr size_t sweep_smem_bytes(int d) {
+    return sweep_smem_base<E>(d) + (sweep_xrow_separate<E>(d) ? (size_t)(d + 1) * BM * sizeof(double) : 0);
 }
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
@@ -261,7 +272,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
     unsigned char* const stB = smem_raw + STAGES * TILE_BYTES;           // [STAGES] B tiles (V_J)
     unsigned char* const rs_raw = smem_raw + 2 * STAGES * TILE_BYTES;
     TD* const Rs = reinterpret_cast<TD*>(rs_raw);                        // [BM][BN] residual tile (B operand of the diagonal GEMM)
-    double* const xrow = reinterpret_cast<double*>(rs_raw);              // aliases Rs: [(d+1)][BM] X/l block row + alpha
+    // [(d+1)][BM] X/l block row + alpha: own buffer behind the barriers when it fits, else aliasing Rs
+    double* const xrow_alias = reinterpret_cast<double*>(rs_raw);
     double* const partM = reinterpret_cast<double*>(rs_raw + 48 * 1024); // aliases Rs: [4][BN]
     double* const partS = reinterpret_cast<double*>(rs_raw + 52 * 1024); // aliases Rs: [4][BN]
     double* const xs_s = reinterpret_cast<double*>(rs_raw + (size_t)BM * BN * sizeof(TD));  // [d][BN] candidates / l
@@ -271,6 +283,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
     uint64_t* const xbar = empty + STAGES;                               // block row of X/l + alpha landed
     uint64_t* const vbar = xbar + 1;                                     // V_I published to the workspace
     MinLoc* const red = reinterpret_cast<MinLoc*>(tail + 128);           // [4]
+    double* const xrow = p.xrow_separate ? reinterpret_cast<double*>(tail + 192) : xrow_alias;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_pad = p.n_blocks * BM;
@@ -346,7 +359,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
             bulk_g2s(xrow, p.Xt + (long long)I * (p.d + 1) * BM, bytes, xbar);
         };
 
-        if (tid == 0) issue_xrow(0);
+        if (tid == 0 && !(p.xrow_separate && tile != blockIdx.x)) issue_xrow(0);   // (prefetched by the previous tile)
         // stage this tile's candidates, scaled like sklearn does (X / length_scale), dimension-major
         for (int e = tid; e < BN * p.d; e += NT) {
             const int c = e / p.d, q = e - c * p.d;
@@ -409,6 +422,10 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
                 consumer_sync();
                 if (tid < BN) mean_c += ((partM[tid] + partM[BN + tid]) + partM[2 * BN + tid]) + partM[3 * BN + tid];
                 consumer_sync();  // xrow / partM consumed: Rs may be overwritten from here on
+                if (p.xrow_separate && tid == 0) {   // prefetch the next block row (or the next tile's first) of X/l
+                    if (I + 1 < p.n_blocks) issue_xrow(I + 1);
+                    else if (tile + gridDim.x < p.ntiles) issue_xrow(0);
+                }
                 if constexpr (E::kMixed) {
                     // fp64 residual tile R lives in shared memory (diagonal policy's B layout); every thread owns the
                     // same elements throughout, so the read-modify-write flushes below need no barrier
@@ -510,8 +527,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
             }
             consumer_sync();   // every warp finished the diagonal GEMM (Rs reads) and published its part of V_I
             if (tid == 0 && I + 1 < p.n_blocks) {
-                mbar_arrive(vbar);       // producer may now load V_I
-                issue_xrow(I + 1);       // lands in the (now free) Rs region
+                mbar_arrive(vbar);                          // producer may now load V_I
+                if (!p.xrow_separate) issue_xrow(I + 1);    // lands in the (now free) Rs region
             }
             if (tid < BN) ss_c += ((partS[tid] + partS[BN + tid]) + partS[2 * BN + tid]) + partS[3 * BN + tid];
         }
