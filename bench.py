@@ -40,6 +40,12 @@ METRIC = "fused posterior+EI candidate evals/sec (n=2048, d=6)"
 UNIT = "evals/s"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE sweep_kernel launch from `ncu --set full` at the default workload
+# (profiles/r01/ncu_sweep_v3_f64_dmma_fullsize_summary.json): 191.7 GB read + 32.2 GB written, all of it re-reads /
+# writes of the per-CTA V workspace (L2 hit rate 53 %).  Other workloads: not captured -> null.
+NCU_TRAFFIC_BYTES = {(2048, 6, "f64", 1 << 21): 223.9e9}
+
+
 def flops_per_candidate(n, d):
     return n * n + n * (3 * d + 5)
 
@@ -313,7 +319,8 @@ def run_b200(args):
                        "(MEASURED_PEAKS.json holds only HBM and bf16 peaks; the path is FP-pipe bound, SURVEY.md 8d)",
         "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
         "flops_per_candidate": F, "candidates_per_launch": m, "kernel_ms": kernel_ms,
-        "traffic": None,
+        "traffic": NCU_TRAFFIC_BYTES.get((n, d, args.dtype, m)),
+        "traffic_note": "ncu dram bytes per launch; V workspace re-reads (0.78 TB/s, 12 % of HBM peak), kernel is FP64-pipe bound",
         "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (kernel_ms * 1e-3) / 1e9,
                 "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if measured else "fallback"},
         "measured_peaks_tflops": peaks_all,
