@@ -52,17 +52,48 @@ struct SweepParams {
     int xrow_separate;  // 1: the X/l block row has its own shared-memory buffer and is prefetched one row ahead
 };
 
+// exp(x) for x <= 0, branch-free so that the 64 evaluations a thread makes per block row interleave instead of
+// serialising on libdevice's special-case branches (the kernel-tile step was latency bound on them).
+// 2^k * exp(r), k = rint(x log2 e) by the 1.5*2^52 trick, r = x - k ln2 (hi/lo), degree-13 Taylor polynomial on
+// |r| <= ln2/2 (truncation 4e-18): <= 1.01 ulp against np.exp over [-708, 0] (restated in tools/exp_study.py).
+// Below -708 the true value is a denormal < 2.5e-308: returned as 0.  NaN propagates.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double xc = fmax(x, -708.0);
+    const double t = fma(xc, 1.4426950408889634, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, xc);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));   // * 2^k, k in [-1022, 0]
+    res = x < -708.0 ? 0.0 : res;
+    return x != x ? x : res;
+}
+
 // base kernel as sklearn evaluates it from the squared scaled distance
 template <int KIND> __device__ __forceinline__ double base_kernel(double d2) {
-    if (KIND == K_RBF) return exp(-0.5 * d2);
+    if (KIND == K_RBF) return exp_nonpos(-0.5 * d2);
     const double r = sqrt(d2);
-    if (KIND == K_M12) return exp(-r);
+    if (KIND == K_M12) return exp_nonpos(-r);
     if (KIND == K_M32) {
         const double k = r * 1.7320508075688772;  // math.sqrt(3)
-        return (1.0 + k) * exp(-k);
+        return (1.0 + k) * exp_nonpos(-k);
     }
     const double k = r * 2.23606797749979;        // math.sqrt(5)
-    return __dadd_rn(__dadd_rn(1.0, k), __ddiv_rn(__dmul_rn(k, k), 3.0)) * exp(-k);
+    return __dadd_rn(__dadd_rn(1.0, k), __ddiv_rn(__dmul_rn(k, k), 3.0)) * exp_nonpos(-k);
 }
 
 // scipy.special.ndtr (cephes): 0.5*erfc(-a/sqrt(2)) evaluated the way scipy branches it
@@ -393,8 +424,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
                     for (int i = 0; i < PG::RI; ++i)
 #pragma unroll
                         for (int j = 0; j < PG::CJ; ++j) {
-                            const double df = __dadd_rn(xc[j], -xr[i]);
-                            d2[i][j] = __dadd_rn(d2[i][j], __dmul_rn(df, df));  // cdist order, unfused
+                            const double df = xc[j] - xr[i];
+                            d2[i][j] = fma(df, df, d2[i][j]);   // cdist's summation order over the dimensions
                         }
                 }
                 double mp[PG::CJ];

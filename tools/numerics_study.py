@@ -67,3 +67,4 @@ print(f"fp32 strtrs: rel dvar max {rel.max():.3e} median {np.median(rel):.3e}; a
 mean_ref = Kt @ gp.alpha_
 mean32 = (Kt.astype(np.float32) @ gp.alpha_.astype(np.float32)).astype(np.float64)
 print("fp32 mean: max abs err", np.max(np.abs(mean32 - mean_ref)), " |alpha|max", np.abs(gp.alpha_).max(), "mean range", mean_ref.min(), mean_ref.max())
+
