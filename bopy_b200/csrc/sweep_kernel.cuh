@@ -55,7 +55,7 @@ struct SweepParams {
 // exp(x) for x <= 0, branch-free so that the 64 evaluations a thread makes per block row interleave instead of
 // serialising on libdevice's special-case branches (the kernel-tile step was latency bound on them).
 // 2^k * exp(r), k = rint(x log2 e) by the 1.5*2^52 trick, r = x - k ln2 (hi/lo), degree-13 Taylor polynomial on
-// |r| <= ln2/2 (truncation 4e-18): <= 1.01 ulp against np.exp over [-708, 0] (restated in tools/exp_study.py).
+// |r| <= ln2/2 (truncation 4e-18): <= 2 ulp against np.exp over [-708, 0] (restated in tools/exp_study.py).
 // Below -708 the true value is a denormal < 2.5e-308: returned as 0.  NaN propagates.
 __device__ __forceinline__ double exp_nonpos(double x) {
     const double xc = fmax(x, -708.0);
@@ -64,20 +64,18 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     const double kd = t - 6755399441055744.0;
     double r = fma(kd, -6.93147180369123816490e-01, xc);
     r = fma(kd, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;            // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    // degree-13 Taylor polynomial, Estrin's scheme: depth 4 instead of Horner's 14 dependent FMAs
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = 1.0 + r;                                                     // 1/0! + r/1!
+    const double a1 = fma(1.6666666666666666e-01, r, 0.5);                         // 1/2! + r/3!
+    const double a2 = fma(8.333333333333333e-03, r, 4.1666666666666664e-02);       // 1/4! + r/5!
+    const double a3 = fma(1.984126984126984e-04, r, 1.388888888888889e-03);        // 1/6! + r/7!
+    const double a4 = fma(2.7557319223985893e-06, r, 2.48015873015873e-05);        // 1/8! + r/9!
+    const double a5 = fma(2.505210838544172e-08, r, 2.755731922398589e-07);        // 1/10! + r/11!
+    const double a6 = fma(1.6059043836821613e-10, r, 2.08767569878681e-09);        // 1/12! + r/13!
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+    const double c0 = fma(b1, r4, b0), c1 = fma(a6, r4, b2);
+    const double p = fma(c1, r8, c0);
     double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));   // * 2^k, k in [-1022, 0]
     res = x < -708.0 ? 0.0 : res;
     return x != x ? x : res;
@@ -409,39 +407,46 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
             mbar_wait(xbar, xphase);
             xphase ^= 1;
             {
-                double d2[PG::RI][PG::CJ];
-#pragma unroll
-                for (int i = 0; i < PG::RI; ++i)
-#pragma unroll
-                    for (int j = 0; j < PG::CJ; ++j) d2[i][j] = 0.0;
-                for (int q = 0; q < p.d; ++q) {
-                    double xr[PG::RI], xc[PG::CJ];
-#pragma unroll
-                    for (int i = 0; i < PG::RI; ++i) xr[i] = xrow[q * BM + pg.row_of(i)];
-#pragma unroll
-                    for (int j = 0; j < PG::CJ; ++j) xc[j] = xs_s[q * BN + pg.cand_of(j)];
-#pragma unroll
-                    for (int i = 0; i < PG::RI; ++i)
-#pragma unroll
-                        for (int j = 0; j < PG::CJ; ++j) {
-                            const double df = xc[j] - xr[i];
-                            d2[i][j] = fma(df, df, d2[i][j]);   // cdist's summation order over the dimensions
-                        }
-                }
+                // two halves of the thread's rows: 32 squared distances live at a time leave the scheduler enough
+                // registers to interleave the (branch-free) kernel evaluations
+                constexpr int RH = PG::RI / 2;
+                double kq[E::kMixed ? PG::RI : 1][E::kMixed ? PG::CJ : 1];   // mixed engine: K* stays fp64
                 double mp[PG::CJ];
 #pragma unroll
                 for (int j = 0; j < PG::CJ; ++j) mp[j] = 0.0;
 #pragma unroll
-                for (int i = 0; i < PG::RI; ++i) {
-                    const int row = pg.row_of(i);
-                    const bool live = I * BM + row < p.n;
-                    const double a_i = xrow[p.d * BM + row];
+                for (int h = 0; h < 2; ++h) {
+                    double d2[RH][PG::CJ];
 #pragma unroll
-                    for (int j = 0; j < PG::CJ; ++j) {
-                        const double kv = live ? __dmul_rn(p.amp, base_kernel<KIND>(d2[i][j])) : 0.0;
-                        d2[i][j] = kv;   // mixed engine: K* stays fp64 until it seeds the residual tile
-                        acc[i][j] = E::kMixed ? static_cast<TG>(0) : static_cast<TG>(kv);
-                        mp[j] = fma(kv, a_i, mp[j]);
+                    for (int i = 0; i < RH; ++i)
+#pragma unroll
+                        for (int j = 0; j < PG::CJ; ++j) d2[i][j] = 0.0;
+                    for (int q = 0; q < p.d; ++q) {
+                        double xr[RH], xc[PG::CJ];
+#pragma unroll
+                        for (int i = 0; i < RH; ++i) xr[i] = xrow[q * BM + pg.row_of(h * RH + i)];
+#pragma unroll
+                        for (int j = 0; j < PG::CJ; ++j) xc[j] = xs_s[q * BN + pg.cand_of(j)];
+#pragma unroll
+                        for (int i = 0; i < RH; ++i)
+#pragma unroll
+                            for (int j = 0; j < PG::CJ; ++j) {
+                                const double df = xc[j] - xr[i];
+                                d2[i][j] = fma(df, df, d2[i][j]);   // cdist's summation order over the dimensions
+                            }
+                    }
+#pragma unroll
+                    for (int i = 0; i < RH; ++i) {
+                        const int row = pg.row_of(h * RH + i);
+                        const bool live = I * BM + row < p.n;
+                        const double a_i = xrow[p.d * BM + row];
+#pragma unroll
+                        for (int j = 0; j < PG::CJ; ++j) {
+                            const double kv = live ? __dmul_rn(p.amp, base_kernel<KIND>(d2[i][j])) : 0.0;
+                            if constexpr (E::kMixed) kq[h * RH + i][j] = kv;
+                            acc[h * RH + i][j] = E::kMixed ? static_cast<TG>(0) : static_cast<TG>(kv);
+                            mp[j] = fma(kv, a_i, mp[j]);
+                        }
                     }
                 }
 #pragma unroll
@@ -466,7 +471,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
 #pragma unroll
                         for (int jv = 0; jv < PG::CJ / 2; ++jv)
                             *reinterpret_cast<double2*>(&Rs[PD::b_index(row, pg.cand_of(jv * 2))]) =
-                                make_double2(d2[i][jv * 2], d2[i][jv * 2 + 1]);
+                                make_double2(kq[i][jv * 2], kq[i][jv * 2 + 1]);
                     }
                 }
             }
