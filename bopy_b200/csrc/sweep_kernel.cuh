@@ -438,11 +438,13 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
 #pragma unroll
                     for (int i = 0; i < RH; ++i) {
                         const int row = pg.row_of(h * RH + i);
-                        const bool live = I * BM + row < p.n;
+                        // rows beyond n (identity padding) get amplitude 0: no branch, so that all the kernel
+                        // evaluations of a half stay in one basic block and the scheduler interleaves them
+                        const double amp_i = (I * BM + row < p.n) ? p.amp : 0.0;
                         const double a_i = xrow[p.d * BM + row];
 #pragma unroll
                         for (int j = 0; j < PG::CJ; ++j) {
-                            const double kv = live ? __dmul_rn(p.amp, base_kernel<KIND>(d2[i][j])) : 0.0;
+                            const double kv = __dmul_rn(amp_i, base_kernel<KIND>(d2[i][j]));
                             if constexpr (E::kMixed) kq[h * RH + i][j] = kv;
                             acc[h * RH + i][j] = E::kMixed ? static_cast<TG>(0) : static_cast<TG>(kv);
                             mp[j] = fma(kv, a_i, mp[j]);
