@@ -155,11 +155,10 @@ template <typename T> struct FmaPolicy {
         v += __shfl_xor_sync(0xffffffffu, v, 16);
         return v;
     }
-    __device__ __forceinline__ int active_atoms(int /*valid*/) const { return 8; }   // no partial-tile skipping
     // acc += A (x) B over one tile; DIAG marks tile kc of the diagonal GEMM (dense here)
-    template <bool DIAG, bool PARTIAL = false>
+    template <bool DIAG>
     __device__ __forceinline__ void mma_tile(T (&acc)[RI][CJ], const T* __restrict__ As, const T* __restrict__ Bs,
-                                             int /*kc*/, int /*nact*/ = 8) const {
+                                             int /*kc*/) const {
         using V = typename VecOf<T>::type;
         constexpr int NV = 8 / VEC;
 #pragma unroll
@@ -220,17 +219,10 @@ struct DmmaPolicy {
         v += __shfl_xor_sync(0xffffffffu, v, 16);
         return v;
     }
-    // number of this warp's 8-candidate atoms that hold real candidates when only `valid` of the tile's 128 do
-    __device__ __forceinline__ int active_atoms(int valid) const {
-        const int a = (valid - 64 * cg + 7) >> 3;
-        return a < 0 ? 0 : (a > CJ / 2 ? CJ / 2 : a);
-    }
-    // DIAG: inv(L_II) is lower triangular, so row atom a only needs the k tiles kc <= a.
-    // PARTIAL: the tile is the ragged tail of a candidate set; only the first nact candidate atoms are multiplied
-    // (a 1-candidate call costs 1/16 of a full tile's MMA work instead of all of it).
-    template <bool DIAG, bool PARTIAL = false>
+    // DIAG: inv(L_II) is lower triangular, so row atom a only needs the k tiles kc <= a
+    template <bool DIAG>
     __device__ __forceinline__ void mma_tile(double (&acc)[RI][CJ], const double* __restrict__ As,
-                                             const double* __restrict__ Bs, int kc, int nact = CJ / 2) const {
+                                             const double* __restrict__ Bs, int kc) const {
 #pragma unroll
         for (int s = 0; s < KC / 4; ++s) {
             double a[RI], b[CJ / 2];
@@ -242,10 +234,7 @@ struct DmmaPolicy {
             for (int i = 0; i < RI; ++i) {
                 if (DIAG && atom(i) < kc) continue;   // warp-uniform
 #pragma unroll
-                for (int jj = 0; jj < CJ / 2; ++jj) {
-                    if (PARTIAL && jj >= nact) continue;   // warp-uniform
-                    dmma_m8n8k4(acc[i][2 * jj], acc[i][2 * jj + 1], a[i], b[jj]);
-                }
+                for (int jj = 0; jj < CJ / 2; ++jj) dmma_m8n8k4(acc[i][2 * jj], acc[i][2 * jj + 1], a[i], b[jj]);
             }
         }
     }
@@ -390,9 +379,6 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
 
     for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const long long c0 = tile * BN;
-        const int valid = (int)(p.m - c0 < BN ? p.m - c0 : BN);   // real candidates in this tile
-        const bool partial = valid < BN;
-        const int nact_g = pg.active_atoms(valid), nact_d = pd.active_atoms(valid);
         TG* const Vt = reinterpret_cast<TG*>(reinterpret_cast<unsigned char*>(p.Vws) +
                                              (p.slot_per_tile ? tile : (long long)blockIdx.x) * slot_bytes);
 
@@ -428,16 +414,6 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
                 double mp[PG::CJ];
 #pragma unroll
                 for (int j = 0; j < PG::CJ; ++j) mp[j] = 0.0;
-                if (nact_g == 0) {   // ragged tail tile: none of this warp's candidates is real
-#pragma unroll
-                    for (int i = 0; i < PG::RI; ++i)
-#pragma unroll
-                        for (int j = 0; j < PG::CJ; ++j) {
-                            acc[i][j] = static_cast<TG>(0);
-                            if constexpr (E::kMixed) kq[i][j] = 0.0;
-                        }
-                }
-                if (nact_g != 0)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     double d2[RH][PG::CJ];
@@ -506,12 +482,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
             for (int t = 0; t < T_gemm; ++t, ++gcount) {
                 const uint32_t stage = gcount % STAGES;
                 mbar_wait(&full[stage], (gcount / STAGES) & 1u);
-                if (!partial)
-                    pg.template mma_tile<false, false>(acc, reinterpret_cast<const TG*>(stA + stage * TILE_BYTES),
-                                                       reinterpret_cast<const TG*>(stB + stage * TILE_BYTES), -1);
-                else
-                    pg.template mma_tile<false, true>(acc, reinterpret_cast<const TG*>(stA + stage * TILE_BYTES),
-                                                      reinterpret_cast<const TG*>(stB + stage * TILE_BYTES), -1, nact_g);
+                pg.template mma_tile<false>(acc, reinterpret_cast<const TG*>(stA + stage * TILE_BYTES),
+                                            reinterpret_cast<const TG*>(stB + stage * TILE_BYTES), -1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage
                 if constexpr (E::kMixed) {
@@ -556,12 +528,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
             for (int kc = 0; kc < CHD; ++kc, ++gcount) {
                 const uint32_t stage = gcount % STAGES;
                 mbar_wait(&full[stage], (gcount / STAGES) & 1u);
-                if (!partial)
-                    pd.template mma_tile<true, false>(accd, reinterpret_cast<const TD*>(stA + stage * TILE_BYTES),
-                                                      Rs + kc * PD::KC * BN, kc);
-                else
-                    pd.template mma_tile<true, true>(accd, reinterpret_cast<const TD*>(stA + stage * TILE_BYTES),
-                                                     Rs + kc * PD::KC * BN, kc, nact_d);
+                pd.template mma_tile<true>(accd, reinterpret_cast<const TD*>(stA + stage * TILE_BYTES),
+                                           Rs + kc * PD::KC * BN, kc);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
             }
