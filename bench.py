@@ -14,8 +14,9 @@ min-loc exchange between ranks.  One JSON line is printed by rank 0.
 value   : candidates/s with the candidates already resident in HBM.
 e2e     : the same through the public API with HOST candidates in pinned memory: H2D copy, sweep, D2H of the
           (index, value) result inside the timed region.
-roofline: the sweep kernel is FP64-FMA bound (F(n,d) = n^2 + n(3d+5) flops per candidate,
-          48 B of HBM traffic per candidate); peak = DFMA rate measured live by bopy_measure_peak.
+roofline: the sweep kernel is bound by the FP64 tensor sub-pipe (DMMA) (F(n,d) = n^2 + n(3d+5)
+          flops per candidate against 48 B of HBM input); peak = max(DFMA, DMMA) rate measured live by
+          bopy_measure_peak (MEASURED_PEAKS.json has no FP64 figure).
 cpu_baseline / --impl reference: bopy's own call sequence (sklearn predict(return_cov=True) -> np.diag ->
           scipy.stats.norm EI, 64 candidates per call = the reference's best chunk) on this box's host cores.
 """
@@ -312,7 +313,9 @@ def run_b200(args):
     hbm_peak = measured.get("hbm_gbs", 6650.0)
     algo_bytes = m * d * 8 + 16
     roofline = {
-        "bound": "fp64 pipe (DMMA)" if args.dtype == "f64" else "fp32 FMA pipe (fp64 DMMA for the diagonal solve)",
+        "bound": "tensor" if args.dtype == "f64" else "fp32_fma",
+        "pipe": ("FP64 tensor sub-pipe (mma.sync.m8n8k4.f64 = SASS DMMA; tcgen05 has no f64 kind)" if args.dtype == "f64"
+                 else "FP32 FMA pipe for the off-diagonal GEMM, FP64 DMMA for the diagonal solve"),
         "kernel": "sweep_kernel",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "peak_source": "bopy_measure_peak: register-resident DFMA / DMMA / FFMA loops measured live on this GPU "

@@ -137,14 +137,18 @@ class NativeGP:
         check(self.lib.bopy_gp_create(byref(handle), self.device.index, self.dtype, KERNEL_IDS[kernel], self.n, self.d),
               "bopy_gp_create")
         self._handle = handle
-        self._keep = None
 
     def close(self):
-        if getattr(self, "_handle", None):
-            self.lib.bopy_gp_destroy(self._handle)
-            self._handle = None
+        """Free the handle's device memory (idempotent)."""
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            try:
+                self.lib.bopy_gp_destroy(handle)
+            except Exception:      # interpreter shutdown: the library may already be gone
+                pass
 
-    __del__ = close
+    def __del__(self):
+        self.close()
 
     def _dev64(self, a, shape=None):
         import numpy as np

@@ -8,7 +8,7 @@ namespace bopy {
 // ---- tile geometry of the blocked solve ------------------------------------------------------
 constexpr int BM = 128;        // training rows per block row (= size of an inverted diagonal block)
 constexpr int BN = 128;        // candidates per tile (one CTA owns one tile at a time)
-constexpr int NT = 256;        // threads per CTA, 16 x 16 grid of 8 x 8 register tiles
+constexpr int NT = 256;        // compute threads per CTA (8 warps); the sweep kernel adds a producer warpgroup
 constexpr int STAGES = 4;      // bulk-copy ring depth
 constexpr int TILE_BYTES = 8192;  // one operand tile: BM x KC x sizeof(T) = BN x KC x sizeof(T)
 constexpr int MAX_D = 32;
@@ -18,12 +18,6 @@ template <typename T> struct Geo {
     static constexpr int KC = TILE_BYTES / (BM * sizeof(T));  // contraction depth per tile: 8 (f64) / 16 (f32)
     static constexpr int CH = BM / KC;                   // tiles per 128 columns: 16 (f64) / 8 (f32)
 };
-
-// interleaved ownership: thread coordinate t (0..15) owns element slots 0..7 of a 128-wide axis
-template <typename T> __host__ __device__ __forceinline__ int owned(int t, int slot) {
-    constexpr int VEC = Geo<T>::VEC;
-    return t * VEC + (slot / VEC) * (16 * VEC) + (slot % VEC);
-}
 
 // ---- argmin record -----------------------------------------------------------------------------
 struct MinLoc {
