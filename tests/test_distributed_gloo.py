@@ -75,3 +75,26 @@ def test_sharded_argmin_over_gloo_matches_single_process(m):
     assert x == xs[int(np.argmin(v))].tolist() and val == float(v.min())
     assert np.isnan(nan_case[0]) and nan_case[1] == 11          # a NaN beats every number
     assert tie_case == (1.25, 99)                                # equal values: lowest global index wins
+
+
+def test_minloc_reduction_properties():
+    """Order-independence and agreement with np.argmin for random records incl. NaNs, ties, -0.0 and empty slots."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st_
+
+    values = st_.sampled_from([0.0, -0.0, 1.5, -2.25, float("nan"), float("inf"), -float("inf")])
+
+    @settings(max_examples=200, deadline=None)
+    @given(st_.lists(values, min_size=1, max_size=12), st_.randoms(use_true_random=False))
+    def check(vals, rnd):
+        recs = [(v, i) for i, v in enumerate(vals)] + [(0.0, -1)]      # plus an empty record
+        expected = int(np.argmin(np.array(vals)))
+        rnd.shuffle(recs)
+        val, idx = reduce_minloc(recs)
+        assert idx == expected
+        assert (np.isnan(val) and np.isnan(vals[expected])) or val == vals[expected]
+        # associativity: reduce in two halves, then reduce the partial results
+        half = len(recs) // 2
+        assert reduce_minloc([reduce_minloc(recs[:half]), reduce_minloc(recs[half:])])[1] == expected
+
+    check()

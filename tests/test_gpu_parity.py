@@ -204,3 +204,33 @@ def test_c_abi_error_behaviour():
     with pytest.raises(Exception, match="m must be"):
         _native.check(lib.bopy_gp_posterior_acq(gp._handle, xs.data_ptr(), 0, 1, 0.0, 2.0, None, None, None, 0, None,
                                                 None, None), "posterior_acq")
+
+
+@pytest.mark.parametrize("n,d", [(1, 1), (2, 32), (127, 3), (128, 1), (129, 5), (257, 32)])
+def test_extreme_shapes_against_the_oracle(n, d):
+    """Smallest / largest supported dimensionality, n around the 128-row block edge, candidates far away."""
+    from bopy_b200 import _native
+    rng = np.random.default_rng(100 * n + d)
+    X = rng.random((n, d))
+    y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(n)
+    spec = O.KernelSpec(kind="rbf", length_scale=0.5 + rng.random(d), amplitude=1.7)
+    st = O.fit_state(X, y, spec, 1e-6, normalize_y=True)
+    gp = native_for(st, "f64")
+    xs = np.concatenate([rng.random((300, d)), 50.0 + rng.random((11, d))])     # the last 11 are far-field
+    out = gp.sweep(gp.candidates(xs), acq="ei", eta=float(y.min()), want_mean=True, want_var=True, want_acq=True,
+                   want_min=True, index_base=1 << 40)
+    mean, var, a = (out[k].cpu().numpy() for k in ("mean", "var", "acq"))
+    o_mean, o_var, o_a, (o_idx, _) = O.acquisition_sweep(st, "ei", xs, eta=float(y.min()))
+    err, bound = check_mean(mean, o_mean, st, "f64")
+    assert (err <= bound).all()
+    err, bound = check_var(var, o_var, st, "f64")
+    assert (err <= bound).all()
+    assert np.all(var[-11:] == prior_var(st)) and np.all(a[-11:] == 0.0)        # far field: prior variance, EI == 0
+    idx = int(out["min_idx"].item()) - (1 << 40)
+    assert idx == int(np.argmin(a)) and is_stated_tie(o_a, o_idx, idx, "f64")
+
+
+def test_c_abi_rejects_unsupported_dimensionality():
+    from bopy_b200 import _native
+    with pytest.raises(Exception, match="exceeds the supported maximum"):
+        _native.NativeGP(10, 33)
