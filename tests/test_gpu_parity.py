@@ -225,7 +225,8 @@ def test_extreme_shapes_against_the_oracle(n, d):
     assert (err <= bound).all()
     err, bound = check_var(var, o_var, st, "f64")
     assert (err <= bound).all()
-    assert np.all(var[-11:] == prior_var(st)) and np.all(a[-11:] == 0.0)        # far field: prior variance, EI == 0
+    # far field: the posterior is the prior -> exactly the prior variance, one common acquisition value
+    assert np.all(var[-11:] == prior_var(st)) and np.ptp(a[-11:]) == 0.0 and np.ptp(mean[-11:]) == 0.0
     idx = int(out["min_idx"].item()) - (1 << 40)
     assert idx == int(np.argmin(a)) and is_stated_tie(o_a, o_idx, idx, "f64")
 
