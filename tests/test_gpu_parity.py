@@ -222,7 +222,10 @@ def test_extreme_shapes_against_the_oracle(n, d):
     mean, var, a = (out[k].cpu().numpy() for k in ("mean", "var", "acq"))
     o_mean, o_var, o_a, (o_idx, _) = O.acquisition_sweep(st, "ei", xs, eta=float(y.min()))
     err, bound = check_mean(mean, o_mean, st, "f64")
-    assert (err <= bound).all()
+    # dense 1-D designs make alpha_ huge (|alpha|_1 ~ 1e6): the mean is a cancelling dot product whose value moves by
+    # eps * |k*|.|alpha| per ulp of exp() -- the oracle's libm and the kernel's exp_nonpos differ by up to 2 ulp
+    dot_cond = st.y_std * (np.abs(O.kernel_cross(st.kernel, xs, st.X_train)) @ np.abs(st.alpha))
+    assert (err <= bound + 16 * np.finfo(np.float64).eps * dot_cond).all()
     err, bound = check_var(var, o_var, st, "f64")
     assert (err <= bound).all()
     # far field: the posterior is the prior -> exactly the prior variance, one common acquisition value
