@@ -333,8 +333,14 @@ def run_b200(args):
     cores, model = host_info()
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sur.gp.predict(X[:8], return_cov=True)
-        done, dt = time_reference_path(sur.gp, eta, lo, hi, budget_s=args.cpu_budget)
+        # the surrogate above was fitted on the device (its sklearn object holds no L_): the CPU arm gets its own
+        # host-fitted scikit-learn model, exactly what the reference's ScipyGPSurrogate.fit would build
+        from sklearn.base import clone
+        gp_host = clone(gp)
+        with all_host_threads():
+            gp_host.fit(X, y)
+        gp_host.predict(X[:8], return_cov=True)
+        done, dt = time_reference_path(gp_host, eta, lo, hi, budget_s=args.cpu_budget)
         cpu = {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port", "host_cpu": model,
                "sample": f"first {done} candidates of the step's batch ({dt:.1f} s), bopy's call sequence on "
                          f"sklearn/scipy: predict(return_cov=True) on 64 candidates per call -> np.diag -> norm EI"}
