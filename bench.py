@@ -165,7 +165,7 @@ def run_reference(args):
     gp.fit(X, y)
     eta = float(np.min(y))
     lo, hi = np.zeros(DIM), np.ones(DIM)
-    per_step_budget = max(1.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    per_step_budget = args.ref_budget or max(1.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
     for w in range(args.warmup):
         time_reference_path(gp, eta, lo, hi, per_step_budget / 4, base_index=w << 17)
     total, elapsed = 0, 0.0
@@ -180,8 +180,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Hartmann-6D synthetic, n=2048, d=6, EI, candidates U[0,1]^6 (bounded CPU sample)",
-                   "host_cpu": model},
+        "config": {"workload": f"Hartmann-6D synthetic, n={N_TRAIN} observations, d={DIM}, 1.0*RBF({LENGTH_SCALE}), "
+                               f"alpha={ALPHA_REG}, normalize_y, EI + argmin, candidates U[0,1]^d from (seed, global "
+                               f"index); bounded CPU sample of the step's batch",
+                   "n": N_TRAIN, "d": DIM, "acquisition": "EI", "host_cpu": model},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -382,6 +384,7 @@ def main():
     ap.add_argument("--d", type=int, default=DIM)
     ap.add_argument("--candidates", type=int, default=CAND_PER_GPU, help="candidates per GPU per step")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--ref-budget", type=float, default=None, help="--impl reference: seconds of CPU work per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
