@@ -33,6 +33,7 @@ _SIGNATURES = {
                             POINTER(c_double), POINTER(c_double), c_void_p]),
     "bopy_gp_posterior_acq": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_double, c_void_p, c_void_p,
                                       c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "bopy_gp_set_latency_path": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
     "bopy_gp_predict_diag": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "bopy_acq_eval": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p]),
     "bopy_acq_argmin": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
@@ -211,6 +212,13 @@ class NativeGP:
                                        float(noise_level), float(alpha_reg), byref(value), grad, _stream(self.device)),
                   "bopy_gp_lml")
         return value.value, (np.array(grad[:]) if want_grad else None)
+
+    def set_latency_path(self, max_m):
+        """Candidate sets of up to `max_m` rows take the latency path (probe_kernel); 0 switches it off.
+        Returns the limit in force (0 for fp32 handles)."""
+        eff = c_int64()
+        check(self.lib.bopy_gp_set_latency_path(self._handle, int(max_m), byref(eff)), "bopy_gp_set_latency_path")
+        return eff.value
 
     def candidates(self, x):
         """(m, d) fp64 device tensor from numpy / torch input."""

@@ -14,6 +14,7 @@
 #include "aux_kernels.cuh"
 #include "common.cuh"
 #include "fit_kernels.cuh"
+#include "probe_kernel.cuh"
 #include "sweep_kernel.cuh"
 
 using namespace bopy;
@@ -57,6 +58,14 @@ struct bopy_gp {
     double amp = 1.0, noise = 0.0, y_mean = 0.0, y_std = 1.0;
     bool ready = false;
     bool fma64 = false;        // fp64 solve with the register-tiled FMA engine instead of DMMA (BOPY_B200_F64_ENGINE=fma)
+    // latency path (probe_kernel): used for m <= probe_max_m on fp64 handles whose block rows fit one wave of CTAs
+    bool probe_capable = false;
+    long long probe_max_m = 0;
+    int probe_max_batch = 0;
+    MinLoc* probe_records = nullptr;   // [probe_max_batch]
+    unsigned* probe_flags = nullptr;   // [probe_max_batch][n_blocks], then the role ticket
+    double* probe_part = nullptr;      // [probe_max_batch][n_blocks][2][PROBE_MAX_NC]
+    unsigned probe_ticket_base = 0, probe_epoch = 0;
 };
 
 namespace {
@@ -79,6 +88,47 @@ template <class E> int launch_sweep_k(int kernel, const SweepParams& p, int grid
         case BOPY_KERNEL_MATERN52: return launch_sweep_t<E, K_M52>(p, grid, st);
     }
     return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
+}
+
+template <int NA, int KIND> int launch_probe_t(const ProbeParams& p, int grid, cudaStream_t st) {
+    const size_t smem = probe_smem_bytes<NA>(p.d);
+    CUDA_TRY(cudaFuncSetAttribute(probe_kernel<NA, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    probe_kernel<NA, KIND><<<grid, PROBE_NT, smem, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
+template <int NA> int launch_probe_k(int kernel, const ProbeParams& p, int grid, cudaStream_t st) {
+    switch (kernel) {
+        case BOPY_KERNEL_RBF: return launch_probe_t<NA, K_RBF>(p, grid, st);
+        case BOPY_KERNEL_MATERN12: return launch_probe_t<NA, K_M12>(p, grid, st);
+        case BOPY_KERNEL_MATERN32: return launch_probe_t<NA, K_M32>(p, grid, st);
+        case BOPY_KERNEL_MATERN52: return launch_probe_t<NA, K_M52>(p, grid, st);
+    }
+    return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
+}
+
+// candidates per batch (8, 16 or 32) and the launch shape of the latency path for m candidates
+struct ProbePlan {
+    int na, nbatch, groups, grid;
+};
+ProbePlan probe_plan(const bopy_gp* gp, long long m) {
+    ProbePlan pl;
+    const int gmax = std::max(1, gp->sm_count / gp->n_blocks);
+    pl.na = (m + 7) / 8 <= gmax ? 1 : ((m + 15) / 16 <= gmax ? 2 : 4);
+    pl.nbatch = (int)((m + 8 * pl.na - 1) / (8 * pl.na));
+    pl.groups = std::min(pl.nbatch, gmax);
+    pl.grid = pl.groups * gp->n_blocks;
+    return pl;
+}
+
+// most candidates one latency-path launch can hold: V lives in the sweep workspace, records / flags per batch
+long long probe_capacity(const bopy_gp* gp) {
+    return std::min<long long>((long long)gp->sm_count * BN, (long long)gp->probe_max_batch * PROBE_MAX_NC);
+}
+
+bool probe_applies(const bopy_gp* gp, long long m, int slot_per_tile, const MinLoc* tile_records) {
+    return gp->probe_max_m > 0 && m <= gp->probe_max_m && slot_per_tile == 0 && tile_records == nullptr;
 }
 
 template <class P> int launch_cov_k(const bopy_gp* gp, const void* Vws, const double* Xs, long long m,
@@ -153,6 +203,51 @@ int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, d
     p.acq_out = acq_out;
     p.index_base = index_base;
     const bool want_min = (min_val != nullptr || min_idx != nullptr);
+    if (probe_applies(gp, m, slot_per_tile, tile_records)) {
+        // small m: latency path, the forward substitution spread over the block rows of L (probe_kernel.cuh)
+        const ProbePlan pl = probe_plan(gp, m);
+        ProbeParams q;
+        std::memset(&q, 0, sizeof(q));
+        q.Lt = reinterpret_cast<const unsigned char*>(gp->Lt);
+        q.Xt = gp->Xt;
+        q.V = reinterpret_cast<double*>(gp->Vws);
+        q.Xs = Xs;
+        q.m = m;
+        q.nbatch = pl.nbatch;
+        q.groups = pl.groups;
+        q.n = p.n;
+        q.n_blocks = p.n_blocks;
+        q.d = p.d;
+        for (int k = 0; k < gp->d; ++k) q.ls[k] = gp->ls[k];
+        q.amp = p.amp;
+        q.kss = p.kss;
+        q.y_mean = p.y_mean;
+        q.y_std = p.y_std;
+        q.y_var = p.y_var;
+        q.acq = acq;
+        q.eta = eta;
+        q.kappa = kappa;
+        q.mean_out = mean_out;
+        q.var_out = var_out;
+        q.acq_out = acq_out;
+        q.index_base = index_base;
+        q.records = want_min ? gp->probe_records : nullptr;
+        q.flags = gp->probe_flags;
+        q.part = gp->probe_part;
+        q.ticket = gp->probe_flags + (size_t)gp->probe_max_batch * gp->n_blocks;
+        q.ticket_base = gp->probe_ticket_base;
+        q.epoch = ++gp->probe_epoch;
+        int rc = pl.na == 1 ? launch_probe_k<1>(gp->kernel, q, pl.grid, st)
+                            : (pl.na == 2 ? launch_probe_k<2>(gp->kernel, q, pl.grid, st)
+                                          : launch_probe_k<4>(gp->kernel, q, pl.grid, st));
+        if (rc != BOPY_OK) return rc;
+        gp->probe_ticket_base += (unsigned)pl.grid;
+        if (want_min) {
+            minloc_finalize_kernel<<<1, 256, 0, st>>>(gp->probe_records, pl.nbatch, min_val, min_idx);
+            CUDA_TRY(cudaGetLastError());
+        }
+        return BOPY_OK;
+    }
     p.partials = want_min ? gp->partials : nullptr;
     p.tile_records = tile_records;
     const int grid = (int)std::min<long long>(p.ntiles, gp->sm_count);
@@ -217,6 +312,20 @@ int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, 
     if (e == cudaSuccess) e = cudaMalloc(&gp->Dinv, (size_t)gp->n_blocks * BM * BM * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&gp->Vws, (size_t)gp->sm_count * gp->n_pad * BN * es);
     if (e == cudaSuccess) e = cudaMalloc(&gp->partials, (size_t)gp->sm_count * sizeof(MinLoc));
+    // latency path: fp64 DMMA handles whose block rows fit one wave of CTAs (the V chain needs them all in flight)
+    gp->probe_capable = dtype == BOPY_F64 && !gp->fma64 && gp->n_blocks <= gp->sm_count;
+    if (gp->probe_capable) {
+        gp->probe_max_batch = 4 * gp->sm_count;   // sm_count*128 candidates in batches of 32; >= one batch of 8 per CTA group
+        const size_t nflags = (size_t)gp->probe_max_batch * gp->n_blocks + 1;
+        if (e == cudaSuccess) e = cudaMalloc(&gp->probe_records, (size_t)gp->probe_max_batch * sizeof(MinLoc));
+        if (e == cudaSuccess) e = cudaMalloc(&gp->probe_flags, nflags * sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMemset(gp->probe_flags, 0, nflags * sizeof(unsigned));
+        if (e == cudaSuccess)
+            e = cudaMalloc(&gp->probe_part, (size_t)gp->probe_max_batch * gp->n_blocks * 2 * PROBE_MAX_NC * sizeof(double));
+        long long max_m = 4096;
+        if (const char* v = std::getenv("BOPY_B200_PROBE_MAX_M")) max_m = std::atoll(v);
+        gp->probe_max_m = std::max(0LL, std::min<long long>(max_m, probe_capacity(gp)));
+    }
     if (e != cudaSuccess) {
         bopy_gp_destroy(gp);
         return fail(BOPY_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
@@ -233,6 +342,9 @@ void bopy_gp_destroy(bopy_gp* gp) {
     cudaFree(gp->Dinv);
     cudaFree(gp->Vws);
     cudaFree(gp->partials);
+    cudaFree(gp->probe_records);
+    cudaFree(gp->probe_flags);
+    cudaFree(gp->probe_part);
     delete gp;
 }
 
@@ -487,6 +599,14 @@ int bopy_gp_posterior_acq(bopy_gp* gp, const double* Xs_dev, int64_t m, int acq,
                      reinterpret_cast<long long*>(min_idx_out), gp->Vws, 0, static_cast<cudaStream_t>(stream));
 }
 
+int bopy_gp_set_latency_path(bopy_gp* gp, int64_t max_m, int64_t* effective_out) {
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    if (max_m < 0) return fail(BOPY_ERR_BAD_ARG, "max_m must be >= 0 (got %lld)", (long long)max_m);
+    gp->probe_max_m = gp->probe_capable ? std::min<long long>(max_m, probe_capacity(gp)) : 0;
+    if (effective_out) *effective_out = gp->probe_max_m;
+    return BOPY_OK;
+}
+
 int bopy_gp_predict_diag(bopy_gp* gp, const double* Xs_dev, int64_t m, double* mean_out, double* var_out,
                          void* stream) {
     return bopy_gp_posterior_acq(gp, Xs_dev, m, BOPY_ACQ_NONE, 0.0, 0.0, mean_out, var_out, nullptr, 0, nullptr,
@@ -670,7 +790,11 @@ int bopy_measure_peak(int what, double* tflops_out) {
 int bopy_gp_launch_info(const bopy_gp* gp, int64_t m, int* grid_out, int* launches_out, int64_t* workspace_bytes_out) {
     if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
     const long long ntiles = (m + BN - 1) / BN;
-    if (grid_out) *grid_out = (int)std::min<long long>(ntiles, gp->sm_count);
+    if (probe_applies(gp, m, 0, nullptr)) {
+        if (grid_out) *grid_out = probe_plan(gp, m).grid;
+    } else if (grid_out) {
+        *grid_out = (int)std::min<long long>(ntiles, gp->sm_count);
+    }
     if (launches_out) *launches_out = 2;  // sweep_kernel + minloc_finalize_kernel (argmin); 1 without argmin
     if (workspace_bytes_out) *workspace_bytes_out = (int64_t)gp->sm_count * gp->n_pad * BN * (int64_t)elem_size(gp->dtype);
     return BOPY_OK;

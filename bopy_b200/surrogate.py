@@ -71,9 +71,13 @@ class B200GPSurrogate(Surrogate):
                 The optimiser path is sensitive to rounding, so the hyper-parameters can differ from the host
                 route's in the last digits (or pick another local optimum where scikit-learn's would, too).
         False   always the host route.
+    latency_max_m : int | None
+        Calls with at most this many candidates take the latency path of the library (`bopy_gp_set_latency_path`:
+        the solve of a small batch is spread over the block rows of L, ~n/128 hops of a few microseconds, instead
+        of one thread block walking all of L).  None keeps the library default (4096); 0 switches it off.
     """
 
-    def __init__(self, gp, dtype: str = "f64", device=None, device_fit="auto"):
+    def __init__(self, gp, dtype: str = "f64", device=None, device_fit="auto", latency_max_m=None):
         super().__init__()
         if dtype not in ("f64", "f32"):
             raise ValueError("dtype must be 'f64' or 'f32'")
@@ -81,6 +85,7 @@ class B200GPSurrogate(Surrogate):
         self.dtype = dtype
         self.device = device
         self.device_fit = device_fit
+        self.latency_max_m = latency_max_m
         self.native = None          # _native.NativeGP once fitted
         self.kernel_spec = None
         self.fitted_on_device = False
@@ -146,6 +151,8 @@ class B200GPSurrogate(Surrogate):
             if self.native is not None:
                 self.native.close()
             self.native = _native.NativeGP(n, d, kernel=kernel, dtype=self.dtype, device=self.device)
+            if getattr(self, "latency_max_m", None) is not None:
+                self.native.set_latency_path(self.latency_max_m)
         return self.native
 
     def _fit_on_device(self, x: np.ndarray, y: np.ndarray) -> None:
@@ -267,7 +274,7 @@ class GPyGPSurrogate(B200GPSurrogate):
         self.gp_initializer = gp_initializer
         self.n_restarts = n_restarts
         self.gp = None
-        self.dtype, self.device, self.device_fit = dtype, device, False
+        self.dtype, self.device, self.device_fit, self.latency_max_m = dtype, device, False, None
         self.native, self.kernel_spec, self.fitted_on_device = None, None, False
 
     def _fit(self, x: np.ndarray, y: np.ndarray) -> None:

@@ -26,19 +26,32 @@ def native_for(state, dtype):
 
 _NATIVE = {}
 
+# which kernel serves a call: "latency" = probe_kernel for every m it can hold (fp64 handles only),
+# "sweep" = the throughput kernel for every m
+PATHS = ["latency", "sweep"]
+DTYPE_PATHS = [("f64", "latency"), ("f64", "sweep"), ("f32", "sweep")]
 
-def cached_native(name, dtype):
+
+def select_path(gp, path):
+    eff = gp.set_latency_path(0 if path == "sweep" else 1 << 30)
+    if path == "latency":
+        assert eff >= 4096
+    return gp
+
+
+def cached_native(name, dtype, path="sweep"):
     key = (name, dtype)
     if key not in _NATIVE:
         g, st = golden_state(name)
         _NATIVE[key] = (g, st, native_for(st, dtype))
-    return _NATIVE[key]
+    g, st, gp = _NATIVE[key]
+    return g, st, select_path(gp, path)
 
 
-@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("dtype,path", DTYPE_PATHS)
 @pytest.mark.parametrize("name", NAMES)
-def test_posterior_diag_matches_reference(name, dtype):
-    g, st, gp = cached_native(name, dtype)
+def test_posterior_diag_matches_reference(name, dtype, path):
+    g, st, gp = cached_native(name, dtype, path)
     out = gp.sweep(gp.candidates(g["Xs"]), want_mean=True, want_var=True)
     mean, var = out["mean"].cpu().numpy(), out["var"].cpu().numpy()
     o_mean, o_var = O.posterior_diag(st, g["Xs"])
@@ -49,11 +62,11 @@ def test_posterior_diag_matches_reference(name, dtype):
         assert (err <= bound).all(), f"var vs {who}: worst {np.max(err / bound):.3g}x the bound, max err {err.max():.3g}"
 
 
-@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("dtype,path", DTYPE_PATHS)
 @pytest.mark.parametrize("acq", ["lcb", "ei", "poi"])
 @pytest.mark.parametrize("name", NAMES)
-def test_acquisition_and_argmin(name, acq, dtype):
-    g, st, gp = cached_native(name, dtype)
+def test_acquisition_and_argmin(name, acq, dtype, path):
+    g, st, gp = cached_native(name, dtype, path)
     eta, kappa = float(g["eta"]), 2.0
     xs = gp.candidates(g["Xs"])
     out = gp.sweep(xs, acq=acq, eta=eta, kappa=kappa, want_mean=True, want_var=True, want_acq=True, want_min=True,
@@ -106,9 +119,9 @@ def test_candidate_generator_bit_exact():
         assert np.array_equal(got, O.candidates_uniform(1235, base, m, lo, hi))
 
 
-@pytest.mark.parametrize("dtype", ["f64", "f32"])
-def test_ragged_candidate_counts_and_position_independence(dtype):
-    g, st, gp = cached_native("ragged_n333_d4_opt", dtype)
+@pytest.mark.parametrize("dtype,path", DTYPE_PATHS)
+def test_ragged_candidate_counts_and_position_independence(dtype, path):
+    g, st, gp = cached_native("ragged_n333_d4_opt", dtype, path)
     Xs = g["Xs"]
     full = gp.sweep(gp.candidates(Xs), acq="ei", eta=float(g["eta"]), want_mean=True, want_var=True, want_acq=True)
     full = {k: full[k].cpu().numpy() for k in ("mean", "var", "acq")}
@@ -123,8 +136,9 @@ def test_ragged_candidate_counts_and_position_independence(dtype):
             assert int(part["min_idx"].item()) == int(np.argmin(full["acq"][off:off + m]))
 
 
-def test_nan_rules_end_to_end():
-    g, st, gp = cached_native("edge_alpha0_nan", "f64")
+@pytest.mark.parametrize("path", PATHS)
+def test_nan_rules_end_to_end(path):
+    g, st, gp = cached_native("edge_alpha0_nan", "f64", path)
     out = gp.sweep(gp.candidates(g["Xs"]), acq="ei", eta=float(g["eta"]), want_var=True, want_acq=True, want_min=True)
     var, a = out["var"].cpu().numpy(), out["acq"].cpu().numpy()
     bad = ~(np.sqrt(np.where(var < 0, np.nan, var)) > 0)
@@ -138,7 +152,7 @@ def test_sharded_argmin_equals_global_argmin():
     """The multi-GPU reduction on one GPU: min-loc of per-slice arg-mins == arg-min of the whole range."""
     from bopy_b200 import _native
     from bopy_b200.distributed import reduce_minloc, shard_range
-    g, st, gp = cached_native("c3_branin_n256", "f64")
+    g, st, gp = cached_native("c3_branin_n256", "f64", "sweep")
     lo, hi, m = [-5.0, 0.0], [10.0, 15.0], 100_003
     eta = float(g["eta"])
     whole = gp.sweep(_native.candidates_uniform(99, 0, m, lo, hi), acq="ei", eta=eta, want_min=True)
@@ -155,7 +169,7 @@ def test_sharded_argmin_equals_global_argmin():
 def test_full_size_c4_properties():
     """BASELINE config C4 at full per-GPU size (n=2048, d=6, 2^21 candidates): size-independent properties."""
     from bopy_b200 import _native
-    g, st, gp = cached_native("c4_hartmann6_n2048", "f64")
+    g, st, gp = cached_native("c4_hartmann6_n2048", "f64", "sweep")
     m, eta = 1 << 21, float(g["eta"])
     xs = _native.candidates_uniform(1235, 0, m, np.zeros(6), np.ones(6))
     out = gp.sweep(xs, acq="ei", eta=eta, want_mean=True, want_var=True, want_acq=True, want_min=True)
@@ -173,10 +187,17 @@ def test_full_size_c4_properties():
     # checksum-of-checksums: a strided sub-sweep reproduces the same values bit for bit
     sub = gp.sweep(xs[::4097].contiguous(), acq="ei", eta=eta, want_acq=True)["acq"].cpu().numpy()
     assert np.array_equal(sub, a[::4097])
+    # the latency path on the same subset: same arithmetic, another order of a few partial sums
+    select_path(gp, "latency")
+    lat = gp.sweep(xs[::4097].contiguous(), acq="ei", eta=eta, want_acq=True, want_var=True, want_min=True)
+    np.testing.assert_allclose(lat["var"].cpu().numpy(), var[::4097], rtol=0, atol=1e-13 * pv)
+    np.testing.assert_allclose(lat["acq"].cpu().numpy(), sub, rtol=1e-9, atol=1e-12 * np.abs(sub).max())
+    assert int(lat["min_idx"].item()) == int(np.argmin(lat["acq"].cpu().numpy()))
 
 
-def test_interpolation_property_at_training_points():
-    g, st, gp = cached_native("c3_branin_n256", "f64")
+@pytest.mark.parametrize("path", PATHS)
+def test_interpolation_property_at_training_points(path):
+    g, st, gp = cached_native("c3_branin_n256", "f64", path)
     out = gp.sweep(gp.candidates(st.X_train), want_mean=True, want_var=True)
     mean, var = out["mean"].cpu().numpy(), out["var"].cpu().numpy()
     assert np.max(np.abs(mean - g["y"])) < 1e-3 * np.ptp(g["y"])       # alpha_reg = 1e-6: near-interpolation
@@ -206,8 +227,9 @@ def test_c_abi_error_behaviour():
                                                 None, None), "posterior_acq")
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("n,d", [(1, 1), (2, 32), (127, 3), (128, 1), (129, 5), (257, 32)])
-def test_extreme_shapes_against_the_oracle(n, d):
+def test_extreme_shapes_against_the_oracle(n, d, path):
     """Smallest / largest supported dimensionality, n around the 128-row block edge, candidates far away."""
     from bopy_b200 import _native
     rng = np.random.default_rng(100 * n + d)
@@ -215,7 +237,7 @@ def test_extreme_shapes_against_the_oracle(n, d):
     y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(n)
     spec = O.KernelSpec(kind="rbf", length_scale=0.5 + rng.random(d), amplitude=1.7)
     st = O.fit_state(X, y, spec, 1e-6, normalize_y=True)
-    gp = native_for(st, "f64")
+    gp = select_path(native_for(st, "f64"), path)
     xs = np.concatenate([rng.random((300, d)), 50.0 + rng.random((11, d))])     # the last 11 are far-field
     out = gp.sweep(gp.candidates(xs), acq="ei", eta=float(y.min()), want_mean=True, want_var=True, want_acq=True,
                    want_min=True, index_base=1 << 40)

@@ -1,5 +1,10 @@
-"""Per-call latency of the public API for the reference's own calling pattern (few candidates per call:
-DIRECT probes with m = 1, bopy/optimizer.py:96-97; plotting grids with m = 100..2500), beside the reference path."""
+"""Per-call latency for the reference's own calling pattern (few candidates per call: DIRECT probes with m = 1,
+bopy/optimizer.py:96-97; plotting grids with m = 100..2500), beside the reference path on the host.
+
+Columns: EI(x) through the public API (numpy in, numpy out) with the latency path (probe_kernel) and with the
+throughput path (sweep_kernel), the device time of the fused launch alone (CUDA events, candidates resident), and
+bopy's call sequence on scikit-learn / scipy (64 candidates per predict(return_cov=True) call)."""
+import json
 import os
 import sys
 import time
@@ -13,9 +18,34 @@ from bopy_b200.surrogate import B200GPSurrogate  # noqa: E402
 from oracle import reference_path as R  # noqa: E402
 
 
-def main():
+def device_ms(native, xs, eta, reps):
     import torch
-    for n, d in ((256, 2), (2048, 6)):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    native.sweep(xs, acq="ei", eta=eta, want_acq=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        native.sweep(xs, acq="ei", eta=eta, want_acq=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def api_ms(ei, xs, reps):
+    import torch
+    ei(xs)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ei(xs)
+    return 1e3 * (time.perf_counter() - t0) / reps
+
+
+def main():
+    shapes = [(256, 2), (2048, 6)] + ([(8192, 20)] if "--large" in sys.argv else [])
+    ms = (1, 8, 64, 128, 512, 1024, 4096, 8192)
+    rows = []
+    for n, d in shapes:
         X, y, gp = bench.make_problem(n, d)
         sur = B200GPSurrogate(gp)
         sur.fit(X, y)
@@ -24,23 +54,29 @@ def main():
         host = bench.make_problem(n, d)[2].fit(X, y)
         eta = float(y.min())
         rng = np.random.default_rng(0)
-        for m in (1, 8, 64, 128, 1024):
+        for m in ms:
             xs = rng.random((m, d))
-            ei(xs)
-            torch.cuda.synchronize()
-            reps = 20
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                ei(xs)
-            t_gpu = (time.perf_counter() - t0) / reps
-            with bench.all_host_threads():
-                R.ei(host, xs[:min(m, 256)], eta)
-                t0 = time.perf_counter()
-                for _ in range(3):
-                    for s in range(0, m, 64):
-                        R.ei(host, xs[s:s + 64], eta)
-                t_ref = (time.perf_counter() - t0) / 3
-            print(f"n={n:5d} d={d} m={m:5d}: EI(x) through the API {1e3 * t_gpu:8.3f} ms/call   reference path {1e3 * t_ref:8.3f} ms/call")
+            xd = sur.native.candidates(xs)
+            reps = 50 if m <= 1024 else 10
+            sur.native.set_latency_path(1 << 30)
+            t_lat_api, t_lat_dev = api_ms(ei, xs, reps), device_ms(sur.native, xd, eta, reps)
+            sur.native.set_latency_path(0)
+            t_swp_api, t_swp_dev = api_ms(ei, xs, reps), device_ms(sur.native, xd, eta, reps)
+            sur.native.set_latency_path(4096)
+            t_ref = float("nan")
+            if m <= 1024:
+                with bench.all_host_threads():
+                    R.ei(host, xs[:min(m, 256)], eta)
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        for s in range(0, m, 64):
+                            R.ei(host, xs[s:s + 64], eta)
+                    t_ref = 1e3 * (time.perf_counter() - t0) / 3
+            rows.append(dict(n=n, d=d, m=m, latency_api_ms=t_lat_api, latency_dev_ms=t_lat_dev, sweep_api_ms=t_swp_api,
+                             sweep_dev_ms=t_swp_dev, reference_ms=t_ref))
+            print(f"n={n:5d} d={d:2d} m={m:5d}: latency path {t_lat_api:8.3f} ms/call (device {t_lat_dev:7.3f})   "
+                  f"throughput path {t_swp_api:8.3f} (device {t_swp_dev:7.3f})   reference {t_ref:8.3f}", flush=True)
+    print(json.dumps(rows))
 
 
 if __name__ == "__main__":
