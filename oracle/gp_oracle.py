@@ -260,6 +260,71 @@ def acquisition_sweep(state: GPState, kind: str, Xs: np.ndarray, eta: float = 0.
 
 
 # --------------------------------------------------------------------------------------
+# gradient of the acquisition with respect to the candidate (for the multi-start refinement)
+# --------------------------------------------------------------------------------------
+def kernel_cross_grad_factor(spec: KernelSpec, Xa: np.ndarray, Xb: np.ndarray) -> np.ndarray:
+    """kd (ma, mb) with  d k(xa, xb) / d xa_q = kd * (xa_q - xb_q) / l_q^2.
+
+    From the closed forms kernel_cross() evaluates (kernels.py:1569-1570, 1720-1729), r = |xa/l - xb/l|:
+    RBF -k; Matern 1/2 -amp e^-r / r (0 at r = 0, where the kernel has a kink); 3/2 -3 amp e^(-sqrt3 r);
+    5/2 -(5/3) (1 + sqrt5 r) amp e^(-sqrt5 r).  The reference has no gradient code: this extension is pinned by
+    finite differences of the (pinned) acquisition above, tests/test_oracle_gradient.py."""
+    ls = spec.length_scale
+    A, B = Xa / ls, Xb / ls
+    if spec.kind == KIND_RBF:
+        return -spec.amplitude * np.exp(-0.5 * cdist(A, B, metric="sqeuclidean"))
+    r = cdist(A, B, metric="euclidean")
+    if spec.nu == 0.5:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out = -spec.amplitude * np.exp(-r) / r
+        return np.where(r > 0, out, 0.0)
+    if spec.nu == 1.5:
+        return -3.0 * spec.amplitude * np.exp(-math.sqrt(3) * r)
+    if spec.nu == 2.5:
+        k = math.sqrt(5) * r
+        return -(5.0 / 3.0) * (1.0 + k) * spec.amplitude * np.exp(-k)
+    raise ValueError("matern nu must be 0.5, 1.5 or 2.5")
+
+
+def acquisition_partials(kind: str, mean, var, eta: float = 0.0, kappa: float = 2.0):
+    """(d acq / d mean, d acq / d var) of LCB / EI / POI as acquisition() defines them; NaN unless sqrt(var) > 0."""
+    with np.errstate(all="ignore"):
+        sd = np.sqrt(var)
+        z = (eta - mean) / sd
+        pdf = np.exp(-z * z / 2.0) / _SQRT_2PI
+        if kind == ACQ_LCB:
+            dm, dv = np.ones_like(mean), -kappa / (2.0 * sd)
+        elif kind == ACQ_EI:           # a = -sd pdf(z) - (eta - mean) cdf(z)
+            dm, dv = ndtr(z), -pdf / (2.0 * sd)
+        elif kind == ACQ_POI:          # a = 1 - cdf(z)
+            dm, dv = pdf / sd, pdf * z / (2.0 * var)
+        else:
+            raise ValueError(kind)
+    bad = ~(sd > 0)
+    return np.where(bad, np.nan, dm), np.where(bad, np.nan, dv)
+
+
+def acquisition_value_and_grad(state: GPState, kind: str, Xs: np.ndarray, eta: float = 0.0, kappa: float = 2.0):
+    """acq (m,), d acq / d x (m, d), plus (mean, var):
+        d mean / dx = y_std   * sum_i alpha_i dk_i/dx
+        d var  / dx = -2 y_var * sum_i w_i dk_i/dx,   w = K^-1 k* = L^-T (L^-1 k*)."""
+    spec = state.kernel
+    ls = np.broadcast_to(spec.length_scale, (state.X_train.shape[1],))
+    Kt = kernel_cross(spec, Xs, state.X_train)
+    mean = state.y_std * (Kt @ state.alpha) + state.y_mean
+    V = solve_triangular(state.L, Kt.T, lower=True, check_finite=False)
+    var = (kernel_self_diag(spec, Xs.shape[0]) - np.einsum("ij,ij->j", V, V)) * state.y_std ** 2
+    W = solve_triangular(state.L.T, V, lower=False, check_finite=False)           # (n, m)
+    kd = kernel_cross_grad_factor(spec, Xs, state.X_train)                         # (m, n)
+    diff = (Xs[:, None, :] - state.X_train[None, :, :]) / (ls * ls)                # (m, n, d)
+    gm = np.einsum("mn,mnd->md", kd * state.alpha[None, :], diff)
+    gv = np.einsum("mn,mnd->md", kd * W.T, diff)
+    dm, dv = acquisition_partials(kind, mean, var, eta, kappa)
+    grad = dm[:, None] * (state.y_std * gm) + dv[:, None] * (-2.0 * state.y_std ** 2 * gv)
+    return acquisition(kind, mean, var, eta, kappa), grad, mean, var
+
+
+# --------------------------------------------------------------------------------------
 # the reference's own call sequence, with its m x m covariance (used as the CPU baseline)
 # --------------------------------------------------------------------------------------
 def reference_style_acquisition(state: GPState, kind: str, Xs: np.ndarray, eta: float, kappa: float = 2.0,
