@@ -34,6 +34,8 @@ _SIGNATURES = {
     "bopy_gp_posterior_acq": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_double, c_void_p, c_void_p,
                                       c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "bopy_gp_set_latency_path": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
+    "bopy_acq_value_and_grad": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
     "bopy_gp_predict_diag": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "bopy_acq_eval": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p]),
     "bopy_acq_argmin": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
@@ -245,6 +247,22 @@ class NativeGP:
                                                  _ptr(mini), _stream(dev)), "bopy_gp_posterior_acq")
         out.update(mean=mean, var=var, acq=acqv, min_val=minv, min_idx=mini)
         return out
+
+    def value_and_grad(self, Xs, acq, eta=0.0, kappa=2.0):
+        """Acquisition values (m,), their gradient w.r.t. the candidates (m, d), posterior mean and variance (m,):
+        device tensors.  fp64 handles only."""
+        torch = require_cuda()
+        m = Xs.shape[0]
+        dev = self.device
+        val = torch.empty(m, dtype=torch.float64, device=dev)
+        grad = torch.empty((m, self.d), dtype=torch.float64, device=dev)
+        mean = torch.empty(m, dtype=torch.float64, device=dev)
+        var = torch.empty(m, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(self.lib.bopy_acq_value_and_grad(self._handle, ACQ_IDS[acq], float(eta), float(kappa), _ptr(Xs), m,
+                                                   _ptr(val), _ptr(grad), _ptr(mean), _ptr(var), _stream(dev)),
+                  "bopy_acq_value_and_grad")
+        return val, grad, mean, var
 
     def segment_argmin(self, Xs, seg_len, acq, eta=0.0, kappa=2.0, index_base=0):
         """Per-segment arg-min of the acquisition over consecutive segments of `seg_len` rows of Xs (one launch).

@@ -69,6 +69,15 @@ class _MomentAcquisition(AcquisitionFunction):
         out, _, _ = _native.acquisition_from_moments(self.kind, mean_d, var_d, **self.native_args())
         return out.cpu().numpy()
 
+    def value_and_grad(self, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """(values (m,), gradient with respect to x (m, d)).  Additive to the reference's interface (which has no
+        gradients); needs a B200-native surrogate."""
+        self._validate_ok_for_predicting(x)
+        sur = self.surrogate
+        if not hasattr(sur, "acquisition_value_and_grad"):
+            raise TypeError("value_and_grad needs a B200GPSurrogate")
+        return sur.acquisition_value_and_grad(self.kind, x, **self.native_args())
+
     def argmin(self, x, index_base: int = 0) -> Tuple[int, float]:
         """Index and value of the smallest acquisition value over the rows of `x` (fused on the device;
         np.argmin's rules: first minimum, first NaN wins)."""

@@ -14,6 +14,7 @@
 #include "aux_kernels.cuh"
 #include "common.cuh"
 #include "fit_kernels.cuh"
+#include "grad_kernel.cuh"
 #include "probe_kernel.cuh"
 #include "sweep_kernel.cuh"
 
@@ -66,6 +67,11 @@ struct bopy_gp {
     unsigned* probe_flags = nullptr;   // [probe_max_batch][n_blocks], then the role ticket
     double* probe_part = nullptr;      // [probe_max_batch][n_blocks][2][PROBE_MAX_NC]
     unsigned probe_ticket_base = 0, probe_epoch = 0;
+    // acquisition gradient (grad_kernel), allocated on first use: chunks of up to sm_count batches
+    unsigned* grad_flags = nullptr;    // [2][sm_count][n_blocks]: W_I published / gradient shares published
+    double* grad_part = nullptr;       // [sm_count][n_blocks][2][d][PROBE_MAX_NC]
+    double* grad_mv = nullptr;         // [2][sm_count * PROBE_MAX_NC]: mean / var scratch of a chunk
+    unsigned grad_epoch = 0;
 };
 
 namespace {
@@ -173,6 +179,67 @@ int check_ready(const bopy_gp* gp) {
     return BOPY_OK;
 }
 
+// one launch of the latency path (probe_kernel) over m candidates laid out by `pl`
+int launch_probe(bopy_gp* gp, const ProbePlan& pl, const double* Xs, long long m, int acq, double eta, double kappa,
+                 double* mean_out, double* var_out, double* acq_out, long long index_base, MinLoc* records, int keep_v,
+                 cudaStream_t st) {
+    ProbeParams q;
+    std::memset(&q, 0, sizeof(q));
+    q.Lt = reinterpret_cast<const unsigned char*>(gp->Lt);
+    q.Xt = gp->Xt;
+    q.V = reinterpret_cast<double*>(gp->Vws);
+    q.Xs = Xs;
+    q.m = m;
+    q.nbatch = pl.nbatch;
+    q.groups = pl.groups;
+    q.n = (int)gp->n;
+    q.n_blocks = gp->n_blocks;
+    q.d = gp->d;
+    for (int k = 0; k < gp->d; ++k) q.ls[k] = gp->ls[k];
+    q.amp = gp->amp;
+    q.kss = gp->amp + gp->noise;
+    q.y_mean = gp->y_mean;
+    q.y_std = gp->y_std;
+    q.y_var = gp->y_std * gp->y_std;
+    q.acq = acq;
+    q.eta = eta;
+    q.kappa = kappa;
+    q.mean_out = mean_out;
+    q.var_out = var_out;
+    q.acq_out = acq_out;
+    q.index_base = index_base;
+    q.records = records;
+    q.flags = gp->probe_flags;
+    q.part = gp->probe_part;
+    q.ticket = gp->probe_flags + (size_t)gp->probe_max_batch * gp->n_blocks;
+    q.ticket_base = gp->probe_ticket_base;
+    q.epoch = ++gp->probe_epoch;
+    q.keep_v = keep_v;
+    int rc = pl.na == 1 ? launch_probe_k<1>(gp->kernel, q, pl.grid, st)
+                        : (pl.na == 2 ? launch_probe_k<2>(gp->kernel, q, pl.grid, st)
+                                      : launch_probe_k<4>(gp->kernel, q, pl.grid, st));
+    if (rc == BOPY_OK) gp->probe_ticket_base += (unsigned)pl.grid;
+    return rc;
+}
+
+template <int NA, int KIND> int launch_grad_t(const GradParams& p, int grid, cudaStream_t st) {
+    const size_t smem = grad_smem_bytes<NA>(p.d);
+    CUDA_TRY(cudaFuncSetAttribute(grad_kernel<NA, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    grad_kernel<NA, KIND><<<grid, PROBE_NT, smem, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
+template <int NA> int launch_grad_k(int kernel, const GradParams& p, int grid, cudaStream_t st) {
+    switch (kernel) {
+        case BOPY_KERNEL_RBF: return launch_grad_t<NA, K_RBF>(p, grid, st);
+        case BOPY_KERNEL_MATERN12: return launch_grad_t<NA, K_M12>(p, grid, st);
+        case BOPY_KERNEL_MATERN32: return launch_grad_t<NA, K_M32>(p, grid, st);
+        case BOPY_KERNEL_MATERN52: return launch_grad_t<NA, K_M52>(p, grid, st);
+    }
+    return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
+}
+
 // the one place the sweep is launched from
 int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, double kappa, double* mean_out,
               double* var_out, double* acq_out, long long index_base, double* min_val, long long* min_idx,
@@ -206,42 +273,9 @@ int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, d
     if (probe_applies(gp, m, slot_per_tile, tile_records)) {
         // small m: latency path, the forward substitution spread over the block rows of L (probe_kernel.cuh)
         const ProbePlan pl = probe_plan(gp, m);
-        ProbeParams q;
-        std::memset(&q, 0, sizeof(q));
-        q.Lt = reinterpret_cast<const unsigned char*>(gp->Lt);
-        q.Xt = gp->Xt;
-        q.V = reinterpret_cast<double*>(gp->Vws);
-        q.Xs = Xs;
-        q.m = m;
-        q.nbatch = pl.nbatch;
-        q.groups = pl.groups;
-        q.n = p.n;
-        q.n_blocks = p.n_blocks;
-        q.d = p.d;
-        for (int k = 0; k < gp->d; ++k) q.ls[k] = gp->ls[k];
-        q.amp = p.amp;
-        q.kss = p.kss;
-        q.y_mean = p.y_mean;
-        q.y_std = p.y_std;
-        q.y_var = p.y_var;
-        q.acq = acq;
-        q.eta = eta;
-        q.kappa = kappa;
-        q.mean_out = mean_out;
-        q.var_out = var_out;
-        q.acq_out = acq_out;
-        q.index_base = index_base;
-        q.records = want_min ? gp->probe_records : nullptr;
-        q.flags = gp->probe_flags;
-        q.part = gp->probe_part;
-        q.ticket = gp->probe_flags + (size_t)gp->probe_max_batch * gp->n_blocks;
-        q.ticket_base = gp->probe_ticket_base;
-        q.epoch = ++gp->probe_epoch;
-        int rc = pl.na == 1 ? launch_probe_k<1>(gp->kernel, q, pl.grid, st)
-                            : (pl.na == 2 ? launch_probe_k<2>(gp->kernel, q, pl.grid, st)
-                                          : launch_probe_k<4>(gp->kernel, q, pl.grid, st));
+        int rc = launch_probe(gp, pl, Xs, m, acq, eta, kappa, mean_out, var_out, acq_out, index_base,
+                              want_min ? gp->probe_records : nullptr, 0, st);
         if (rc != BOPY_OK) return rc;
-        gp->probe_ticket_base += (unsigned)pl.grid;
         if (want_min) {
             minloc_finalize_kernel<<<1, 256, 0, st>>>(gp->probe_records, pl.nbatch, min_val, min_idx);
             CUDA_TRY(cudaGetLastError());
@@ -345,6 +379,9 @@ void bopy_gp_destroy(bopy_gp* gp) {
     cudaFree(gp->probe_records);
     cudaFree(gp->probe_flags);
     cudaFree(gp->probe_part);
+    cudaFree(gp->grad_flags);
+    cudaFree(gp->grad_part);
+    cudaFree(gp->grad_mv);
     delete gp;
 }
 
@@ -604,6 +641,71 @@ int bopy_gp_set_latency_path(bopy_gp* gp, int64_t max_m, int64_t* effective_out)
     if (max_m < 0) return fail(BOPY_ERR_BAD_ARG, "max_m must be >= 0 (got %lld)", (long long)max_m);
     gp->probe_max_m = gp->probe_capable ? std::min<long long>(max_m, probe_capacity(gp)) : 0;
     if (effective_out) *effective_out = gp->probe_max_m;
+    return BOPY_OK;
+}
+
+int bopy_acq_value_and_grad(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
+                            double* acq_out, double* grad_out, double* mean_out, double* var_out, void* stream) {
+    int rc = check_ready(gp);
+    if (rc != BOPY_OK) return rc;
+    if (Xs_dev == nullptr || grad_out == nullptr) return fail(BOPY_ERR_BAD_ARG, "Xs_dev / grad_out is NULL");
+    if (m < 1) return fail(BOPY_ERR_BAD_ARG, "m must be >= 1 (got %lld)", (long long)m);
+    if (acq < BOPY_ACQ_LCB || acq > BOPY_ACQ_POI) return fail(BOPY_ERR_BAD_ARG, "unknown acquisition id %d", acq);
+    if (!gp->probe_capable)
+        return fail(BOPY_ERR_UNSUPPORTED, "the acquisition gradient needs an fp64 handle with n <= %d", gp->sm_count * BM);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    const int gb = gp->sm_count, nb = gp->n_blocks;            // batches per chunk
+    const long long chunk = (long long)gb * PROBE_MAX_NC;       // candidates per chunk: V and W share the sweep workspace
+    if (gp->grad_flags == nullptr) {
+        const size_t nflags = (size_t)2 * gb * nb;
+        CUDA_TRY(cudaMalloc(&gp->grad_flags, nflags * sizeof(unsigned)));
+        CUDA_TRY(cudaMemset(gp->grad_flags, 0, nflags * sizeof(unsigned)));
+        CUDA_TRY(cudaMalloc(&gp->grad_part, (size_t)gb * nb * 2 * gp->d * PROBE_MAX_NC * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&gp->grad_mv, (size_t)2 * chunk * sizeof(double)));
+    }
+    for (long long off = 0; off < m; off += chunk) {
+        const long long mc = std::min<long long>(chunk, m - off);
+        const ProbePlan pl = probe_plan(gp, mc);
+        double* const mean = mean_out ? mean_out + off : gp->grad_mv;
+        double* const var = var_out ? var_out + off : gp->grad_mv + chunk;
+        rc = launch_probe(gp, pl, Xs_dev + off * gp->d, mc, acq, eta, kappa, mean, var, acq_out ? acq_out + off : nullptr, 0,
+                          nullptr, 1, st);
+        if (rc != BOPY_OK) return rc;
+        GradParams q;
+        std::memset(&q, 0, sizeof(q));
+        q.Lt = reinterpret_cast<const unsigned char*>(gp->Lt);
+        q.Xt = gp->Xt;
+        q.V = reinterpret_cast<const double*>(gp->Vws);
+        q.W = reinterpret_cast<double*>(gp->Vws) + chunk * gp->n_pad;
+        q.Xs = Xs_dev + off * gp->d;
+        q.m = mc;
+        q.nbatch = pl.nbatch;
+        q.groups = pl.groups;
+        q.n = (int)gp->n;
+        q.n_blocks = nb;
+        q.d = gp->d;
+        for (int k = 0; k < gp->d; ++k) q.ls[k] = gp->ls[k];
+        q.amp = gp->amp;
+        q.y_std = gp->y_std;
+        q.y_var = gp->y_std * gp->y_std;
+        q.acq = acq;
+        q.eta = eta;
+        q.kappa = kappa;
+        q.mean = mean;
+        q.var = var;
+        q.grad_out = grad_out + off * gp->d;
+        q.flags = gp->grad_flags;
+        q.flags2 = gp->grad_flags + (size_t)gb * nb;
+        q.gpart = gp->grad_part;
+        q.ticket = gp->probe_flags + (size_t)gp->probe_max_batch * nb;
+        q.ticket_base = gp->probe_ticket_base;
+        q.epoch = ++gp->grad_epoch;
+        rc = pl.na == 1 ? launch_grad_k<1>(gp->kernel, q, pl.grid, st)
+                        : (pl.na == 2 ? launch_grad_k<2>(gp->kernel, q, pl.grid, st) : launch_grad_k<4>(gp->kernel, q, pl.grid, st));
+        if (rc != BOPY_OK) return rc;
+        gp->probe_ticket_base += (unsigned)pl.grid;
+    }
     return BOPY_OK;
 }
 

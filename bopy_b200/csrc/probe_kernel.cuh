@@ -50,6 +50,7 @@ struct ProbeParams {
     double* part;              // [nbatch][n_blocks][2][NC]: mean / sum v^2 partials of block row I
     unsigned* ticket;          // role counter (monotonic over launches)
     unsigned ticket_base, epoch;
+    int keep_v;                // 1: the last block row of V is stored too (the gradient's backward solve reads all of V)
 };
 
 template <int NA> __host__ __device__ constexpr int probe_stages() { return NA == 4 ? 8 : 16; }
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
 #pragma unroll
                 for (int a = 0; a < NA; ++a) {
                     const double v0 = acc[i][a][0][0] + acc[i][a][1][0], v1 = acc[i][a][0][1] + acc[i][a][1][1];
-                    if (!last)
+                    if (!last || p.keep_v)
                         *reinterpret_cast<double2*>(
                             &p.V[(((long long)b * NA + a) * n_pad + (long long)I * BM) * 8 + roff[i]]) = make_double2(v0, v1);
                     sq[a][0] = fma(v0, v0, sq[a][0]);

@@ -242,6 +242,12 @@ class B200GPSurrogate(Surrogate):
         return int(out["min_idx"].item()), float(out["min_val"].item())
 
 
+    def acquisition_value_and_grad(self, kind: str, x, eta: float = 0.0, kappa: float = 2.0):
+        """Acquisition values (m,) and their gradient with respect to the rows of x (m, d), numpy
+        (`bopy_acq_value_and_grad`: the forward solve plus a mirrored backward solve on the device)."""
+        val, grad, _, _ = self.native.value_and_grad(self.native.candidates(x), kind, eta=eta, kappa=kappa)
+        return val.cpu().numpy(), grad.cpu().numpy()
+
     def acquisition_segment_argmin(self, kind: str, xs, seg_len: int, eta: float = 0.0, kappa: float = 2.0,
                                    index_base: int = 0):
         """Per-segment fused argmin over consecutive segments of `seg_len` rows (a multiple of 128) of the device

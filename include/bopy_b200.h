@@ -127,6 +127,17 @@ int bopy_gp_posterior_acq(bopy_gp* gp, const double* Xs_dev, int64_t m, int acq,
  */
 int bopy_gp_set_latency_path(bopy_gp* gp, int64_t max_m, int64_t* effective_out);
 
+/*
+ * Acquisition value AND its gradient with respect to the candidate, for the multi-start refinement behind
+ * Optimizer._optimize (bopy/optimizer.py:65-67; SURVEY.md section 8f rank 3 -- the reference has no gradient code):
+ *   d mean/dx = y_std sum_i alpha_i dk_i/dx,  d var/dx = -2 y_std^2 sum_i w_i dk_i/dx,  w = L^-T (L^-1 k*),
+ * chained with the partials of LCB / EI / POI.  grad_out (m,d) row-major is required; acq_out, mean_out, var_out (m,)
+ * may be NULL.  Rows whose posterior standard deviation is not > 0 get NaN gradients (the scale > 0 rule).
+ * Runs the latency path's forward solve plus a mirrored backward solve; fp64 handles only (BOPY_ERR_UNSUPPORTED else).
+ */
+int bopy_acq_value_and_grad(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
+                            double* acq_out, double* grad_out, double* mean_out, double* var_out, void* stream);
+
 /* Named views of the fused sweep. */
 int bopy_gp_predict_diag(bopy_gp* gp, const double* Xs_dev, int64_t m, double* mean_out, double* var_out,
                          void* stream);
