@@ -44,6 +44,8 @@ _SIGNATURES = {
                                         c_void_p, c_void_p, c_void_p]),
     "bopy_candidates_around": (c_int, [c_uint64, c_void_p, c_int64, c_int, c_int, POINTER(c_double), POINTER(c_double),
                                        POINTER(c_double), c_void_p, c_void_p]),
+    "bopy_multistart_step": (c_int, [c_int64, c_int, POINTER(c_double), POINTER(c_double), c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "bopy_gather_rows": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "bopy_acq_from_moments": (c_int, [c_int, c_double, c_double, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                       c_void_p, c_void_p, c_void_p]),
@@ -222,6 +224,10 @@ class NativeGP:
         check(self.lib.bopy_gp_set_latency_path(self._handle, int(max_m), byref(eff)), "bopy_gp_set_latency_path")
         return eff.value
 
+    def gradient_capable(self):
+        """True if bopy_acq_value_and_grad serves this handle (fp64 solve, block rows fit one wave of thread blocks)."""
+        return self.dtype == F64 and (self.n + 127) // 128 <= 148
+
     def candidates(self, x):
         """(m, d) fp64 device tensor from numpy / torch input."""
         t = self._dev64(x)
@@ -338,6 +344,18 @@ def candidates_around(seed, starts, P, halfwidth, lowers, uppers):
         check(lib.bopy_candidates_around(int(seed), _ptr(starts), S, int(P), d, hw, lo, hi, _ptr(out),
                                          _stream(starts.device)), "bopy_candidates_around")
     return out
+
+
+def multistart_step(lowers, uppers, xc, fc, gc, xt, ft, gt, alpha, first):
+    """One lock-step projected-gradient step of all starts (device tensors, updated in place)."""
+    lib = load()
+    S, d = xt.shape
+    lo = (c_double * d)(*[float(v) for v in lowers])
+    hi = (c_double * d)(*[float(v) for v in uppers])
+    import torch
+    with torch.cuda.device(xt.device):
+        check(lib.bopy_multistart_step(S, d, lo, hi, _ptr(xc), _ptr(fc), _ptr(gc), _ptr(xt), _ptr(ft), _ptr(gt),
+                                       _ptr(alpha), 1 if first else 0, _stream(xt.device)), "bopy_multistart_step")
 
 
 def gather_rows(xs, idx, index_base=0):

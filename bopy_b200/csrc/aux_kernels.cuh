@@ -200,6 +200,66 @@ __global__ void gather_rows_kernel(const double* __restrict__ xs, const long lon
     out[e] = (r >= 0 && r < m) ? xs[r * d + j] : __longlong_as_double(0x7ff8000000000000LL);
 }
 
+// ---- batched multi-start refinement: one projected-gradient step of every start ------------------------------------
+// Monotone projected gradient with Barzilai-Borwein step lengths, all starts in lock step (one thread per start):
+//   trial point xt = P(xc - alpha gc) has just been evaluated -> (ft, gt).
+//   accept (ft <= fc, or fc is NaN and ft is not): s = xt - xc, y = gt - gc, alpha = s.s / s.y if s.y > 0 else 4 alpha
+//           (clamped to [1e-12, 1e12]); (xc, fc, gc) <- (xt, ft, gt)
+//   reject: alpha <- alpha / 4
+//   next trial xt <- P(xc - alpha gc), P = clip to the box.  NaN values are never accepted over numbers.
+// first != 0: (xt, ft, gt) is the evaluated START: it becomes (xc, fc, gc) and alpha = 0.1 min_q(hi-lo) / max_q |g_q|.
+// Restated in oracle/gp_oracle.py (multistart_step) operation by operation.
+__global__ void multistart_step_kernel(long long S, int d, BoxParam box, double* xc, double* fc, double* gc, double* xt,
+                                       const double* __restrict__ ft, const double* __restrict__ gt, double* alpha,
+                                       int first) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double* const xcs = xc + s * d;
+    double* const gcs = gc + s * d;
+    double* const xts = xt + s * d;
+    const double* const gts = gt + s * d;
+    double a = alpha[s];
+    const double f_new = ft[s], f_cur = fc[s];
+    bool accept;
+    if (first) {
+        accept = true;
+        double gmax = 0.0, span = box.hi[0] - box.lo[0];
+        for (int q = 0; q < d; ++q) {
+            gmax = fmax(gmax, fabs(gts[q]));          // fmax ignores NaN: a NaN gradient leaves gmax unchanged
+            span = fmin(span, box.hi[q] - box.lo[q]);
+        }
+        a = gmax > 0.0 ? 0.1 * span / gmax : 1.0;
+    } else {
+        const bool new_nan = f_new != f_new, cur_nan = f_cur != f_cur;
+        accept = !new_nan && (cur_nan || f_new <= f_cur);
+        if (accept) {
+            double ss = 0.0, sy = 0.0;
+            for (int q = 0; q < d; ++q) {
+                const double sq = xts[q] - xcs[q], yq = gts[q] - gcs[q];
+                ss = __dadd_rn(ss, __dmul_rn(sq, sq));   // unfused: the oracle restates this in plain fp64 arithmetic
+                sy = __dadd_rn(sy, __dmul_rn(sq, yq));
+            }
+            a = sy > 0.0 ? ss / sy : 4.0 * a;
+            a = fmin(fmax(a, 1e-12), 1e12);
+        } else {
+            a = 0.25 * a;
+        }
+    }
+    if (accept) {
+        fc[s] = f_new;
+        for (int q = 0; q < d; ++q) {
+            xcs[q] = xts[q];
+            gcs[q] = gts[q];
+        }
+    }
+    alpha[s] = a;
+    for (int q = 0; q < d; ++q) {
+        const double gq = gcs[q];
+        const double step = gq == gq ? __dmul_rn(a, gq) : 0.0;  // NaN gradient (sigma <= 0): stay
+        xts[q] = fmin(fmax(__dadd_rn(xcs[q], -step), box.lo[q]), box.hi[q]);
+    }
+}
+
 // ---- register-resident peak microbenchmarks ---------------------------------------------------------
 template <typename T> __global__ void peak_fma_kernel(T* out, int iters, T x, T y) {
     T a[16];

@@ -776,6 +776,24 @@ int bopy_candidates_around(uint64_t seed, const double* starts_dev, int64_t S, i
     return BOPY_OK;
 }
 
+int bopy_multistart_step(int64_t S, int d, const double* lowers_host, const double* uppers_host, double* xc_dev,
+                         double* fc_dev, double* gc_dev, double* xt_dev, const double* ft_dev, const double* gt_dev,
+                         double* alpha_dev, int first, void* stream) {
+    if (lowers_host == nullptr || uppers_host == nullptr || xc_dev == nullptr || fc_dev == nullptr || gc_dev == nullptr ||
+        xt_dev == nullptr || ft_dev == nullptr || gt_dev == nullptr || alpha_dev == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "bopy_multistart_step: NULL argument");
+    if (S < 1 || d < 1 || d > MAX_D) return fail(BOPY_ERR_BAD_ARG, "need S >= 1 and 1 <= d <= %d", MAX_D);
+    BoxParam box;
+    for (int q = 0; q < MAX_D; ++q) {
+        box.lo[q] = q < d ? lowers_host[q] : 0.0;
+        box.hi[q] = q < d ? uppers_host[q] : 1.0;
+    }
+    multistart_step_kernel<<<(unsigned)((S + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        S, d, box, xc_dev, fc_dev, gc_dev, xt_dev, ft_dev, gt_dev, alpha_dev, first);
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
 int bopy_gather_rows(const double* Xs_dev, int64_t m, int d, const int64_t* idx_dev, int64_t S, int64_t index_base,
                      double* out_dev, void* stream) {
     if (Xs_dev == nullptr || idx_dev == nullptr || out_dev == nullptr)

@@ -110,9 +110,15 @@ class MultiStartOptimizer(Optimizer):
 
     1. A global sweep of `n_candidates` counter-based candidates is cut into `n_starts` segments; the fused
        segmented argmin returns the best point of every segment: `n_starts` stratified starts.
-    2. `rounds` times: a cloud of `points_per_start` points is drawn around every start in a box of half-width
-       `shrink**k * initial_halfwidth * (upper - lower)` (clipped to the bounds, the start itself is point 0), all
-       clouds are swept in ONE launch, and each start moves to the best point of its own cloud.
+    2. Refinement, `method`:
+       'gradient'  `iterations` lock-step steps of a monotone projected-gradient method with Barzilai-Borwein step
+                   lengths (`bopy_multistart_step`); value and gradient of the acquisition at all trial points come
+                   from ONE device call per step (`bopy_acq_value_and_grad`: forward + mirrored backward solve).
+       'cloud'     `rounds` times: a cloud of `points_per_start` points is drawn around every start in a box of
+                   half-width `shrink**k * initial_halfwidth * (upper - lower)` (clipped to the bounds, the start
+                   itself is point 0), all clouds are swept in ONE launch, and each start moves to the best point of
+                   its own cloud.  Derivative-free; serves fp32 surrogates too.
+       'auto'      'gradient' where the surrogate offers it (fp64 handle), else 'cloud'.
     3. The best start wins (`np.argmin` ordering).  `local_minima()` returns all refined starts of the last call.
 
     Everything between the first candidate and the final (x, value) stays on the device.  With a process group the
@@ -123,10 +129,14 @@ class MultiStartOptimizer(Optimizer):
     def __init__(self, acquisition_function: AcquisitionFunction, bounds: Bounds, n_starts: int = 256,
                  n_candidates: int = 1 << 20, rounds: int = 6, points_per_start: int = 256, shrink: float = 0.5,
                  initial_halfwidth: Optional[float] = None, seed: int = 0, process_group=None,
-                 distributed: bool = False):
+                 distributed: bool = False, method: str = "auto", iterations: int = 40):
         super().__init__(acquisition_function, bounds)
-        if n_starts < 1 or rounds < 0:
-            raise ValueError("`n_starts` must be positive and `rounds` non-negative.")
+        if n_starts < 1 or rounds < 0 or iterations < 0:
+            raise ValueError("`n_starts` must be positive and `rounds` / `iterations` non-negative.")
+        if method not in ("auto", "gradient", "cloud"):
+            raise ValueError("`method` must be 'auto', 'gradient' or 'cloud'.")
+        self.method = method
+        self.iterations = int(iterations)
         if points_per_start % 128 != 0 or points_per_start < 128:
             raise ValueError("`points_per_start` must be a positive multiple of 128.")
         self.n_starts = int(n_starts)
@@ -182,16 +192,31 @@ class MultiStartOptimizer(Optimizer):
             vals, idxs = sur.acquisition_segment_argmin(acq.kind, xs, self.segment, index_base=base, **args)
             starts = _native.gather_rows(xs, idxs, index_base=base)
             del xs
-            # a start owns ~1/n_starts of the box: begin with a cloud of that size
-            frac = self.initial_halfwidth if self.initial_halfwidth is not None else \
-                min(0.5, 0.5 * (1.0 / self.n_starts) ** (1.0 / d) * 2.0)
-            half = (hi - lo) * frac
-            P = self.points_per_start
-            for k in range(self.rounds):
-                cloud = _native.candidates_around(seed + 1 + k + 1000 * rank, starts, P, half, lo, hi)
-                vals, idxs = sur.acquisition_segment_argmin(acq.kind, cloud, P, **args)
-                starts = _native.gather_rows(cloud, idxs)
-                half = half * self.shrink
+            method = self.method
+            if method == "auto":
+                method = "gradient" if getattr(sur, "supports_gradient", lambda: False)() else "cloud"
+            if method == "gradient":
+                # all starts advance together: one value+gradient call and one step kernel per iteration
+                native = sur.native
+                xt = starts.clone()
+                xc, gc = torch.empty_like(xt), torch.empty_like(xt)
+                fc = torch.empty(xt.shape[0], dtype=torch.float64, device=xt.device)
+                alpha = torch.ones_like(fc)
+                for k in range(self.iterations + 1):
+                    ft, gt, _, _ = native.value_and_grad(xt, acq.kind, **args)
+                    _native.multistart_step(lo, hi, xc, fc, gc, xt, ft, gt, alpha, first=(k == 0))
+                starts, vals = xc, fc
+            else:
+                # a start owns ~1/n_starts of the box: begin with a cloud of that size
+                frac = self.initial_halfwidth if self.initial_halfwidth is not None else \
+                    min(0.5, 0.5 * (1.0 / self.n_starts) ** (1.0 / d) * 2.0)
+                half = (hi - lo) * frac
+                P = self.points_per_start
+                for k in range(self.rounds):
+                    cloud = _native.candidates_around(seed + 1 + k + 1000 * rank, starts, P, half, lo, hi)
+                    vals, idxs = sur.acquisition_segment_argmin(acq.kind, cloud, P, **args)
+                    starts = _native.gather_rows(cloud, idxs)
+                    half = half * self.shrink
             v = vals.cpu().numpy()
             self._last = (starts.cpu().numpy(), v)
             j = int(np.argmin(v))

@@ -242,6 +242,10 @@ class B200GPSurrogate(Surrogate):
         return int(out["min_idx"].item()), float(out["min_val"].item())
 
 
+    def supports_gradient(self) -> bool:
+        """True if `acquisition_value_and_grad` is available (fp64 solve, n <= 148 * 128)."""
+        return self.native is not None and self.native.gradient_capable()
+
     def acquisition_value_and_grad(self, kind: str, x, eta: float = 0.0, kappa: float = 2.0):
         """Acquisition values (m,) and their gradient with respect to the rows of x (m, d), numpy
         (`bopy_acq_value_and_grad`: the forward solve plus a mirrored backward solve on the device)."""

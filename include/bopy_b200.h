@@ -159,6 +159,15 @@ int bopy_candidates_around(uint64_t seed, const double* starts_dev, int64_t S, i
                            const double* halfwidth_host, const double* lowers_host, const double* uppers_host,
                            double* out_dev, void* stream);
 
+/* One step of the batched multi-start refinement, all S starts in lock step: monotone projected gradient with
+ * Barzilai-Borwein step lengths inside [lowers, uppers].  (xt, ft, gt) = trial points with their just-evaluated
+ * acquisition values / gradients (bopy_acq_value_and_grad); (xc, fc, gc) = accepted points; alpha_dev (S,) step
+ * lengths.  Accepts a trial if it does not increase the value (NaN never beats a number), updates alpha, and
+ * overwrites xt with the next trial points.  first != 0: the trial points are the starts themselves. */
+int bopy_multistart_step(int64_t S, int d, const double* lowers_host, const double* uppers_host, double* xc_dev,
+                         double* fc_dev, double* gc_dev, double* xt_dev, const double* ft_dev, const double* gt_dev,
+                         double* alpha_dev, int first, void* stream);
+
 /* out_dev[s] = Xs_dev[idx_dev[s] - index_base] for s < S (rows of d doubles). */
 int bopy_gather_rows(const double* Xs_dev, int64_t m, int d, const int64_t* idx_dev, int64_t S, int64_t index_base,
                      double* out_dev, void* stream);

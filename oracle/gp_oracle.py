@@ -324,6 +324,46 @@ def acquisition_value_and_grad(state: GPState, kind: str, Xs: np.ndarray, eta: f
     return acquisition(kind, mean, var, eta, kappa), grad, mean, var
 
 
+def multistart_step(lowers, uppers, xc, fc, gc, xt, ft, gt, alpha, first):
+    """One lock-step step of the batched multi-start refinement, restating multistart_step_kernel
+    (bopy_b200/csrc/aux_kernels.cuh) operation by operation.  Arrays are updated in place."""
+    lowers, uppers = np.asarray(lowers, dtype=np.float64), np.asarray(uppers, dtype=np.float64)
+    S, d = xt.shape
+    for s in range(S):
+        a = alpha[s]
+        f_new, f_cur = ft[s], fc[s]
+        if first:
+            accept = True
+            gmax, span = 0.0, uppers[0] - lowers[0]
+            for q in range(d):
+                if not np.isnan(gt[s, q]):
+                    gmax = max(gmax, abs(gt[s, q]))
+                span = min(span, uppers[q] - lowers[q])
+            a = 0.1 * span / gmax if gmax > 0.0 else 1.0
+        else:
+            new_nan, cur_nan = np.isnan(f_new), np.isnan(f_cur)
+            accept = (not new_nan) and (cur_nan or f_new <= f_cur)
+            if accept:
+                ss = sy = 0.0
+                for q in range(d):
+                    sq, yq = xt[s, q] - xc[s, q], gt[s, q] - gc[s, q]
+                    ss = ss + sq * sq
+                    sy = sy + sq * yq
+                a = ss / sy if sy > 0.0 else 4.0 * a
+                a = min(max(a, 1e-12), 1e12)
+            else:
+                a = 0.25 * a
+        if accept:
+            fc[s] = f_new
+            xc[s] = xt[s]
+            gc[s] = gt[s]
+        alpha[s] = a
+        for q in range(d):
+            gq = gc[s, q]
+            step = a * gq if not np.isnan(gq) else 0.0
+            xt[s, q] = min(max(xc[s, q] - step, lowers[q]), uppers[q])
+
+
 # --------------------------------------------------------------------------------------
 # the reference's own call sequence, with its m x m covariance (used as the CPU baseline)
 # --------------------------------------------------------------------------------------

@@ -264,7 +264,8 @@ class TestMultiStart:
             assert (np.abs(block - starts[s].cpu().numpy()) <= np.array([0.05, 0.2]) + 1e-15).all()
             assert block[:, 0].std() > 0.01
 
-    def test_multi_start_optimizer_beats_the_plain_sweep(self):
+    @pytest.mark.parametrize("method", ["gradient", "cloud"])
+    def test_multi_start_optimizer_beats_the_plain_sweep(self, method):
         from bopy_b200.benchmark_functions import branin
         from bopy_b200.optimizer import MultiStartOptimizer
         lo, hi = np.array([-5.0, 0.0]), np.array([10.0, 15.0])
@@ -277,7 +278,7 @@ class TestMultiStart:
         acq.fit(X, y)
         bounds = Bounds([Bound(-5.0, 10.0), Bound(0.0, 15.0)])
         plain = CandidateSweepOptimizer(acq, bounds, n_candidates=1 << 14, seed=11).optimize()
-        ms = MultiStartOptimizer(acq, bounds, n_starts=64, n_candidates=1 << 14, rounds=8, seed=11)
+        ms = MultiStartOptimizer(acq, bounds, n_starts=64, n_candidates=1 << 14, rounds=8, seed=11, method=method)
         res = ms.optimize()
         assert res.x_min.shape == (1, 2) and res.f_min.shape == (1,)
         assert res.f_min[0] <= plain.f_min[0] + 1e-12

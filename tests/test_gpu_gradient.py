@@ -106,3 +106,63 @@ def test_fp32_handle_is_refused():
     g, st, gp = cached_native("c3_branin_n256", "f32")
     with pytest.raises(Exception, match="fp64 handle"):
         gp.value_and_grad(gp.candidates(g["Xs"][:4]), "ei")
+
+
+def test_step_kernel_is_the_oracle_rule_bit_for_bit():
+    import torch
+
+    from bopy_b200 import _native
+    rng = np.random.default_rng(9)
+    S, d = 257, 5
+    lo, hi = -1.0 + np.zeros(d), np.array([1.0, 2.0, 0.5, 3.0, 1.5])
+    for first in (True, False):
+        xc = lo + rng.random((S, d)) * (hi - lo)
+        xt = np.clip(xc + 0.05 * rng.standard_normal((S, d)), lo, hi)
+        fc, ft = rng.standard_normal(S), rng.standard_normal(S)
+        gc, gt = rng.standard_normal((S, d)), rng.standard_normal((S, d))
+        alpha = np.abs(rng.standard_normal(S)) + 0.01
+        ft[::17] = np.nan            # NaN trial values are never accepted
+        fc[5::31] = np.nan           # ... unless the current value is NaN too
+        gt[3::29] = np.nan           # NaN gradients freeze the start
+        gt[7] = 0.0
+        dev = [torch.as_tensor(a.copy(), device="cuda") for a in (xc, fc, gc, xt, ft, gt, alpha)]
+        _native.multistart_step(lo, hi, *dev, first=first)
+        host = [a.copy() for a in (xc, fc, gc, xt, ft, gt, alpha)]
+        O.multistart_step(lo, hi, *host, first=first)
+        for name, a, b in zip(("xc", "fc", "gc", "xt", "ft", "gt", "alpha"), dev, host):
+            assert np.array_equal(a.cpu().numpy(), b, equal_nan=True), (name, first)
+
+
+def test_gradient_multistart_finds_stationary_points():
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel
+
+    from bopy_b200.acquisition import LCB
+    from bopy_b200.benchmark_functions import hartmann6
+    from bopy_b200.bounds import Bound, Bounds
+    from bopy_b200.optimizer import MultiStartOptimizer
+    from bopy_b200.surrogate import B200GPSurrogate
+    rng = np.random.default_rng(8)
+    X = rng.random((500, 6))
+    y = hartmann6(X)
+    sur = B200GPSurrogate(GaussianProcessRegressor(ConstantKernel(1.0) * RBF(0.3 * np.ones(6)), alpha=1e-6,
+                                                    normalize_y=True, optimizer=None))
+    sur.fit(X, y)
+    acq = LCB(sur, kappa=2.0)
+    acq.fit(X, y)
+    bounds = Bounds([Bound(0.0, 1.0)] * 6)
+    grad_opt = MultiStartOptimizer(acq, bounds, n_starts=128, n_candidates=1 << 16, seed=3, method="gradient", iterations=60)
+    cloud_opt = MultiStartOptimizer(acq, bounds, n_starts=128, n_candidates=1 << 16, seed=3, method="cloud", rounds=6)
+    rg, rc = grad_opt.optimize(), cloud_opt.optimize()
+    assert rg.x_min.shape == (1, 6) and (rg.x_min >= 0).all() and (rg.x_min <= 1).all()
+    assert rg.f_min[0] <= rc.f_min[0] + 1e-3 * abs(rc.f_min[0])          # as good as the derivative-free clouds
+    assert abs(acq(rg.x_min)[0] - rg.f_min[0]) <= 1e-10 * max(1.0, abs(rg.f_min[0]))
+    # the refined starts are (projected-)stationary: the gradient vanishes in every coordinate that is not pinned to a bound
+    xs, vs = grad_opt.local_minima()
+    _, g = acq.value_and_grad(xs)
+    free = (xs > 1e-9) & (xs < 1 - 1e-9)
+    pg = np.where(free, g, np.where(xs <= 1e-9, np.minimum(g, 0.0), np.maximum(g, 0.0)))
+    start_vals = None
+    assert np.median(np.abs(pg).max(axis=1)) < 1e-3 * np.abs(g).max() + 1e-6
+    # never worse than where it started: monotone method
+    assert vs.min() == rg.f_min[0]
