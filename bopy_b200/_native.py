@@ -25,6 +25,7 @@ _SIGNATURES = {
     "bopy_last_error": (c_char_p, []),
     "bopy_gp_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int64, c_int]),
     "bopy_gp_destroy": (None, [c_void_p]),
+    "bopy_gp_resize": (c_int, [c_void_p, c_int64]),
     "bopy_gp_set_state": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_double,
                                   c_double, c_double, c_double, c_void_p]),
     "bopy_gp_fit": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_double, c_double, c_double,
@@ -216,6 +217,16 @@ class NativeGP:
                                        float(noise_level), float(alpha_reg), byref(value), grad, _stream(self.device)),
                   "bopy_gp_lml")
         return value.value, (np.array(grad[:]) if want_grad else None)
+
+    def resize(self, n):
+        """Reuse the handle (and its workspaces) for another n with the same number of 128-row blocks; returns False
+        if a new handle is needed.  The state has to be installed again."""
+        n = int(n)
+        if n < 1 or (n + 127) // 128 != (self.n + 127) // 128:
+            return False
+        check(self.lib.bopy_gp_resize(self._handle, n), "bopy_gp_resize")
+        self.n = n
+        return True
 
     def set_latency_path(self, max_m):
         """Candidate sets of up to `max_m` rows take the latency path (probe_kernel); 0 switches it off.

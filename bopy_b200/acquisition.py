@@ -165,7 +165,10 @@ class KriggingBeliever(SequentialBatchAcquisitionFunction):
         self.n_data = len(self.surrogate.x)
 
     def add_to_batch(self, optimization_result) -> None:
-        believed, _ = self.surrogate.predict(optimization_result.x_min)
+        # only the posterior mean is believed: take the diagonal-only entry where the surrogate has one (one-point
+        # latency path) instead of predict()'s full covariance
+        predict = getattr(self.surrogate, "predict_diag", self.surrogate.predict)
+        believed, _ = predict(optimization_result.x_min)
         grown_x = np.concatenate((self.surrogate.x, optimization_result.x_min))
         grown_y = np.concatenate((self.surrogate.y, believed))
         self.surrogate.fit(grown_x, grown_y)

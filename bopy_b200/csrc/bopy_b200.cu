@@ -636,6 +636,16 @@ int bopy_gp_posterior_acq(bopy_gp* gp, const double* Xs_dev, int64_t m, int acq,
                      reinterpret_cast<long long*>(min_idx_out), gp->Vws, 0, static_cast<cudaStream_t>(stream));
 }
 
+int bopy_gp_resize(bopy_gp* gp, int64_t n) {
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    if (n < 1 || (n + BM - 1) / BM != gp->n_blocks)
+        return fail(BOPY_ERR_BAD_ARG, "n = %lld does not fit this handle's %d block rows of %d (create a new handle)",
+                    (long long)n, gp->n_blocks, BM);
+    gp->n = n;
+    gp->ready = false;
+    return BOPY_OK;
+}
+
 int bopy_gp_set_latency_path(bopy_gp* gp, int64_t max_m, int64_t* effective_out) {
     if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
     if (max_m < 0) return fail(BOPY_ERR_BAD_ARG, "max_m must be >= 0 (got %lld)", (long long)max_m);

@@ -147,6 +147,8 @@ class B200GPSurrogate(Surrogate):
         gp.log_marginal_likelihood_value_ = -np.min(values)
 
     def _native_for(self, n: int, d: int, kernel: str):
+        if self.native is not None and self.native.d == d and self.native.kernel == kernel and self.native.resize(n):
+            return self.native        # same number of 128-row blocks: workspaces are reused (one more point per trial)
         if (self.native is None or self.native.n != n or self.native.d != d or self.native.kernel != kernel):
             if self.native is not None:
                 self.native.close()

@@ -70,6 +70,12 @@ const char* bopy_last_error(void);
 int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, int d);
 void bopy_gp_destroy(bopy_gp* gp);
 
+/* Change the number of training points of a handle without reallocating, as long as ceil(n / 128) stays the same
+ * (a BayesOpt loop grows the data set by one point per trial, bopy/bayes_opt.py:255-262; the Kriging believer by one
+ * per batch member, bopy/acquisition.py:188-192).  The state must be installed again (bopy_gp_set_state / bopy_gp_fit).
+ * BOPY_ERR_BAD_ARG if n needs another number of 128-row blocks: create a new handle then. */
+int bopy_gp_resize(bopy_gp* gp, int64_t n);
+
 /*
  * Install the fitted state.  X_dev (n,d) row-major, L_dev (n,n) row-major lower Cholesky factor of
  * K + alpha*I (entries above the diagonal are ignored), alpha_dev (n,): device pointers, fp64.

@@ -143,3 +143,35 @@ def test_direct_style_single_point_probes_through_the_public_api():
     ei_off = EI(sur_off)
     ei_off.fit(X, y)
     np.testing.assert_allclose(ei_off(probes), got, rtol=1e-9, atol=1e-12 * np.abs(got).max())
+
+
+def test_handle_is_reused_while_n_stays_within_its_blocks():
+    """A BayesOpt loop adds one point per trial: the handle (310 MB of workspace at n = 2048) is kept as long as
+    ceil(n / 128) does not change, and a reused handle gives exactly what a fresh one gives."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel
+
+    from bopy_b200.surrogate import B200GPSurrogate
+    rng = np.random.default_rng(21)
+    X = rng.random((400, 3))
+    y = np.cos(3 * X[:, 0]) + X[:, 1] * X[:, 2]
+    xs = rng.random((50, 3))
+
+    def make():
+        return B200GPSurrogate(GaussianProcessRegressor(ConstantKernel(1.0) * RBF(0.3 * np.ones(3)), alpha=1e-6,
+                                                         normalize_y=True, optimizer=None))
+    sur = make()
+    sur.fit(X[:300], y[:300])
+    first = sur.native
+    for n in (301, 384, 290, 257):
+        sur.fit(X[:n], y[:n])
+        assert sur.native is first and sur.native.n == n
+        fresh = make()
+        fresh.fit(X[:n], y[:n])
+        for a, b in zip(sur.predict_diag(xs), fresh.predict_diag(xs)):
+            assert np.array_equal(a, b)
+        big = rng.random((5000, 3))                       # throughput path on the reused handle too
+        for a, b in zip(sur.predict_diag(big), fresh.predict_diag(big)):
+            assert np.array_equal(a, b)
+    sur.fit(X[:385], y[:385])
+    assert sur.native is not first and sur.native.n == 385
