@@ -37,6 +37,8 @@ _SIGNATURES = {
     "bopy_gp_set_latency_path": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
     "bopy_acq_value_and_grad": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p]),
+    "bopy_acq_eval_host": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
     "bopy_gp_predict_diag": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "bopy_acq_eval": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p]),
     "bopy_acq_argmin": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
@@ -263,6 +265,22 @@ class NativeGP:
                                                  _ptr(mean), _ptr(var), _ptr(acqv), int(index_base), _ptr(minv),
                                                  _ptr(mini), _stream(dev)), "bopy_gp_posterior_acq")
         out.update(mean=mean, var=var, acq=acqv, min_val=minv, min_idx=mini)
+        return out
+
+    HOST_CALL_MAX_M = 4096
+
+    def eval_host(self, x, acq=None, eta=0.0, kappa=2.0, want_acq=True, want_mean=False, want_var=False):
+        """Small numpy candidate set in, numpy out, one native call (H2D, fused sweep, D2H, stream sync inside):
+        the per-probe path of DIRECT-style callers.  x: C-contiguous float64 (m, d), m <= HOST_CALL_MAX_M."""
+        import numpy as np
+        torch = require_cuda()
+        m = x.shape[0]
+        out = [np.empty(m) if w else None for w in (want_acq, want_mean, want_var)]
+        ptrs = [c_void_p(o.ctypes.data) if o is not None else c_void_p(0) for o in out]
+        with torch.cuda.device(self.device):
+            check(self.lib.bopy_acq_eval_host(self._handle, ACQ_IDS[acq], float(eta), float(kappa),
+                                              c_void_p(x.ctypes.data), m, ptrs[0], ptrs[1], ptrs[2],
+                                              _stream(self.device)), "bopy_acq_eval_host")
         return out
 
     def value_and_grad(self, Xs, acq, eta=0.0, kappa=2.0):

@@ -72,6 +72,9 @@ struct bopy_gp {
     double* grad_part = nullptr;       // [sm_count][n_blocks][2][d][PROBE_MAX_NC]
     double* grad_mv = nullptr;         // [2][sm_count * PROBE_MAX_NC]: mean / var scratch of a chunk
     unsigned grad_epoch = 0;
+    // staging of the host-buffer entry point (small calls: one point per DIRECT probe)
+    double* host_x = nullptr;          // [HOST_CALL_MAX_M][d]
+    double* host_out = nullptr;        // [3][HOST_CALL_MAX_M]: acq / mean / var
 };
 
 namespace {
@@ -240,6 +243,8 @@ template <int NA> int launch_grad_k(int kernel, const GradParams& p, int grid, c
     return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
 }
 
+constexpr long long HOST_CALL_MAX_M = 4096;
+
 // the one place the sweep is launched from
 int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, double kappa, double* mean_out,
               double* var_out, double* acq_out, long long index_base, double* min_val, long long* min_idx,
@@ -382,6 +387,8 @@ void bopy_gp_destroy(bopy_gp* gp) {
     cudaFree(gp->grad_flags);
     cudaFree(gp->grad_part);
     cudaFree(gp->grad_mv);
+    cudaFree(gp->host_x);
+    cudaFree(gp->host_out);
     delete gp;
 }
 
@@ -716,6 +723,36 @@ int bopy_acq_value_and_grad(bopy_gp* gp, int acq, double eta, double kappa, cons
         if (rc != BOPY_OK) return rc;
         gp->probe_ticket_base += (unsigned)pl.grid;
     }
+    return BOPY_OK;
+}
+
+int bopy_acq_eval_host(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_host, int64_t m,
+                       double* acq_out_host, double* mean_out_host, double* var_out_host, void* stream) {
+    int rc = check_ready(gp);
+    if (rc != BOPY_OK) return rc;
+    if (Xs_host == nullptr) return fail(BOPY_ERR_BAD_ARG, "Xs_host is NULL");
+    if (m < 1 || m > HOST_CALL_MAX_M)
+        return fail(BOPY_ERR_BAD_ARG, "m must be in [1, %lld] for the host-buffer entry (got %lld)", HOST_CALL_MAX_M, (long long)m);
+    if (acq < BOPY_ACQ_NONE || acq > BOPY_ACQ_POI) return fail(BOPY_ERR_BAD_ARG, "unknown acquisition id %d", acq);
+    if (acq == BOPY_ACQ_NONE && acq_out_host != nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "acquisition output requested with BOPY_ACQ_NONE");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    if (gp->host_x == nullptr) {
+        CUDA_TRY(cudaMalloc(&gp->host_x, (size_t)HOST_CALL_MAX_M * gp->d * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&gp->host_out, (size_t)3 * HOST_CALL_MAX_M * sizeof(double)));
+    }
+    double* const a_dev = acq_out_host ? gp->host_out : nullptr;
+    double* const m_dev = mean_out_host ? gp->host_out + HOST_CALL_MAX_M : nullptr;
+    double* const v_dev = var_out_host ? gp->host_out + 2 * HOST_CALL_MAX_M : nullptr;
+    CUDA_TRY(cudaMemcpyAsync(gp->host_x, Xs_host, (size_t)m * gp->d * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = run_sweep(gp, gp->host_x, m, acq, eta, kappa, m_dev, v_dev, a_dev, 0, nullptr, nullptr, gp->Vws, 0, st);
+    if (rc != BOPY_OK) return rc;
+    const size_t bytes = (size_t)m * sizeof(double);
+    if (a_dev) CUDA_TRY(cudaMemcpyAsync(acq_out_host, a_dev, bytes, cudaMemcpyDeviceToHost, st));
+    if (m_dev) CUDA_TRY(cudaMemcpyAsync(mean_out_host, m_dev, bytes, cudaMemcpyDeviceToHost, st));
+    if (v_dev) CUDA_TRY(cudaMemcpyAsync(var_out_host, v_dev, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return BOPY_OK;
 }
 

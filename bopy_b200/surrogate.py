@@ -224,14 +224,28 @@ class B200GPSurrogate(Surrogate):
         return mean.cpu().numpy(), cov.cpu().numpy()
 
     # -- additive, diagonal-only and fused entry points ---------------------------------------------
+    def _small_host_call(self, x):
+        """x as a C-contiguous float64 array if it qualifies for the one-call host-buffer entry, else None."""
+        if isinstance(x, np.ndarray) and x.ndim == 2 and 0 < x.shape[0] <= self.native.HOST_CALL_MAX_M \
+                and x.shape[1] == self.native.d:
+            return np.ascontiguousarray(x, dtype=np.float64)
+        return None
+
     def predict_diag(self, x) -> Tuple[np.ndarray, np.ndarray]:
         """mean (m,), var (m,) = diagonal of `predict` without the m x m matrix."""
         self._validate_ok_for_predicting(x)
+        xh = self._small_host_call(x)
+        if xh is not None:
+            _, mean, var = self.native.eval_host(xh, want_acq=False, want_mean=True, want_var=True)
+            return mean, var
         out = self.native.sweep(self.native.candidates(x), want_mean=True, want_var=True)
         return out["mean"].cpu().numpy(), out["var"].cpu().numpy()
 
     def acquisition_values(self, kind: str, x, eta: float = 0.0, kappa: float = 2.0) -> np.ndarray:
         """Fused posterior -> acquisition; (m,) numpy."""
+        xh = self._small_host_call(x)
+        if xh is not None:       # one point per DIRECT probe (bopy/optimizer.py:96-97): one native call, no torch ops
+            return self.native.eval_host(xh, kind, eta=eta, kappa=kappa)[0]
         out = self.native.sweep(self.native.candidates(x), acq=kind, eta=eta, kappa=kappa, want_acq=True)
         return out["acq"].cpu().numpy()
 

@@ -144,6 +144,16 @@ int bopy_gp_set_latency_path(bopy_gp* gp, int64_t max_m, int64_t* effective_out)
 int bopy_acq_value_and_grad(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
                             double* acq_out, double* grad_out, double* mean_out, double* var_out, void* stream);
 
+/*
+ * The same for a SMALL candidate set in HOST memory -- the reference's own calling pattern, one point per DIRECT
+ * probe: AcquisitionFunction.__call__(x.reshape(1, -1)), bopy/optimizer.py:96-97 -> bopy/acquisition.py:26-42.
+ * Xs_host (m,d) and the requested outputs (m,) are plain host pointers (pageable or pinned), 1 <= m <= 4096; the call
+ * copies in, runs the fused sweep (latency path), copies out and synchronises the stream before returning.
+ * acq = BOPY_ACQ_NONE with mean/var outputs = np.diag of Surrogate.predict.
+ */
+int bopy_acq_eval_host(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_host, int64_t m,
+                       double* acq_out_host, double* mean_out_host, double* var_out_host, void* stream);
+
 /* Named views of the fused sweep. */
 int bopy_gp_predict_diag(bopy_gp* gp, const double* Xs_dev, int64_t m, double* mean_out, double* var_out,
                          void* stream);

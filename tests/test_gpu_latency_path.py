@@ -175,3 +175,23 @@ def test_handle_is_reused_while_n_stays_within_its_blocks():
             assert np.array_equal(a, b)
     sur.fit(X[:385], y[:385])
     assert sur.native is not first and sur.native.n == 385
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_host_buffer_entry_equals_the_device_buffer_entry(dtype):
+    g, st, gp = cached_native("ragged_n333_d4_opt", dtype)
+    if dtype == "f64":
+        select_path(gp, "latency")
+    eta = float(g["eta"])
+    for m in (1, 5, 300, 2048):
+        xs = np.ascontiguousarray(g["Xs"][:m])
+        acq, mean, var = gp.eval_host(xs, "ei", eta=eta, want_acq=True, want_mean=True, want_var=True)
+        dev = gp.sweep(gp.candidates(xs), acq="ei", eta=eta, want_mean=True, want_var=True, want_acq=True)
+        for host, key in ((acq, "acq"), (mean, "mean"), (var, "var")):
+            assert np.array_equal(host, dev[key].cpu().numpy(), equal_nan=True), (key, m)
+    only_var = gp.eval_host(xs, None, want_acq=False, want_var=True)
+    assert only_var[0] is None and only_var[1] is None and np.array_equal(only_var[2], var)
+    with pytest.raises(Exception, match="host-buffer entry"):
+        gp.eval_host(np.zeros((4097, 4)), "ei")
+    with pytest.raises(Exception, match="BOPY_ACQ_NONE"):
+        gp.eval_host(xs, None, want_acq=True)
