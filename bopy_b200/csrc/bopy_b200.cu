@@ -216,7 +216,11 @@ int launch_probe(bopy_gp* gp, const ProbePlan& pl, const double* Xs, long long m
     q.part = gp->probe_part;
     q.ticket = gp->probe_flags + (size_t)gp->probe_max_batch * gp->n_blocks;
     q.ticket_base = gp->probe_ticket_base;
-    q.epoch = ++gp->probe_epoch;
+    if (++gp->probe_epoch == 0) {   // 2^32 launches: flags of batches not used for a whole cycle must not match again
+        CUDA_TRY(cudaMemsetAsync(gp->probe_flags, 0, (size_t)gp->probe_max_batch * gp->n_blocks * sizeof(unsigned), st));
+        gp->probe_epoch = 1;
+    }
+    q.epoch = gp->probe_epoch;
     q.keep_v = keep_v;
     int rc = pl.na == 1 ? launch_probe_k<1>(gp->kernel, q, pl.grid, st)
                         : (pl.na == 2 ? launch_probe_k<2>(gp->kernel, q, pl.grid, st)
@@ -717,7 +721,11 @@ int bopy_acq_value_and_grad(bopy_gp* gp, int acq, double eta, double kappa, cons
         q.gpart = gp->grad_part;
         q.ticket = gp->probe_flags + (size_t)gp->probe_max_batch * nb;
         q.ticket_base = gp->probe_ticket_base;
-        q.epoch = ++gp->grad_epoch;
+        if (++gp->grad_epoch == 0) {
+            CUDA_TRY(cudaMemsetAsync(gp->grad_flags, 0, (size_t)2 * gb * nb * sizeof(unsigned), st));
+            gp->grad_epoch = 1;
+        }
+        q.epoch = gp->grad_epoch;
         rc = pl.na == 1 ? launch_grad_k<1>(gp->kernel, q, pl.grid, st)
                         : (pl.na == 2 ? launch_grad_k<2>(gp->kernel, q, pl.grid, st) : launch_grad_k<4>(gp->kernel, q, pl.grid, st));
         if (rc != BOPY_OK) return rc;

@@ -28,7 +28,10 @@
  *     bopy_last_error() (thread-local).  Nothing throws across the boundary.  There is no CPU
  *     fallback: without a CUDA device every compute entry returns BOPY_ERR_CUDA.
  *   - calls are asynchronous on the given stream unless stated otherwise.  A handle is not
- *     thread-safe; use one handle per device (one process per GPU).
+ *     thread-safe; use one handle per device (one process per GPU), and issue its calls on ONE stream
+ *     (or synchronise when changing streams): launches of a handle share its solve workspace and the
+ *     latency-path kernels hand thread-block roles out from a per-handle counter, so two launches of the
+ *     same handle must not overlap in time.  For the same reason these calls cannot be captured into a CUDA graph.
  */
 #ifndef BOPY_B200_H
 #define BOPY_B200_H
