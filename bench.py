@@ -347,12 +347,24 @@ def run_b200(args):
                "sample": f"first {done} candidates of the step's batch ({dt:.1f} s), bopy's call sequence on "
                          f"sklearn/scipy: predict(return_cov=True) on 64 candidates per call -> np.diag -> norm EI"}
 
+    # the reference's own calling pattern: one point per acquisition call (DIRECT, bopy/optimizer.py:96-97)
+    probe = None
+    if world == 1:
+        x1 = np.ascontiguousarray(np.random.default_rng(7).random((1, d)))
+        for _ in range(20):
+            ei(x1)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            ei(x1)
+        probe = {"ms_per_call": 1e3 * (time.perf_counter() - t0) / 200,
+                 "what": "EI(x) through the public API, x a (1, d) numpy array, numpy out (latency path)"}
+
     info = native.launch_info(m)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"Hartmann-6D synthetic, n={n} observations, d={d}, 1.0*RBF({LENGTH_SCALE}), "
+        "config": {"workload": f"{'Hartmann-6D' if d == 6 else 'sin-sum'} synthetic, n={n} observations, d={d}, 1.0*RBF({LENGTH_SCALE}), "
                                f"alpha={ALPHA_REG}, normalize_y, EI + argmin, {m} candidates per GPU per step "
                                f"({world * m} per step in total), candidates U[0,1]^d from (seed, global index)",
                    "n": n, "d": d, "candidates_per_gpu": m, "acquisition": "EI",
@@ -367,6 +379,7 @@ def run_b200(args):
         "cpu_baseline": cpu,
         "clocks": clocks.summary(),
         "argmin": {"index": result[1], "value": result[0], "e2e_index": e2e_result[1]},
+        "single_point_probe": probe,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
