@@ -357,7 +357,8 @@ def run_b200(args):
         for _ in range(200):
             ei(x1)
         probe = {"ms_per_call": 1e3 * (time.perf_counter() - t0) / 200,
-                 "what": "EI(x) through the public API, x a (1, d) numpy array, numpy out (latency path)"}
+                 "what": "EI(x) through the public API, x a (1, d) numpy array, numpy out ("
+                         + ("latency path: probe_kernel)" if args.dtype == "f64" else "fp32 handles have no latency path: sweep_kernel)")}
 
     info = native.launch_info(m)
     line = {
