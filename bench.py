@@ -300,8 +300,14 @@ def run_b200(args):
 
     # roofline of the dominant kernel (sweep_kernel): the FP64 pipe (DFMA and DMMA share it on B200; the larger
     # of the two measured rates is the denominator) or, for the fp32 mode, the FP32 FMA pipe
-    peaks_all = {k: _native.measure_peak(k) for k in ("fp64_fma", "fp32_fma", "fp64_mma")}
-    peak = max(peaks_all["fp64_fma"], peaks_all["fp64_mma"]) if args.dtype == "f64" else peaks_all["fp32_fma"]
+    peaks_all = {k: _native.measure_peak(k) for k in ("fp64_fma", "fp32_fma", "fp64_mma", "tf32_mma_sync")}
+    f32_fma_engine = os.environ.get("BOPY_B200_F32_ENGINE") == "fma"
+    if args.dtype == "f64":
+        peak = max(peaks_all["fp64_fma"], peaks_all["fp64_mma"])
+    elif f32_fma_engine:
+        peak = peaks_all["fp32_fma"]
+    else:
+        peak = peaks_all["tf32_mma_sync"] / 3.0      # 3xTF32: three tensor instructions per fp32-grade product
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     nominal = sm_count * (64 if args.dtype == "f64" else 128) * 2 * 1.965e9 / 1e12
     F = flops_per_candidate(n, d)
@@ -315,9 +321,11 @@ def run_b200(args):
     hbm_peak = measured.get("hbm_gbs", 6650.0)
     algo_bytes = m * d * 8 + 16
     roofline = {
-        "bound": "tensor" if args.dtype == "f64" else "fp32_fma",
+        "bound": "fp32_fma" if (args.dtype == "f32" and f32_fma_engine) else "tensor",
         "pipe": ("FP64 tensor sub-pipe (mma.sync.m8n8k4.f64 = SASS DMMA; tcgen05 has no f64 kind)" if args.dtype == "f64"
-                 else "FP32 FMA pipe for the off-diagonal GEMM, FP64 DMMA for the diagonal solve"),
+                 else ("FP32 FMA pipe for the off-diagonal GEMM, FP64 DMMA for the diagonal solve" if f32_fma_engine else
+                       "TF32 tensor pipe, 3xTF32 split (mma.sync.m16n8k8 = SASS HMMA.1688.F32.TF32; peak = measured "
+                       "rate / 3) for the off-diagonal GEMM, FP64 DMMA for the kernel tile's diagonal solve")),
         "kernel": "sweep_kernel",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "peak_source": "bopy_measure_peak: register-resident DFMA / DMMA / FFMA loops measured live on this GPU "

@@ -17,7 +17,7 @@ OK, ERR_BAD_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_READY, ERR_NOT_POSITIVE_DEFI
 F64, F32 = 0, 1
 KERNEL_IDS = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3}
 ACQ_IDS = {None: -1, "none": -1, "lcb": 0, "ei": 1, "poi": 2}
-PEAK_IDS = {"fp64_fma": 0, "fp32_fma": 1, "fp64_mma": 2}
+PEAK_IDS = {"fp64_fma": 0, "fp32_fma": 1, "fp64_mma": 2, "tf32_mma_sync": 3}
 
 # name -> (restype, argtypes); mirrors include/bopy_b200.h line by line
 _SIGNATURES = {

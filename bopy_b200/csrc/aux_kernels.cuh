@@ -299,4 +299,27 @@ __global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, int iters, 
     if (s == -1.2345) out[0] = s;
 }
 
+// legacy warp-level TF32 tensor instruction (mma.sync.m16n8k8, SASS HMMA.1688.F32.TF32): 1024 MACs per warp
+// instruction; 16 independent accumulator quads per warp.  Measures what the non-tcgen05 tensor path sustains.
+__global__ void __launch_bounds__(256) peak_tf32_mma_kernel(float* out, int iters, float x, float y) {
+    float c[16][4];
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[k][u] = threadIdx.x + k - u;
+    const unsigned a0 = __float_as_uint(x), a1 = __float_as_uint(y), b0 = __float_as_uint(y), b1 = __float_as_uint(x);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            asm volatile(
+                "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                : "+f"(c[k][0]), "+f"(c[k][1]), "+f"(c[k][2]), "+f"(c[k][3])
+                : "r"(a0), "r"(a1), "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    }
+    float s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += c[k][0] + c[k][1] + c[k][2] + c[k][3];
+    if (s == -1.2345f) out[0] = s;
+}
+
 }  // namespace bopy

@@ -59,6 +59,7 @@ struct bopy_gp {
     double amp = 1.0, noise = 0.0, y_mean = 0.0, y_std = 1.0;
     bool ready = false;
     bool fma64 = false;        // fp64 solve with the register-tiled FMA engine instead of DMMA (BOPY_B200_F64_ENGINE=fma)
+    bool fma32 = false;        // fp32 solve with register-tiled FFMA instead of 3xTF32 MMAs (BOPY_B200_F32_ENGINE=fma)
     // latency path (probe_kernel): used for m <= probe_max_m on fp64 handles whose block rows fit one wave of CTAs
     bool probe_capable = false;
     long long probe_max_m = 0;
@@ -165,7 +166,7 @@ template <class P> int launch_cov_k(const bopy_gp* gp, const void* Vws, const do
 
 // engine selection: f64 -> DMMA warp tiles (FMA thread tiles on request, for A/B runs); f32 -> mixed engine
 template <class F> int dispatch_engine(const bopy_gp* gp, F&& f) {
-    if (gp->dtype == BOPY_F32) return f(EngineMixed());
+    if (gp->dtype == BOPY_F32) return gp->fma32 ? f(EngineMixedFma()) : f(EngineMixed());
     if (gp->fma64) return f(EngineF64Fma());
     return f(EngineF64());
 }
@@ -348,6 +349,8 @@ int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, 
     }
     const char* engine = std::getenv("BOPY_B200_F64_ENGINE");
     gp->fma64 = engine != nullptr && std::strcmp(engine, "fma") == 0;
+    const char* engine32 = std::getenv("BOPY_B200_F32_ENGINE");
+    gp->fma32 = engine32 != nullptr && std::strcmp(engine32, "fma") == 0;
     const size_t es = elem_size(dtype);
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&gp->Lt, (size_t)packed_tiles(gp) * TILE_BYTES);
@@ -944,6 +947,11 @@ int bopy_measure_peak(int what, double* tflops_out) {
             const int g2 = prop.multiProcessorCount * 2;   // 16 warps per SM, 32 independent DMMAs each
             peak_dmma_kernel<<<g2, block>>>(reinterpret_cast<double*>(sink), iters, 1.0000001, 1e-9);
             flops = 2.0 * g2 * (block / 32) * (double)iters * 32 * 256;
+        } else if (what == BOPY_PEAK_TF32_MMA_SYNC) {
+            const int iters = 4096;
+            const int g2 = prop.multiProcessorCount * 4;
+            peak_tf32_mma_kernel<<<g2, block>>>(reinterpret_cast<float*>(sink), iters, 1.0000001f, 1e-9f);
+            flops = 2.0 * g2 * (block / 32) * (double)iters * 16 * 1024;
         } else {
             cudaFree(sink);
             return fail(BOPY_ERR_BAD_ARG, "unknown peak id %d", what);

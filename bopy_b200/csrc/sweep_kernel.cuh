@@ -240,11 +240,100 @@ struct DmmaPolicy {
     }
 };
 
+// fp32 operands on the warp-level TF32 tensor instruction with the 3xTF32 split (error-compensated: x = hi + lo, both
+// TF32; a.b ~ hi.hi + hi.lo + lo.hi, fp32 accumulate): mma.sync.m16n8k8 (SASS HMMA.1688.F32.TF32).  Same warp tile as
+// DmmaPolicy (32 rows x 64 candidates, 64 accumulators per thread), operand tiles [k=16][128] floats with an XOR
+// swizzle on the 128-wide axis keyed by k%4 so the 4 x 8 fragment gathers hit 32 banks.  Against the register-tiled
+// FFMA policy this needs 5x fewer shared-memory wavefronts per MAC (24 LDS.32 per 16384 MACs of a warp against 128
+// LDS.128 quarter-warp phases), which is what bounded that policy at ~55 % of the FP32 pipe.
+// hi = the TF32 the tensor core reads from an fp32 register anyway (top 19 bits), lo = the exact remainder (the core
+// reads its top 19 bits in turn): two full-rate ALU instructions per element.  (cvt.rna.tf32.f32 would round instead
+// of truncate, but it issues at conversion-unit rate and made the split as expensive as the MMAs themselves.)
+__device__ __forceinline__ void tf32_split(float x, unsigned& hi, unsigned& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void hmma_tf32_m16n8k8(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+struct Tf32x3Policy {
+    using Elem = float;
+    static constexpr int VEC = 4, KC = Geo<float>::KC, CH = Geo<float>::CH;   // 16 k per tile, 8 tiles per 128 columns
+    static constexpr int RI = 4, CJ = 16, CV = 2;
+    static constexpr bool kSwizzled = true;
+    int lane, rg, cg, part;
+    bool leader;
+    __device__ explicit Tf32x3Policy(int tid) {
+        lane = tid & 31;
+        const int warp = tid >> 5;
+        rg = warp >> 1;   // rows 32 rg .. 32 rg + 31
+        cg = warp & 1;    // candidates 64 cg .. 64 cg + 63
+        part = rg;
+        leader = (lane >> 2) == 0;
+    }
+    // accumulator (i, j): m-tile i>>1, row half i&1 (the instruction's c0/c1 vs c2/c3), n-tile j>>1, column j&1
+    __device__ __forceinline__ int row_of(int i) const { return 32 * rg + 16 * (i >> 1) + 8 * (i & 1) + (lane >> 2); }
+    __device__ __forceinline__ int cand_of(int j) const { return 64 * cg + 8 * (j >> 1) + 2 * (lane & 3) + (j & 1); }
+    __host__ __device__ static __forceinline__ int a_index(int k, int r) { return k * BM + (r ^ (8 * (k & 3))); }
+    __host__ __device__ static __forceinline__ int b_index(int k, int c) { return k * BN + (c ^ (8 * (k & 3))); }
+    __device__ __forceinline__ double reduce_rows(double v) const {
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        return v;
+    }
+    template <bool DIAG>
+    __device__ __forceinline__ void mma_tile(float (&acc)[RI][CJ], const float* __restrict__ As,
+                                             const float* __restrict__ Bs, int /*kc*/) const {
+        const int kq = lane & 3, q8 = lane >> 2, swz = 8 * kq;   // k = kq (+4): k & 3 == kq for both
+#pragma unroll
+        for (int s = 0; s < KC / 8; ++s) {
+            const float* const A0 = As + (8 * s + kq) * BM;       // k = 8 s + kq
+            const float* const A1 = A0 + 4 * BM;                  // k + 4
+            const float* const B0 = Bs + (8 * s + kq) * BN;
+            const float* const B1 = B0 + 4 * BN;
+            unsigned ah[2][4], al[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int r = 32 * rg + 16 * mt + q8;
+                const float a[4] = {A0[r ^ swz], A0[(r + 8) ^ swz], A1[r ^ swz], A1[(r + 8) ^ swz]};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) tf32_split(a[u], ah[mt][u], al[mt][u]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < CJ / 2; ++nt) {
+                const int c = 64 * cg + 8 * nt + q8;
+                const float b[2] = {B0[c ^ swz], B1[c ^ swz]};
+                unsigned bh[2], bl[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) tf32_split(b[u], bh[u], bl[u]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    // the tensor core adds into its accumulator with truncation: the 8-term partial products are summed
+                    // from zero and joined to the running fp32 sum by a round-to-nearest FADD (no drift over long k)
+                    float c4[4] = {0.f, 0.f, 0.f, 0.f};
+                    hmma_tf32_m16n8k8(c4, al[mt], bh);   // small terms first
+                    hmma_tf32_m16n8k8(c4, ah[mt], bl);
+                    hmma_tf32_m16n8k8(c4, ah[mt], bh);
+                    acc[2 * mt][2 * nt] += c4[0];
+                    acc[2 * mt][2 * nt + 1] += c4[1];
+                    acc[2 * mt + 1][2 * nt] += c4[2];
+                    acc[2 * mt + 1][2 * nt + 1] += c4[3];
+                }
+            }
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // Engine = (policy of the off-diagonal GEMM, policy of the diagonal GEMM).
 //   Engine<DmmaPolicy, DmmaPolicy>          fp64 everywhere                                   (dtype f64)
 //   Engine<FmaPolicy<double>, FmaPolicy<double>>  fp64 on the FMA pipe (A/B comparison only)
-//   Engine<FmaPolicy<float>, DmmaPolicy>    "mixed": fp32 FFMA for the n^2/2 off-diagonal work, fp64 DMMA for the
+//   Engine<Tf32x3Policy, DmmaPolicy>        "mixed": 3xTF32 tensor MMAs (fp32-grade) for the n^2/2 off-diagonal work
+//   (Engine<FmaPolicy<float>, DmmaPolicy>    the same with register-tiled FFMA: BOPY_B200_F32_ENGINE=fma), fp64 DMMA for the
 //                                           diagonal solve; L_IJ and V are stored in fp32, inv(L_II) in fp64; the
 //                                           residual tile lives in shared memory in fp64 (seeded with the fp64 K*),
 //                                           fp32 partial sums span one 128-column block of L only   (dtype f32)
@@ -264,7 +353,8 @@ template <class PG_, class PD_> struct Engine {
 };
 using EngineF64 = Engine<DmmaPolicy, DmmaPolicy>;
 using EngineF64Fma = Engine<FmaPolicy<double>, FmaPolicy<double>>;
-using EngineMixed = Engine<FmaPolicy<float>, DmmaPolicy>;
+using EngineMixed = Engine<Tf32x3Policy, DmmaPolicy>;
+using EngineMixedFma = Engine<FmaPolicy<float>, DmmaPolicy>;
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 template <class E> constexpr size_t sweep_smem_base(int d) {

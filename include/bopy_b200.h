@@ -64,7 +64,7 @@ enum bopy_kernel { BOPY_KERNEL_RBF = 0, BOPY_KERNEL_MATERN12 = 1, BOPY_KERNEL_MA
 enum bopy_acq { BOPY_ACQ_NONE = -1, BOPY_ACQ_LCB = 0, BOPY_ACQ_EI = 1, BOPY_ACQ_POI = 2 };
 
 /* what bopy_measure_peak times */
-enum bopy_peak { BOPY_PEAK_FP64_FMA = 0, BOPY_PEAK_FP32_FMA = 1, BOPY_PEAK_FP64_MMA = 2 };
+enum bopy_peak { BOPY_PEAK_FP64_FMA = 0, BOPY_PEAK_FP32_FMA = 1, BOPY_PEAK_FP64_MMA = 2, BOPY_PEAK_TF32_MMA_SYNC = 3 };
 
 int bopy_abi_version(void);
 const char* bopy_last_error(void);
