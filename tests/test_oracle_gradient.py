@@ -52,3 +52,45 @@ def test_matern12_gradient_away_from_the_kink():
 def test_partials_nan_rule():
     dm, dv = O.acquisition_partials("ei", np.array([0.0, 0.0]), np.array([0.0, -1.0]), eta=0.1)
     assert np.isnan(dm).all() and np.isnan(dv).all()
+
+
+def test_multistart_step_rule_minimises_a_box_constrained_quadratic():
+    """The lock-step projected-gradient rule (restated from multistart_step_kernel) on f(x) = 1/2 (x-c)' A (x-c):
+    monotone, stays in the box, reaches the projected optimum; NaN trial values are never accepted."""
+    rng = np.random.default_rng(0)
+    S, d = 64, 4
+    lo, hi = np.zeros(d), np.ones(d)
+    A = np.diag([1.0, 10.0, 100.0, 3.0])
+    c = np.array([0.3, 0.7, 1.4, -0.2])          # two coordinates of the optimum are pinned to the box
+
+    def fg(x):
+        r = x - c
+        return 0.5 * np.einsum("sd,de,se->s", r, A, r), r @ A
+
+    xt = rng.random((S, d))
+    xc, gc, fc, alpha = np.empty_like(xt), np.empty_like(xt), np.empty(S), np.ones(S)
+    history = []
+    for k in range(80):
+        ft, gt = fg(xt)
+        if k == 5:
+            ft = ft.copy()
+            ft[::2] = np.nan                      # a NaN evaluation must be rejected, not adopted
+        O.multistart_step(lo, hi, xc, fc, gc, xt, ft, gt, alpha, first=(k == 0))
+        assert (xt >= lo).all() and (xt <= hi).all() and not np.isnan(fc).any()
+        history.append(fc.copy())
+    history = np.array(history)
+    assert (np.diff(history, axis=0) <= 0).all()                       # monotone per start
+    best = np.clip(c, lo, hi)
+    assert np.abs(xc - best).max() < 1e-6
+
+
+def test_multistart_optimizer_argument_validation():
+    from bopy_b200.bounds import Bound, Bounds
+    from bopy_b200.optimizer import MultiStartOptimizer
+    b = Bounds([Bound(0.0, 1.0)])
+    with pytest.raises(ValueError, match="method"):
+        MultiStartOptimizer(None, b, method="newton")
+    with pytest.raises(ValueError, match="non-negative"):
+        MultiStartOptimizer(None, b, iterations=-1)
+    with pytest.raises(ValueError, match="multiple of 128"):
+        MultiStartOptimizer(None, b, points_per_start=100)
