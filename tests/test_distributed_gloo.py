@@ -98,3 +98,73 @@ def test_minloc_reduction_properties():
         assert reduce_minloc([reduce_minloc(recs[:half]), reduce_minloc(recs[half:])])[1] == expected
 
     check()
+
+
+class _ToyNative:
+    """CPU stand-in for NativeGP in the multi-start optimiser: a(x) = |x - c|^2 with its gradient."""
+
+    c = np.array([0.3, 0.6, 0.9])
+
+    def value_and_grad(self, xt, kind, **kw):
+        r = xt - torch.from_numpy(self.c)
+        return (r * r).sum(1), 2.0 * r, None, None
+
+
+class _ToySurrogate:
+    native = _ToyNative()
+
+    def supports_gradient(self):
+        return True
+
+    def acquisition_segment_argmin(self, kind, xs, seg_len, index_base=0, **kw):
+        v = ((xs - torch.from_numpy(_ToyNative.c)) ** 2).sum(1).reshape(-1, seg_len)
+        idx = v.argmin(1)
+        return v.gather(1, idx[:, None])[:, 0], index_base + torch.arange(len(idx)) * seg_len + idx
+
+
+class _ToyAcquisition:
+    kind = "lcb"
+    surrogate = _ToySurrogate()
+
+    def native_args(self):
+        return {}
+
+
+def _multistart_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bopy_b200._native as native
+    from bopy_b200.bounds import Bound, Bounds
+    from bopy_b200.optimizer import MultiStartOptimizer
+    from oracle import gp_oracle as O
+    native.candidates_uniform = lambda seed, base, mm, lo, hi, device=None: torch.from_numpy(
+        O.candidates_uniform(seed, base, mm, lo, hi))
+    native.gather_rows = lambda xs, idx, index_base=0: xs[idx - index_base]
+    native.multistart_step = lambda lo, hi, xc, fc, gc, xt, ft, gt, alpha, first: O.multistart_step(
+        lo, hi, xc.numpy(), fc.numpy(), gc.numpy(), xt.numpy(), ft.numpy(), gt.numpy(), alpha.numpy(), first)
+    opt = MultiStartOptimizer(_ToyAcquisition(), Bounds([Bound(0.0, 1.0)] * 3), n_starts=5, n_candidates=5 * 128,
+                              seed=4, distributed=True, method="gradient", iterations=30)
+    res = opt.optimize()
+    xs, vs = opt.local_minima()
+    out.put((rank, res.x_min.tolist(), res.f_min.tolist(), len(vs)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_multistart_shards_starts_over_gloo_ranks():
+    """5 starts over 2 ranks (3 + 2): each rank refines its own starts, one min-loc picks the winner and its owner
+    broadcasts the point -- every rank returns the same (x_min, f_min)."""
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_multistart_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    got = sorted(out.get() for _ in range(2))
+    (r0, x0, f0, n0), (r1, x1, f1, n1) = got
+    assert (n0, n1) == (3, 2)
+    assert x0 == x1 and f0 == f1
+    assert np.allclose(x0, [_ToyNative.c], atol=1e-8) and f0[0] < 1e-14
