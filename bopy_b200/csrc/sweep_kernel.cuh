@@ -356,6 +356,7 @@ using EngineF64Fma = Engine<FmaPolicy<double>, FmaPolicy<double>>;
 using EngineMixed = Engine<Tf32x3Policy, DmmaPolicy>;
 using EngineMixedFma = Engine<FmaPolicy<float>, DmmaPolicy>;
 
+constexpr int FLUSH_BLOCKS = 4;   // mixed engine: 128-column blocks of L per fp32 partial sum (256 terms)
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 template <class E> constexpr size_t sweep_smem_base(int d) {
     return (size_t)2 * STAGES * TILE_BYTES + (size_t)BM * BN * sizeof(typename E::TD) +
@@ -577,8 +578,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done with the stage
                 if constexpr (E::kMixed) {
-                    // fp32 partial sums cover one 128-column block of L only; they are folded into the fp64 tile
-                    if ((t + 1) % CHG == 0) {
+                    // fp32 partial sums cover FLUSH_BLOCKS 128-column blocks of L only; they are folded into the fp64 tile
+                    if ((t + 1) % (FLUSH_BLOCKS * CHG) == 0 || t + 1 == T_gemm) {
 #pragma unroll
                         for (int i = 0; i < PG::RI; ++i) {
                             const int row = pg.row_of(i);
