@@ -43,6 +43,8 @@ _SIGNATURES = {
     "bopy_acq_eval": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p]),
     "bopy_acq_argmin": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                                 c_void_p]),
+    "bopy_acq_argmin_pruned": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                                       POINTER(c_int64), c_void_p]),
     "bopy_acq_segment_argmin": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_int64, c_int64,
                                         c_void_p, c_void_p, c_void_p]),
     "bopy_candidates_around": (c_int, [c_uint64, c_void_p, c_int64, c_int, c_int, POINTER(c_double), POINTER(c_double),
@@ -298,6 +300,20 @@ class NativeGP:
                                                    _ptr(val), _ptr(grad), _ptr(mean), _ptr(var), _stream(dev)),
                   "bopy_acq_value_and_grad")
         return val, grad, mean, var
+
+    def argmin_pruned(self, Xs, acq, eta=0.0, kappa=2.0, index_base=0):
+        """Branch-and-bound arg-min over device candidates Xs (m, d): (min_val, min_idx) device tensors and a dict
+        with the number of candidates that went through the full sweep."""
+        torch = require_cuda()
+        m = Xs.shape[0]
+        minv = torch.empty(1, dtype=torch.float64, device=self.device)
+        mini = torch.empty(1, dtype=torch.int64, device=self.device)
+        stats = (c_int64 * 3)()
+        with torch.cuda.device(self.device):
+            check(self.lib.bopy_acq_argmin_pruned(self._handle, ACQ_IDS[acq], float(eta), float(kappa), _ptr(Xs), m,
+                                                  int(index_base), _ptr(minv), _ptr(mini), stats, _stream(self.device)),
+                  "bopy_acq_argmin_pruned")
+        return minv, mini, {"candidates": stats[0], "sample": stats[1], "swept": stats[2]}
 
     def segment_argmin(self, Xs, seg_len, acq, eta=0.0, kappa=2.0, index_base=0):
         """Per-segment arg-min of the acquisition over consecutive segments of `seg_len` rows of Xs (one launch).

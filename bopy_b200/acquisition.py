@@ -78,13 +78,14 @@ class _MomentAcquisition(AcquisitionFunction):
             raise TypeError("value_and_grad needs a B200GPSurrogate")
         return sur.acquisition_value_and_grad(self.kind, x, **self.native_args())
 
-    def argmin(self, x, index_base: int = 0) -> Tuple[int, float]:
+    def argmin(self, x, index_base: int = 0, prune: bool = False) -> Tuple[int, float]:
         """Index and value of the smallest acquisition value over the rows of `x` (fused on the device;
-        np.argmin's rules: first minimum, first NaN wins)."""
+        np.argmin's rules: first minimum, first NaN wins).  prune=True: branch and bound on a B200 surrogate (see
+        B200GPSurrogate.acquisition_argmin)."""
         self._validate_ok_for_predicting(x)
         sur = self.surrogate
         if hasattr(sur, "acquisition_argmin"):
-            return sur.acquisition_argmin(self.kind, x, index_base=index_base, **self.native_args())
+            return sur.acquisition_argmin(self.kind, x, index_base=index_base, prune=prune, **self.native_args())
         mean_d, var_d = self._foreign_moments(x if isinstance(x, np.ndarray) else x.cpu().numpy())
         _, minv, mini = _native.acquisition_from_moments(self.kind, mean_d, var_d, want_min=True,
                                                          index_base=index_base, **self.native_args())
@@ -158,8 +159,8 @@ class KriggingBeliever(SequentialBatchAcquisitionFunction):
     def _f(self, x: np.ndarray) -> np.ndarray:
         return self.base_acquisition(x)
 
-    def argmin(self, x, index_base: int = 0):
-        return self.base_acquisition.argmin(x, index_base=index_base)
+    def argmin(self, x, index_base: int = 0, prune: bool = False):
+        return self.base_acquisition.argmin(x, index_base=index_base, prune=prune)
 
     def start_batch(self) -> None:
         self.n_data = len(self.surrogate.x)

@@ -16,6 +16,7 @@
 #include "fit_kernels.cuh"
 #include "grad_kernel.cuh"
 #include "probe_kernel.cuh"
+#include "prune_kernels.cuh"
 #include "sweep_kernel.cuh"
 
 using namespace bopy;
@@ -250,10 +251,38 @@ template <int NA> int launch_grad_k(int kernel, const GradParams& p, int grid, c
 
 constexpr long long HOST_CALL_MAX_M = 4096;
 
+template <int KIND> void launch_mean_bound_k(const bopy_gp* gp, const double* Xs, long long m, const LsParam& ls, double sd_max,
+                                             int acq, double eta, double kappa, double* mean_out, double* bound_out,
+                                             cudaStream_t st) {
+    const unsigned grid = (unsigned)((m + PRUNE_NT - 1) / PRUNE_NT);
+    const size_t smem = (size_t)(gp->d + 1) * BM * sizeof(double);
+#define BOPY_MB(DP) \
+    mean_bound_kernel<KIND, DP><<<grid, PRUNE_NT, smem, st>>>(gp->Xt, Xs, m, gp->n_blocks, gp->d, ls, gp->amp, gp->y_mean, \
+                                                              gp->y_std, sd_max, acq, eta, kappa, mean_out, bound_out)
+    if (gp->d <= 2) BOPY_MB(2);
+    else if (gp->d <= 4) BOPY_MB(4);
+    else if (gp->d <= 8) BOPY_MB(8);
+    else if (gp->d <= 16) BOPY_MB(16);
+    else BOPY_MB(32);
+#undef BOPY_MB
+}
+
+void launch_mean_bound(const bopy_gp* gp, const double* Xs, long long m, double sd_max, int acq, double eta, double kappa,
+                       double* mean_out, double* bound_out, cudaStream_t st) {
+    LsParam ls;
+    for (int q = 0; q < MAX_D; ++q) ls.v[q] = q < gp->d ? gp->ls[q] : 1.0;
+    switch (gp->kernel) {
+        case BOPY_KERNEL_RBF: launch_mean_bound_k<K_RBF>(gp, Xs, m, ls, sd_max, acq, eta, kappa, mean_out, bound_out, st); break;
+        case BOPY_KERNEL_MATERN12: launch_mean_bound_k<K_M12>(gp, Xs, m, ls, sd_max, acq, eta, kappa, mean_out, bound_out, st); break;
+        case BOPY_KERNEL_MATERN32: launch_mean_bound_k<K_M32>(gp, Xs, m, ls, sd_max, acq, eta, kappa, mean_out, bound_out, st); break;
+        default: launch_mean_bound_k<K_M52>(gp, Xs, m, ls, sd_max, acq, eta, kappa, mean_out, bound_out, st); break;
+    }
+}
+
 // the one place the sweep is launched from
 int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, double kappa, double* mean_out,
               double* var_out, double* acq_out, long long index_base, double* min_val, long long* min_idx,
-              void* Vws, int slot_per_tile, cudaStream_t st, MinLoc* tile_records = nullptr) {
+              void* Vws, int slot_per_tile, cudaStream_t st, MinLoc* tile_records = nullptr, bool allow_probe = true) {
     SweepParams p;
     std::memset(&p, 0, sizeof(p));
     p.Lt = gp->Lt;
@@ -280,7 +309,7 @@ int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, d
     p.acq_out = acq_out;
     p.index_base = index_base;
     const bool want_min = (min_val != nullptr || min_idx != nullptr);
-    if (probe_applies(gp, m, slot_per_tile, tile_records)) {
+    if (allow_probe && probe_applies(gp, m, slot_per_tile, tile_records)) {
         // small m: latency path, the forward substitution spread over the block rows of L (probe_kernel.cuh)
         const ProbePlan pl = probe_plan(gp, m);
         int rc = launch_probe(gp, pl, Xs, m, acq, eta, kappa, mean_out, var_out, acq_out, index_base,
@@ -784,6 +813,86 @@ int bopy_acq_argmin(bopy_gp* gp, int acq, double eta, double kappa, const double
     if (min_val_out == nullptr || min_idx_out == nullptr) return fail(BOPY_ERR_BAD_ARG, "min outputs are NULL");
     return bopy_gp_posterior_acq(gp, Xs_dev, m, acq, eta, kappa, nullptr, nullptr, nullptr, index_base, min_val_out,
                                  min_idx_out, stream);
+}
+
+int bopy_acq_argmin_pruned(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
+                           int64_t index_base, double* min_val_out, int64_t* min_idx_out, int64_t* stats_out_host,
+                           void* stream) {
+    int rc = check_ready(gp);
+    if (rc != BOPY_OK) return rc;
+    if (Xs_dev == nullptr || min_val_out == nullptr || min_idx_out == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "Xs_dev / min outputs are NULL");
+    if (m < 1) return fail(BOPY_ERR_BAD_ARG, "m must be >= 1 (got %lld)", (long long)m);
+    if (acq < BOPY_ACQ_LCB || acq > BOPY_ACQ_POI) return fail(BOPY_ERR_BAD_ARG, "unknown acquisition id %d", acq);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    long long* const min_idx = reinterpret_cast<long long*>(min_idx_out);
+    // every sweep in here runs the THROUGHPUT kernel, whatever its size: the values must be the ones the plain sweep of
+    // all m candidates produces, bit for bit (the latency path orders a few partial sums differently)
+    const long long sample = std::min<long long>(m, 8192);
+    if (m <= 4 * sample) {   // nothing to gain: plain sweep
+        if (stats_out_host) stats_out_host[0] = m, stats_out_host[1] = 0, stats_out_host[2] = m;
+        return run_sweep(gp, Xs_dev, m, acq, eta, kappa, nullptr, nullptr, nullptr, index_base, min_val_out, min_idx,
+                         gp->Vws, 0, st);   // exactly what bopy_acq_argmin does for this m
+    }
+    const int d = gp->d;
+    const long long per_block = (long long)PRUNE_NT * COMPACT_ITEMS;
+    const int nblocks = (int)((m + per_block - 1) / per_block);
+    // one pooled scratch: bounds (m), incumbent value (1), sample rows (sample x d), survivor rows (m x d worst case is
+    // never needed: sized after the count), block counts, total
+    double* bound = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&bound),
+                             ((size_t)m + 2 + (size_t)sample * d) * sizeof(double) + ((size_t)nblocks + 4) * sizeof(unsigned) + 16, st));
+    double* const thr = bound + m;                    // incumbent value, then reused
+    double* const srows = thr + 2;
+    unsigned* const counts = reinterpret_cast<unsigned*>(srows + (size_t)sample * d);
+    long long* const total = reinterpret_cast<long long*>(thr + 1);
+    auto cleanup = [&]() { cudaFreeAsync(bound, st); };
+    // 1. lower bounds from the posterior mean
+    const double sd_max = std::sqrt((gp->amp + gp->noise)) * std::fabs(gp->y_std);
+    launch_mean_bound(gp, Xs_dev, m, sd_max, acq, eta, kappa, nullptr, bound, st);
+    // 2. incumbent: the true minimum over a strided sample
+    const long long stride = m / sample;
+    strided_rows_kernel<<<(unsigned)((sample * d + 255) / 256), 256, 0, st>>>(Xs_dev, d, stride, sample, srows);
+    rc = run_sweep(gp, srows, sample, acq, eta, kappa, nullptr, nullptr, nullptr, 0, thr, min_idx, gp->Vws, 0, st, nullptr, false);
+    if (rc != BOPY_OK) {
+        cleanup();
+        return rc;
+    }
+    // 3. survivors = {bound <= incumbent}, ascending order kept
+    compact_count_kernel<<<nblocks, PRUNE_NT, 0, st>>>(bound, m, thr, counts);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, total);
+    long long count = 0;
+    cudaError_t e = cudaMemcpyAsync(&count, total, sizeof(long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(BOPY_ERR_CUDA, "pruned argmin failed: %s", cudaGetErrorString(e));
+    }
+    if (stats_out_host) stats_out_host[0] = m, stats_out_host[1] = sample, stats_out_host[2] = count;
+    if (count <= 0 || count > m / 2) {   // bound not selective (or an all-NaN incumbent): the plain sweep is as good
+        cleanup();
+        if (stats_out_host) stats_out_host[2] = m;
+        return run_sweep(gp, Xs_dev, m, acq, eta, kappa, nullptr, nullptr, nullptr, index_base, min_val_out, min_idx,
+                         gp->Vws, 0, st, nullptr, false);
+    }
+    long long* idx_list = nullptr;
+    e = cudaMallocAsync(reinterpret_cast<void**>(&idx_list), (size_t)count * (sizeof(long long) + (size_t)d * sizeof(double)), st);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(BOPY_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    double* const rows = reinterpret_cast<double*>(idx_list + count);
+    compact_scatter_kernel<<<nblocks, PRUNE_NT, 0, st>>>(bound, m, thr, counts, Xs_dev, d, idx_list, rows);
+    // 4. the full fused sweep over the survivors only; local index -> original index
+    rc = run_sweep(gp, rows, count, acq, eta, kappa, nullptr, nullptr, nullptr, 0, min_val_out, min_idx, gp->Vws, 0, st, nullptr, false);
+    if (rc == BOPY_OK) {
+        remap_index_kernel<<<1, 1, 0, st>>>(idx_list, count, index_base, min_idx);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(BOPY_ERR_CUDA, "remap_index_kernel failed to launch");
+    }
+    cudaFreeAsync(idx_list, st);
+    cleanup();
+    return rc;
 }
 
 int bopy_acq_segment_argmin(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,

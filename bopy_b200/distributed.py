@@ -61,7 +61,7 @@ def all_reduce_minloc(value: float, index: int, group=None, device=None) -> Tupl
     return reduce_minloc(records)
 
 
-def sharded_argmin(acquisition, seed: int, lowers, uppers, m: int, group=None, incumbent=None):
+def sharded_argmin(acquisition, seed: int, lowers, uppers, m: int, group=None, incumbent=None, prune: bool = False):
     """Each rank sweeps its slice of the m counter-based candidates; returns (x (d,), value) on every rank."""
     import torch
     import torch.distributed as dist
@@ -78,7 +78,8 @@ def sharded_argmin(acquisition, seed: int, lowers, uppers, m: int, group=None, i
         xs = _native.candidates_uniform(seed, start, stop - start, lowers, uppers)
         if incumbent is not None and start == 0:
             xs[0] = torch.as_tensor(incumbent, dtype=torch.float64, device=xs.device)
-        index, value = acquisition.argmin(xs, index_base=start)
+        index, value = (acquisition.argmin(xs, index_base=start, prune=True) if prune
+                        else acquisition.argmin(xs, index_base=start))
     value, index = all_reduce_minloc(value, index, group=group)
     if incumbent is not None and index == 0:
         x = np.asarray(incumbent, dtype=np.float64)

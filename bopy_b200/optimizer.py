@@ -61,11 +61,15 @@ class CandidateSweepOptimizer(Optimizer):
     process_group : torch.distributed group or None
         With a group, each rank sweeps its contiguous slice of the index range and ONE min-loc
         all-gather picks the winner (see bopy_b200/distributed.py).
+    prune : bool
+        Branch and bound inside every sweep (`bopy_acq_argmin_pruned`): candidates whose mean-only lower bound cannot
+        beat the best of a strided sample skip the full posterior.  Same winner; see B200GPSurrogate.acquisition_argmin
+        for the one caveat (NaN acquisition values).
     """
 
     def __init__(self, acquisition_function: AcquisitionFunction, bounds: Bounds, n_candidates: int = 1 << 20,
                  zoom_rounds: int = 0, zoom_candidates: int = 1 << 14, zoom_shrink: float = 0.25, seed: int = 0,
-                 process_group=None, distributed: bool = False):
+                 process_group=None, distributed: bool = False, prune: bool = False):
         super().__init__(acquisition_function, bounds)
         if n_candidates < 1:
             raise ValueError("`n_candidates` must be positive.")
@@ -76,6 +80,7 @@ class CandidateSweepOptimizer(Optimizer):
         self.seed = int(seed)
         self.process_group = process_group
         self.distributed = distributed or process_group is not None
+        self.prune = bool(prune)
         self._calls = 0
 
     def _sweep_box(self, seed, lowers, uppers, m, incumbent=None):
@@ -83,12 +88,13 @@ class CandidateSweepOptimizer(Optimizer):
         from .distributed import sharded_argmin
         acq = self.acquisition_function
         if self.distributed:
-            return sharded_argmin(acq, seed, lowers, uppers, m, group=self.process_group, incumbent=incumbent)
+            return sharded_argmin(acq, seed, lowers, uppers, m, group=self.process_group, incumbent=incumbent,
+                                  prune=self.prune)
         torch = _native.require_cuda()
         xs = _native.candidates_uniform(seed, 0, m, lowers, uppers)
         if incumbent is not None:
             xs[0] = torch.as_tensor(incumbent, dtype=torch.float64, device=xs.device)
-        idx, val = acq.argmin(xs)
+        idx, val = acq.argmin(xs, prune=True) if self.prune else acq.argmin(xs)
         return xs[idx].cpu().numpy(), val
 
     def _optimize(self) -> Tuple[np.ndarray, np.ndarray]:

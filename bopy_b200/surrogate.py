@@ -249,10 +249,18 @@ class B200GPSurrogate(Surrogate):
         out = self.native.sweep(self.native.candidates(x), acq=kind, eta=eta, kappa=kappa, want_acq=True)
         return out["acq"].cpu().numpy()
 
-    def acquisition_argmin(self, kind: str, x, eta: float = 0.0, kappa: float = 2.0, index_base: int = 0):
+    def acquisition_argmin(self, kind: str, x, eta: float = 0.0, kappa: float = 2.0, index_base: int = 0,
+                           prune: bool = False):
         """Fused posterior -> acquisition -> argmin over the rows of x (numpy or device tensor).
 
-        Returns (index, value) with np.argmin's rules (first minimum; first NaN wins)."""
+        Returns (index, value) with np.argmin's rules (first minimum; first NaN wins).
+        prune=True: branch and bound (`bopy_acq_argmin_pruned`): a lower bound from the posterior mean discards most
+        candidates before the full sweep; same index and value, except that candidates with a NaN acquisition (posterior
+        variance rounded to <= 0) may be skipped.  `last_prune_stats` holds how many candidates were fully evaluated."""
+        if prune:
+            minv, mini, self.last_prune_stats = self.native.argmin_pruned(self.native.candidates(x), kind, eta=eta,
+                                                                          kappa=kappa, index_base=index_base)
+            return int(mini.item()), float(minv.item())
         out = self.native.sweep(self.native.candidates(x), acq=kind, eta=eta, kappa=kappa, want_min=True,
                                 index_base=index_base)
         return int(out["min_idx"].item()), float(out["min_val"].item())

@@ -165,6 +165,19 @@ int bopy_acq_eval(bopy_gp* gp, int acq, double eta, double kappa, const double* 
 int bopy_acq_argmin(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
                     int64_t index_base, double* min_val_out, int64_t* min_idx_out, void* stream);
 
+/*
+ * The same arg-min by branch and bound (opt-in).  A rigorous lower bound of the acquisition is formed per candidate from
+ * the posterior mean alone (var <= prior variance; LCB / EI / POI are monotone in the standard deviation on the side
+ * that matters) at 1/40 of the cost of the full posterior; the true minimum over a strided sample of 8192 candidates is
+ * the incumbent; only candidates whose bound does not exceed it -- kept in their original order -- go through the fused
+ * sweep.  Index and value are those of bopy_acq_argmin bit for bit, EXCEPT that a candidate whose variance rounds to
+ * <= 0 (NaN acquisition, which np.argmin would return first) may be pruned.  stats_out_host (nullable, 3 values):
+ * candidates, sample size, candidates that went through the full sweep.  Synchronises the stream once internally.
+ */
+int bopy_acq_argmin_pruned(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
+                           int64_t index_base, double* min_val_out, int64_t* min_idx_out, int64_t* stats_out_host,
+                           void* stream);
+
 /* Segmented arg-min: the m candidates are cut into consecutive segments of seg_len (a multiple of 128) and the
  * fused sweep returns one (value, index) per segment: seg_val_out / seg_idx_out (ceil(m / seg_len),).  This is the
  * batched multi-start primitive: one segment per start, all starts in one launch. */
