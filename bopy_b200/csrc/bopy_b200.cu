@@ -491,7 +491,7 @@ void launch_gram(const bopy_gp* gp, const double* X, const LsParam& ls, double a
 
 // in-place blocked Cholesky of the lower triangle of A (n x n, leading dimension ld); Dinv receives inv(L_JJ)
 void launch_cholesky(double* A, int n, int ld, int nb, double* Dinv, int* status, cudaStream_t st) {
-    const size_t chol_smem = ((size_t)BM * (BM + 1) + 2 * BM) * sizeof(double);
+    const size_t chol_smem = ((size_t)BM * (BM + 1) + BM + 2) * sizeof(double);
     cudaFuncSetAttribute(chol_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem);
     for (int J = 0; J < nb; ++J) {
         chol_block_kernel<<<1, CHOL_NT, chol_smem, st>>>(A, n, ld, J, Dinv, status);

@@ -44,85 +44,145 @@ __global__ void gram_kernel(const double* __restrict__ X, int n, int d, LsParam 
 
 // In-place Cholesky of the diagonal block J (identity padded beyond n) + its inverse, all in shared memory.
 // One CTA of CHOL_NT threads.  status[0] is set to J+1 if a non-positive pivot is met (not positive definite).
+// Panel-blocked (16 columns at a time) so that the 128 columns cost 8 x 3 block-wide barriers instead of 256:
+//   (a) the 16 x 16 diagonal block of the panel is factorised by one warp (warp-level barriers only),
+//   (b) every row below it solves its 16 panel entries against that factor on its own (one thread per row),
+//   (c) the trailing lower triangle takes the rank-16 update with no barrier between the 16 rank-1 terms.
+// The inverse is column-parallel and barrier-free: thread j forward-substitutes column j of inv(L_JJ), parking it in
+// row j of the (unused) strict upper triangle of the working block.
 constexpr int CHOL_NT = 256;
+constexpr int CHOL_PANEL = 16;
 __global__ void __launch_bounds__(CHOL_NT) chol_block_kernel(double* A, int n, int ld, int J, double* Dinv, int* status) {
-    extern __shared__ double sm[];          // [BM][BM+1] working block, then col[BM], dg[BM]
-    constexpr int LD = BM + 1;
-    double* const col = sm + BM * LD;
-    double* const dg = col + BM;
-    const int tid = threadIdx.x, base = J * BM;
+    extern __shared__ double sm[];          // [BM][BM+1] working block, then rdg[BM] (1 / L_kk), fail flag
+    constexpr int LD = BM + 1, PW = CHOL_PANEL;
+    double* const rdg = sm + BM * LD;
+    int* const fail = reinterpret_cast<int*>(rdg + BM);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, base = J * BM;
     for (int e = tid; e < BM * BM; e += CHOL_NT) {
         const int r = e / BM, c = e - r * BM, gr = base + r, gc = base + c;
         double v = (r == c) ? 1.0 : 0.0;
         if (gr < n && gc < n && c <= r) v = A[(size_t)gr * ld + gc];
         sm[r * LD + c] = (c <= r) ? v : 0.0;
     }
+    if (tid == 0) *fail = 0;
     __syncthreads();
-    // right-looking factorisation: column k is scaled, then the trailing lower triangle gets a rank-1 update
-    for (int k = 0; k < BM; ++k) {
-        const double akk = sm[k * LD + k];
-        if (!(akk > 0.0)) {               // uniform: every thread reads the same value
+    for (int k0 = 0; k0 < BM; k0 += PW) {
+        // (a) unblocked right-looking Cholesky of the PW x PW diagonal block, one warp
+        if (warp == 0) {
+            for (int k = 0; k < PW; ++k) {
+                const int kk = k0 + k;
+                const double akk = sm[kk * LD + kk];
+                if (!(akk > 0.0)) {           // warp-uniform
+                    if (lane == 0) *fail = 1;
+                    break;
+                }
+                const double lkk = sqrt(akk);
+                __syncwarp();
+                if (lane == k) sm[kk * LD + kk] = lkk;
+                if (lane > k && lane < PW) sm[(k0 + lane) * LD + kk] /= lkk;
+                __syncwarp();
+                for (int e = lane; e < PW * PW; e += 32) {
+                    const int r = e / PW, c = e - r * PW;
+                    if (c > k && c <= r)
+                        sm[(k0 + r) * LD + k0 + c] = fma(-sm[(k0 + r) * LD + kk], sm[(k0 + c) * LD + kk], sm[(k0 + r) * LD + k0 + c]);
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (*fail) {
             if (tid == 0) status[0] = J + 1;
             return;
         }
-        const double lkk = sqrt(akk);
-        if (tid == 0) dg[k] = lkk;        // the diagonal is collected aside so nobody races on sm[k][k]
-        if (tid > k && tid < BM) sm[tid * LD + k] = sm[tid * LD + k] / lkk;
+        // (b) panel rows below the diagonal block: x L16^T = a, one thread per row
+        if (tid < BM && tid >= k0 + PW) {
+            double x[PW];
+#pragma unroll
+            for (int c = 0; c < PW; ++c) {
+                double sacc = sm[tid * LD + k0 + c];
+#pragma unroll
+                for (int k = 0; k < c; ++k) sacc = fma(-x[k], sm[(k0 + c) * LD + k0 + k], sacc);
+                x[c] = sacc / sm[(k0 + c) * LD + k0 + c];
+            }
+#pragma unroll
+            for (int c = 0; c < PW; ++c) sm[tid * LD + k0 + c] = x[c];
+        }
         __syncthreads();
+        // (c) trailing lower triangle -= panel panel^T; thread (ty, tx) owns the (r, c) with (r - t0) % 16 == ty and
+        // (c - t0) % 16 == tx; the 16 rank-1 terms are independent of one another
         {
-            // each thread owns the (r, c) with (r-k-1) % 16 == tid/16 and (c-k-1) % 16 == tid%16; the column values
-            // it needs are loaded once, the row loop is unrolled so the shared-memory latencies overlap
-            const int c0 = k + 1 + (tid & 15);
-            double lck[8];
+            const int t0 = k0 + PW, c0 = t0 + (tid & 15), r0 = t0 + (tid >> 4);
+            if (t0 < BM) {
+                double upd[8][8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) lck[j] = (c0 + 16 * j < BM) ? sm[(c0 + 16 * j) * LD + k] : 0.0;
+                for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = k + 1 + (tid >> 4) + 16 * i;
-                if (r < BM) {
-                    const double lrk = sm[r * LD + k];
+                    for (int j = 0; j < 8; ++j) upd[i][j] = 0.0;
+                for (int k = 0; k < PW; ++k) {
+                    const int kk = k0 + k;
+                    double lck[8], lrk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) lck[j] = (c0 + 16 * j < BM) ? sm[(c0 + 16 * j) * LD + kk] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) lrk[i] = (r0 + 16 * i < BM) ? sm[(r0 + 16 * i) * LD + kk] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) upd[i][j] = fma(lrk[i], lck[j], upd[i][j]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = r0 + 16 * i;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int c = c0 + 16 * j;
-                        if (c <= r) sm[r * LD + c] = fma(-lrk, lck[j], sm[r * LD + c]);
+                        if (r < BM && c <= r) sm[r * LD + c] -= upd[i][j];
                     }
                 }
             }
         }
         __syncthreads();
     }
-    if (tid < BM) sm[tid * LD + tid] = dg[tid];
-    __syncthreads();
     for (int e = tid; e < BM * BM; e += CHOL_NT) {
         const int r = e / BM, c = e - r * BM, gr = base + r, gc = base + c;
         if (gr < n && gc < n && c <= r) A[(size_t)gr * ld + gc] = sm[r * LD + c];
     }
+    if (tid < BM) rdg[tid] = 1.0 / sm[tid * LD + tid];
     __syncthreads();
-    // in-place inverse of the lower-triangular block, last column first (LAPACK trti2 order):
-    //   X[j][j] = 1 / L[j][j];  X[r][j] = -X[j][j] * sum_{k=j+1..r} X[r][k] L[k][j]   (r > j)
-    for (int j = BM - 1; j >= 0; --j) {
-        if (tid < BM) col[tid] = sm[tid * LD + j];     // column j of L, before it is overwritten
-        __syncthreads();
-        const double xjj = 1.0 / col[j];
-        if (tid == j) sm[j * LD + j] = xjj;
-        if (tid > j && tid < BM) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;   // four chains: the loop is latency bound
-            int k = j + 1;
-            for (; k + 3 <= tid; k += 4) {
-                s0 = fma(sm[tid * LD + k], col[k], s0);
-                s1 = fma(sm[tid * LD + k + 1], col[k + 1], s1);
-                s2 = fma(sm[tid * LD + k + 2], col[k + 2], s2);
-                s3 = fma(sm[tid * LD + k + 3], col[k + 3], s3);
+    // inverse: X = inv(L), one column j per lane PAIR (lane, lane ^ 16) of a warp -- warp w owns columns 16 w .. 16 w + 15,
+    // the two lanes of a pair take the even / odd k of  X[r][j] = -(sum_{k=j..r-1} L[r][k] X[k][j]) / L[r][r]  and join
+    // by one shuffle.  X[r][j] (r >= j) is parked at sm[j][r] (diagonal and strict upper triangle of row j, which
+    // nobody else touches: L is only read strictly below its diagonal from here on).  The lanes of a warp walk r and k
+    // in lock step, so the reads of L[r][k] are broadcasts and a warp-level barrier per r orders the pair's exchange.
+    {
+        const int j = 16 * warp + (lane & 15), half = lane >> 4;
+        if (half == 0) sm[j * LD + j] = rdg[j];
+        __syncwarp();
+        const int jw = 16 * warp;   // no column of this warp has entries above row jw
+        for (int r = jw + 1; r < BM; ++r) {
+            double s0 = 0.0, s1 = 0.0;
+            int k = jw + half;
+            for (; k + 2 < r; k += 4) {
+                const double x0 = k >= j ? sm[j * LD + k] : 0.0;
+                const double x1 = k + 2 >= j ? sm[j * LD + k + 2] : 0.0;
+                s0 = fma(sm[r * LD + k], x0, s0);
+                s1 = fma(sm[r * LD + k + 2], x1, s1);
             }
-            for (; k <= tid; ++k) s0 = fma(sm[tid * LD + k], col[k], s0);
-            sm[tid * LD + j] = -xjj * ((s0 + s1) + (s2 + s3));
+            if (k < r) {
+                const double x0 = k >= j ? sm[j * LD + k] : 0.0;
+                s0 = fma(sm[r * LD + k], x0, s0);
+            }
+            double sacc = s0 + s1;
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+            if (half == 0 && r > j) sm[j * LD + r] = -sacc * rdg[r];
+            __syncwarp();
         }
-        __syncthreads();
     }
+    __syncthreads();
     double* D = Dinv + (size_t)J * BM * BM;
     for (int e = tid; e < BM * BM; e += CHOL_NT) {
         const int r = e / BM, c = e - r * BM;
-        D[e] = (c <= r) ? sm[r * LD + c] : 0.0;
+        D[e] = c <= r ? sm[c * LD + r] : 0.0;
     }
 }
 
