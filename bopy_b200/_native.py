@@ -34,6 +34,7 @@ _SIGNATURES = {
                             POINTER(c_double), POINTER(c_double), c_void_p]),
     "bopy_gp_posterior_acq": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_double, c_void_p, c_void_p,
                                       c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "bopy_gp_probe_trace": (c_int, [c_void_p, POINTER(c_int64)]),
     "bopy_gp_set_latency_path": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
     "bopy_acq_value_and_grad": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p]),
@@ -231,6 +232,18 @@ class NativeGP:
         check(self.lib.bopy_gp_resize(self._handle, n), "bopy_gp_resize")
         self.n = n
         return True
+
+    def probe_trace(self, arm=False):
+        """arm=True: record time stamps in the following latency-path launches; arm=False: fetch them as an
+        (n_blocks, 8) int64 array of nanoseconds and disarm."""
+        import numpy as np
+        if arm:
+            check(self.lib.bopy_gp_probe_trace(self._handle, None), "bopy_gp_probe_trace")
+            return None
+        nb = (self.n + 127) // 128
+        buf = (c_int64 * (nb * 8))()
+        check(self.lib.bopy_gp_probe_trace(self._handle, buf), "bopy_gp_probe_trace")
+        return np.array(buf[:], dtype=np.int64).reshape(nb, 8)
 
     def set_latency_path(self, max_m):
         """Candidate sets of up to `max_m` rows take the latency path (probe_kernel); 0 switches it off.

@@ -69,6 +69,7 @@ struct bopy_gp {
     unsigned* probe_flags = nullptr;   // [probe_max_batch][n_blocks], then the role ticket
     double* probe_part = nullptr;      // [probe_max_batch][n_blocks][2][PROBE_MAX_NC]
     unsigned probe_ticket_base = 0, probe_epoch = 0;
+    long long* probe_trace = nullptr;  // [n_blocks][8] time stamps of the next latency-path launch (bopy_gp_probe_trace)
     // acquisition gradient (grad_kernel), allocated on first use: chunks of up to sm_count batches
     unsigned* grad_flags = nullptr;    // [2][sm_count][n_blocks]: W_I published / gradient shares published
     double* grad_part = nullptr;       // [sm_count][n_blocks][2][d][PROBE_MAX_NC]
@@ -224,6 +225,7 @@ int launch_probe(bopy_gp* gp, const ProbePlan& pl, const double* Xs, long long m
     }
     q.epoch = gp->probe_epoch;
     q.keep_v = keep_v;
+    q.trace = gp->probe_trace;
     int rc = pl.na == 1 ? launch_probe_k<1>(gp->kernel, q, pl.grid, st)
                         : (pl.na == 2 ? launch_probe_k<2>(gp->kernel, q, pl.grid, st)
                                       : launch_probe_k<4>(gp->kernel, q, pl.grid, st));
@@ -420,6 +422,7 @@ void bopy_gp_destroy(bopy_gp* gp) {
     cudaFree(gp->probe_records);
     cudaFree(gp->probe_flags);
     cudaFree(gp->probe_part);
+    cudaFree(gp->probe_trace);
     cudaFree(gp->grad_flags);
     cudaFree(gp->grad_part);
     cudaFree(gp->grad_mv);
@@ -686,6 +689,23 @@ int bopy_gp_resize(bopy_gp* gp, int64_t n) {
                     (long long)n, gp->n_blocks, BM);
     gp->n = n;
     gp->ready = false;
+    return BOPY_OK;
+}
+
+int bopy_gp_probe_trace(bopy_gp* gp, int64_t* stamps_out_host) {
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    if (!gp->probe_capable) return fail(BOPY_ERR_UNSUPPORTED, "this handle has no latency path");
+    const size_t bytes = (size_t)gp->n_blocks * 8 * sizeof(long long);
+    if (stamps_out_host == nullptr) {   // arm: the next latency-path launches record their batch-0 time stamps
+        if (gp->probe_trace == nullptr) CUDA_TRY(cudaMalloc(&gp->probe_trace, bytes));
+        CUDA_TRY(cudaMemset(gp->probe_trace, 0, bytes));
+        return BOPY_OK;
+    }
+    if (gp->probe_trace == nullptr) return fail(BOPY_ERR_NOT_READY, "tracing was not armed");
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(stamps_out_host, gp->probe_trace, bytes, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaFree(gp->probe_trace));
+    gp->probe_trace = nullptr;
     return BOPY_OK;
 }
 

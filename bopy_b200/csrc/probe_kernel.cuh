@@ -51,7 +51,18 @@ struct ProbeParams {
     unsigned* ticket;          // role counter (monotonic over launches)
     unsigned ticket_base, epoch;
     int keep_v;                // 1: the last block row of V is stored too (the gradient's backward solve reads all of V)
+    long long* trace;          // optional [n_blocks][8] %globaltimer stamps of batch 0 (tools/probe_trace.py), or nullptr
 };
+
+__device__ __forceinline__ long long global_timer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define BOPY_TRACE(slot)                                                                          \
+    do {                                                                                          \
+        if (p.trace != nullptr && tid == 0 && b == g && g == 0) p.trace[I * 8 + (slot)] = global_timer_ns(); \
+    } while (0)
 
 template <int NA> __host__ __device__ constexpr int probe_stages() { return NA == 4 ? 8 : 16; }
 template <int NA> constexpr size_t probe_smem_bytes(int d) {
@@ -153,6 +164,7 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
 
     for (int b = g; b < p.nbatch; b += p.groups) {
         const long long c0 = (long long)b * NC;
+        BOPY_TRACE(0);
         for (int e = tid; e < NC * p.d; e += NT) {
             const int c = e / p.d, q = e - c * p.d;
             const long long gcand = c0 + c;
@@ -218,6 +230,7 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
                 acc[i][a][1][0] = acc[i][a][1][1] = 0.0;
             }
         consumer_sync();   // K* consumed: Rs is free for the residual
+        BOPY_TRACE(1);
 
         // ---- R_I = K*_I - sum_J L_IJ V_J, V_J in the order the chain produces them --------------------------
         for (int J = 0; J < I; ++J) {
@@ -228,6 +241,7 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
                     if (++spins > PROBE_SPIN_LIMIT) __trap();
             }
             __syncwarp();
+            if (J == I - 1) BOPY_TRACE(2);
             double* const vb = Vb + (J & 1) * NA * 1024;
             for (int e = tid; e < NA * 512; e += NT) {
                 const int a = e >> 9, o = e & 511;
@@ -260,6 +274,7 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
                 *reinterpret_cast<double2*>(&Rs[a * 1024 + roff[i]]) =
                     make_double2(acc[i][a][0][0] + acc[i][a][1][0], acc[i][a][0][1] + acc[i][a][1][1]);
         consumer_sync();
+        BOPY_TRACE(3);
 
         // ---- V_I = inv(L_II) R_I (lower triangular: row atom a needs the k tiles kc <= a) ------------------------
 #pragma unroll
@@ -286,6 +301,7 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
             if (lane == 0) mbar_arrive(&empty[stage]);
         }
 
+        BOPY_TRACE(4);
         // ---- publish V_I, fold into sum v^2 -----------------------------------------------------------------------
         {
             double sq[NA][2];
@@ -329,6 +345,7 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
                 __threadfence();
                 st_release_gpu(p.flags + (long long)b * nb + I, p.epoch);
             }
+            BOPY_TRACE(5);
         } else {
             // ---- epilogue (CTA of the last block row): partials in block-row order, acquisition, arg-min ----------
             MinLoc mine;

@@ -157,6 +157,12 @@ int bopy_acq_value_and_grad(bopy_gp* gp, int acq, double eta, double kappa, cons
 int bopy_acq_eval_host(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_host, int64_t m,
                        double* acq_out_host, double* mean_out_host, double* var_out_host, void* stream);
 
+/* Measurement aid for the latency path: called with NULL it arms tracing (the following latency-path launches record
+ * %globaltimer stamps of their first batch: per block row [start, K* done, last V_J flag seen, GEMM done, diagonal solve
+ * done, V_I published, -, -], nanoseconds); called with a host buffer of n_blocks * 8 int64 it synchronises, copies the
+ * stamps out and disarms. */
+int bopy_gp_probe_trace(bopy_gp* gp, int64_t* stamps_out_host);
+
 /* Named views of the fused sweep. */
 int bopy_gp_predict_diag(bopy_gp* gp, const double* Xs_dev, int64_t m, double* mean_out, double* var_out,
                          void* stream);
