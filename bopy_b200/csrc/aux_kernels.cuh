@@ -60,6 +60,37 @@ __global__ void pack_tiles_kernel(const double* __restrict__ L, int n, const dou
     }
 }
 
+// Latency path: M_I = inv(L_II) L_{I,I-1}, stored NEGATED in the DMMA operand-tile layout ([k = 8][row = 128] per tile,
+// 16 tiles per block row), so that  V_I = inv(L_II) P_I + (-M_I) V_{I-1}.  Block I = blockIdx.x + 1; thread (ty, tx) owns
+// the 8 x 8 patch rows 8 ty.., columns 8 tx.. (= tile tx).  inv(L_II) is lower triangular: k runs to the row only.
+__global__ void __launch_bounds__(256) pack_m_kernel(const double* __restrict__ L, int n, const double* __restrict__ Dinv,
+                                                    unsigned char* out) {
+    const int I = blockIdx.x + 1, ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const double* const D = Dinv + (size_t)I * BM * BM;
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    const int kmax = 8 * ty + 8;   // columns of inv(L_II) that rows 8 ty .. 8 ty + 7 can reach
+    for (int k = 0; k < kmax; ++k) {
+        double dk[8], lk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dk[i] = D[(size_t)(8 * ty + i) * BM + k];          // 0 above the diagonal
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lk[j] = L_at(L, n, I * BM + k, (I - 1) * BM + 8 * tx + j);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fma(dk[i], lk[j], acc[i][j]);
+    }
+    double* const dst = reinterpret_cast<double*>(out + ((size_t)I * 16 + tx) * TILE_BYTES);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[DmmaPolicy::a_index(j, 8 * ty + i)] = -acc[i][j];
+}
+
 struct LsParam {
     double v[MAX_D];
 };

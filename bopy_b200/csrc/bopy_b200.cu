@@ -66,7 +66,8 @@ struct bopy_gp {
     long long probe_max_m = 0;
     int probe_max_batch = 0;
     MinLoc* probe_records = nullptr;   // [probe_max_batch]
-    unsigned* probe_flags = nullptr;   // [probe_max_batch][n_blocks], then the role ticket
+    unsigned* probe_flags = nullptr;   // the role ticket, then [2][probe_max_batch][n_blocks]: V_I published / partials published
+    void* Mt = nullptr;                // [n_blocks][16] tiles of -inv(L_II) L_{I,I-1} (latency path's last hop)
     double* probe_part = nullptr;      // [probe_max_batch][n_blocks][2][PROBE_MAX_NC]
     unsigned probe_ticket_base = 0, probe_epoch = 0;
     long long* probe_trace = nullptr;  // [n_blocks][8] time stamps of the next latency-path launch (bopy_gp_probe_trace)
@@ -215,12 +216,14 @@ int launch_probe(bopy_gp* gp, const ProbePlan& pl, const double* Xs, long long m
     q.acq_out = acq_out;
     q.index_base = index_base;
     q.records = records;
-    q.flags = gp->probe_flags;
+    q.Mt = reinterpret_cast<const unsigned char*>(gp->Mt);
+    q.flags = gp->probe_flags + 1;
+    q.flags2 = gp->probe_flags + 1 + (size_t)gp->probe_max_batch * gp->n_blocks;
     q.part = gp->probe_part;
-    q.ticket = gp->probe_flags + (size_t)gp->probe_max_batch * gp->n_blocks;
+    q.ticket = gp->probe_flags;
     q.ticket_base = gp->probe_ticket_base;
     if (++gp->probe_epoch == 0) {   // 2^32 launches: flags of batches not used for a whole cycle must not match again
-        CUDA_TRY(cudaMemsetAsync(gp->probe_flags, 0, (size_t)gp->probe_max_batch * gp->n_blocks * sizeof(unsigned), st));
+        CUDA_TRY(cudaMemsetAsync(gp->probe_flags + 1, 0, (size_t)2 * gp->probe_max_batch * gp->n_blocks * sizeof(unsigned), st));
         gp->probe_epoch = 1;
     }
     q.epoch = gp->probe_epoch;
@@ -393,7 +396,8 @@ int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, 
     gp->probe_capable = dtype == BOPY_F64 && !gp->fma64 && gp->n_blocks <= gp->sm_count;
     if (gp->probe_capable) {
         gp->probe_max_batch = 4 * gp->sm_count;   // sm_count*128 candidates in batches of 32; >= one batch of 8 per CTA group
-        const size_t nflags = (size_t)gp->probe_max_batch * gp->n_blocks + 1;
+        const size_t nflags = (size_t)2 * gp->probe_max_batch * gp->n_blocks + 1;
+        if (e == cudaSuccess) e = cudaMalloc(&gp->Mt, (size_t)gp->n_blocks * EngineF64::CHG * TILE_BYTES);
         if (e == cudaSuccess) e = cudaMalloc(&gp->probe_records, (size_t)gp->probe_max_batch * sizeof(MinLoc));
         if (e == cudaSuccess) e = cudaMalloc(&gp->probe_flags, nflags * sizeof(unsigned));
         if (e == cudaSuccess) e = cudaMemset(gp->probe_flags, 0, nflags * sizeof(unsigned));
@@ -422,6 +426,7 @@ void bopy_gp_destroy(bopy_gp* gp) {
     cudaFree(gp->probe_records);
     cudaFree(gp->probe_flags);
     cudaFree(gp->probe_part);
+    cudaFree(gp->Mt);
     cudaFree(gp->probe_trace);
     cudaFree(gp->grad_flags);
     cudaFree(gp->grad_part);
@@ -473,6 +478,10 @@ int pack_state(bopy_gp* gp, const double* X_dev, const double* L_dev, const doub
     CUDA_TRY(cudaGetLastError());
     pack_x_kernel<<<gp->n_blocks, BM, 0, st>>>(X_dev, alpha_dev, n, gp->d, ls, gp->Xt);
     CUDA_TRY(cudaGetLastError());
+    if (gp->probe_capable && gp->n_blocks > 1) {
+        pack_m_kernel<<<gp->n_blocks - 1, 256, 0, st>>>(L_dev, n, gp->Dinv, reinterpret_cast<unsigned char*>(gp->Mt));
+        CUDA_TRY(cudaGetLastError());
+    }
     return BOPY_OK;
 }
 
@@ -771,7 +780,7 @@ int bopy_acq_value_and_grad(bopy_gp* gp, int acq, double eta, double kappa, cons
         q.flags = gp->grad_flags;
         q.flags2 = gp->grad_flags + (size_t)gb * nb;
         q.gpart = gp->grad_part;
-        q.ticket = gp->probe_flags + (size_t)gp->probe_max_batch * nb;
+        q.ticket = gp->probe_flags;
         q.ticket_base = gp->probe_ticket_base;
         if (++gp->grad_epoch == 0) {
             CUDA_TRY(cudaMemsetAsync(gp->grad_flags, 0, (size_t)2 * gb * nb * sizeof(unsigned), st));

@@ -7,11 +7,16 @@
 // forward substitution of one small batch of candidates is spread over the block rows of L instead:
 //
 //   CTA (I, g) owns block row I of L for candidate group g.  For every batch b of its group (8*NA candidates):
-//     R_I = K*_I - sum_{J<I} L_IJ V_J     V_J arrives from CTA (J, g) through global memory + a release/acquire flag
-//     V_I = inv(L_II) R_I                 published the same way; sum v^2 and K*_I.alpha go to a partials array
+//     P_I = K*_I - sum_{J<I-1} L_IJ V_J   V_J arrives from CTA (J, g) through global memory + a release/acquire flag
+//     V_I = inv(L_II) P_I - M_I V_{I-1}   M_I = inv(L_II) L_{I,I-1} is precomputed, so that only ONE 128 x 128 x 8 product
+//                                         separates the arrival of V_{I-1} from the publication of V_I (the diagonal
+//                                         solve of P_I is done while waiting);  sum v^2 and K*_I.alpha go to a partials
+//                                         array under a second flag, off the chain's critical path
 //   the CTA of the last block row adds the partials in block-row order and runs the epilogue
 //   (de-normalise, LCB / EI / POI, outputs, per-batch arg-min record).
 //
+// (A %globaltimer trace of the first version -- update by L_{I,I-1}, then the diagonal solve, then partials and V under
+// one flag -- showed a 5.5 us hop = 0.4 flag + 2.3 load/update + 1.8 diagonal solve + 1.1 publish.)
 // The chain V_0 -> V_1 -> ... is n/128 hops of a few microseconds; the 128 KB blocks of L a CTA needs stream from L2
 // through a bulk-copy ring while it waits for the hop before.  Same arithmetic ($SK/_gpr.py:446-469), same packed
 // operand tiles (swizzled [k][row], off-diagonal negated, diagonal blocks inverted), same DMMA fragments as
@@ -31,6 +36,7 @@ constexpr long long PROBE_SPIN_LIMIT = 1LL << 24;   // ~10 s of polling: trap in
 
 struct ProbeParams {
     const unsigned char* Lt;   // packed factor tiles (EngineF64 layout)
+    const unsigned char* Mt;   // [n_blocks][16] tiles of -inv(L_II) L_{I,I-1} (same layout): the last hop of a block row
     const double* Xt;          // [n_blocks][d+1][BM]
     double* V;                 // [nbatch][NA][n_pad][8]
     const double* Xs;          // candidates (m, d) row-major
@@ -47,6 +53,7 @@ struct ProbeParams {
     long long index_base;
     MinLoc* records;           // [nbatch] or nullptr
     unsigned* flags;           // [nbatch][n_blocks]: == epoch once V_I of the batch is published
+    unsigned* flags2;          // [nbatch][n_blocks]: == epoch once the mean / sum v^2 partials of block row I are published
     double* part;              // [nbatch][n_blocks][2][NC]: mean / sum v^2 partials of block row I
     unsigned* ticket;          // role counter (monotonic over launches)
     unsigned ticket_base, epoch;
@@ -132,13 +139,20 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
     if (warp == NT / 32) {
         // =============================== bulk-copy producer (one lane) ====================================
         if (lane != 0) return;
+        // tile order of a batch: blocks (I, 0 .. I-2), the inverted diagonal block, then M_I (stands for block (I, I-1))
+        const unsigned char* const m_row = p.Mt + (long long)I * E::CHG * TILE_BYTES;
+        const int T_early = (I > 0 ? I - 1 : 0) * E::CHG;
         uint32_t gc = 0;
         for (int b = g; b < p.nbatch; b += p.groups)
             for (int t = 0; t < T_all; ++t, ++gc) {
                 const uint32_t stage = gc % STG;
                 mbar_wait(&empty[stage], ((gc / STG) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&full[stage], TILE_BYTES);
-                bulk_g2s(ring + stage * TILE_BYTES, a_row + (long long)t * TILE_BYTES, TILE_BYTES, &full[stage]);
+                const unsigned char* src;
+                if (t < T_early) src = a_row + (long long)t * TILE_BYTES;
+                else if (t < T_early + E::CHD) src = a_row + (long long)(I * E::CHG + (t - T_early)) * TILE_BYTES;
+                else src = m_row + (long long)(t - T_early - E::CHD) * TILE_BYTES;
+                bulk_g2s(ring + stage * TILE_BYTES, src, TILE_BYTES, &full[stage]);
             }
         return;
     }
@@ -232,8 +246,8 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
         consumer_sync();   // K* consumed: Rs is free for the residual
         BOPY_TRACE(1);
 
-        // ---- R_I = K*_I - sum_J L_IJ V_J, V_J in the order the chain produces them --------------------------
-        for (int J = 0; J < I; ++J) {
+        // one block of the solve: wait for V_J, stage it, acc += (16 tiles from the ring) . V_J
+        auto block_update = [&](int J) {
             if (lane == 0) {
                 const unsigned* const f = p.flags + (long long)b * nb + J;
                 long long spins = 0;
@@ -266,7 +280,10 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
             }
-        }
+        };
+
+        // ---- P_I = K*_I - sum_{J < I-1} L_IJ V_J: everything that does not need the previous hop ------------------
+        for (int J = 0; J + 1 < I; ++J) block_update(J);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -276,7 +293,7 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
         consumer_sync();
         BOPY_TRACE(3);
 
-        // ---- V_I = inv(L_II) R_I (lower triangular: row atom a needs the k tiles kc <= a) ------------------------
+        // ---- inv(L_II) P_I (lower triangular: row atom a needs the k tiles kc <= a) --------------------------------
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -300,6 +317,10 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
         }
+        BOPY_TRACE(6);
+
+        // ---- the hop: V_I = inv(L_II) P_I - M_I V_{I-1}, the M_I tiles already sit in the ring ----------------------
+        if (I > 0) block_update(I - 1);
 
         BOPY_TRACE(4);
         // ---- publish V_I, fold into sum v^2 -----------------------------------------------------------------------
@@ -329,7 +350,12 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
                     if (q8 == 0) partS[warp * NC + a * 8 + 2 * kq + u] = v;
                 }
         }
-        consumer_sync();
+        consumer_sync();   // every V_I store of this CTA is ordered before the release below
+        if (!last && tid == 0) {
+            __threadfence();
+            st_release_gpu(p.flags + (long long)b * nb + I, p.epoch);   // the chain moves on
+        }
+        BOPY_TRACE(5);
         if (tid < NC) {
             ss_part = ((partS[tid] + partS[NC + tid]) + (partS[2 * NC + tid] + partS[3 * NC + tid])) +
                       ((partS[4 * NC + tid] + partS[5 * NC + tid]) + (partS[6 * NC + tid] + partS[7 * NC + tid]));
@@ -340,20 +366,28 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
                 dst[tid] = mean_part;
                 dst[NC + tid] = ss_part;
             }
-            consumer_sync();   // every V_I / partial store of this CTA is ordered before the release below
+            consumer_sync();
             if (tid == 0) {
                 __threadfence();
-                st_release_gpu(p.flags + (long long)b * nb + I, p.epoch);
+                st_release_gpu(p.flags2 + (long long)b * nb + I, p.epoch);
             }
-            BOPY_TRACE(5);
         } else {
             // ---- epilogue (CTA of the last block row): partials in block-row order, acquisition, arg-min ----------
             MinLoc mine;
             mine.val = 0.0;
             mine.idx = -1;
+            if (warp == 0) {   // the partials of every earlier block row, published under their second flag
+                for (int J = lane; J < I; J += 32) {
+                    const unsigned* const f = p.flags2 + (long long)b * nb + J;
+                    long long spins = 0;
+                    while (ld_acquire_gpu(f) != p.epoch)
+                        if (++spins > PROBE_SPIN_LIMIT) __trap();
+                }
+            }
+            consumer_sync();
             if (tid < NC) {
                 double mean_c = 0.0, ss_c = 0.0;
-                for (int J = 0; J < I; ++J) {   // flags J < I were acquired in the loop above
+                for (int J = 0; J < I; ++J) {
                     const double* const src = p.part + (((long long)b * nb + J) * 2) * NC;
                     mean_c += ld_cg(src + tid);
                     ss_c += ld_cg(src + NC + tid);
