@@ -196,8 +196,34 @@ class OneShotBatchAcquisitionFunction(AcquisitionFunction):
         self.a_xs.append(np.array(values))
         return values
 
+    def argmin(self, x, index_base: int = 0, prune: bool = False) -> Tuple[int, float]:
+        """The sweep optimisers' entry: one fused device pass evaluates ALL rows of `x` (numpy or device tensor),
+        which are logged like any other evaluation; the arg-min follows np.argmin's rules.  (`prune` is ignored: a
+        one-shot strategy chooses from every evaluation, so none may be skipped.)"""
+        self._validate_ok_for_predicting(x)
+        base = self.base_acquisition
+        sur = base.surrogate
+        if hasattr(sur, "native") and hasattr(base, "kind"):
+            xs = sur.native.candidates(x)
+            out = sur.native.sweep(xs, acq=base.kind, want_acq=True, want_min=True, index_base=index_base,
+                                   **base.native_args())
+            self.xs.append(xs)                 # stay on the device until a strategy asks for them
+            self.a_xs.append(out["acq"])
+            return int(out["min_idx"].item()), float(out["min_val"].item())
+        values = self._f(x if isinstance(x, np.ndarray) else x.cpu().numpy())
+        i = int(np.argmin(values))
+        return index_base + i, float(values[i])
+
     def start_optimization(self) -> None:
         self.xs, self.a_xs = [], []
 
     def get_evaluations(self) -> Tuple[np.ndarray, np.ndarray]:
-        return np.concatenate(self.xs), np.concatenate(self.a_xs)
+        to_host = lambda a: a if isinstance(a, np.ndarray) else a.cpu().numpy()   # noqa: E731
+        return np.concatenate([to_host(a) for a in self.xs]), np.concatenate([to_host(a) for a in self.a_xs])
+
+    def get_evaluations_on_device(self):
+        """(x (N, d), a(x) (N,)) as device tensors: what a device-side strategy (top-k) selects from."""
+        torch = _native.require_cuda()
+        dev = _native.resolve_device(getattr(self.surrogate, "device", None))
+        to_dev = lambda a: a if isinstance(a, torch.Tensor) else torch.as_tensor(a, dtype=torch.float64, device=dev)  # noqa: E731
+        return torch.cat([to_dev(a) for a in self.xs]), torch.cat([to_dev(a) for a in self.a_xs])

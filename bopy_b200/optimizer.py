@@ -320,6 +320,58 @@ class OneShotBatchOptimizerRandomSamplingStrategy(OneShotBatchOptimizerStrategy)
         return x[chosen], a_x[chosen]
 
 
+class OneShotBatchOptimizerTopKStrategy(OneShotBatchOptimizerStrategy):
+    """The `batch_size` best evaluations that are at least `min_distance` apart (greedy, best first; distance in units
+    of the box, i.e. after scaling every coordinate by `scale`).  The natural strategy when the base optimiser is a
+    device sweep that logged a million evaluations: the selection runs on the device-resident log
+    (`select_on_device`), only the batch comes back."""
+
+    def __init__(self, min_distance: float = 0.0, scale=None):
+        super().__init__()
+        self.min_distance = float(min_distance)
+        self.scale = scale
+
+    def select(self, x, a_x, batch_size):
+        order = np.argsort(a_x, kind="stable")
+        scale = np.ones(x.shape[1]) if self.scale is None else np.asarray(self.scale, dtype=np.float64)
+        chosen = []
+        for i in order:
+            if np.isnan(a_x[i]):
+                continue
+            if all(np.linalg.norm((x[i] - x[j]) / scale) >= self.min_distance for j in chosen):
+                chosen.append(int(i))
+                if len(chosen) == batch_size:
+                    break
+        chosen = np.array(chosen, dtype=np.int64)
+        return x[chosen], a_x[chosen]
+
+    def select_on_device(self, x, a_x, batch_size):
+        """Same rule on device tensors: candidates are examined best first in chunks of the sorted order."""
+        import torch
+        scale = torch.ones(x.shape[1], dtype=torch.float64, device=x.device) if self.scale is None else \
+            torch.as_tensor(np.asarray(self.scale, dtype=np.float64), device=x.device)
+        vals = torch.where(torch.isnan(a_x), torch.full_like(a_x, float("inf")), a_x)
+        order = torch.argsort(vals, stable=True)
+        chosen = []
+        chunk = max(64, 16 * batch_size)
+        for s0 in range(0, len(order), chunk):
+            idx = order[s0:s0 + chunk]
+            pts = x[idx] / scale
+            for r in range(len(idx)):
+                if not torch.isfinite(vals[idx[r]]):
+                    break
+                if chosen:
+                    kept = x[torch.stack(chosen)] / scale
+                    if float(torch.min(torch.linalg.norm(kept - pts[r], dim=1))) < self.min_distance:
+                        continue
+                chosen.append(idx[r])
+                if len(chosen) == batch_size:
+                    sel = torch.stack(chosen)
+                    return x[sel].cpu().numpy(), a_x[sel].cpu().numpy()
+        sel = torch.stack(chosen) if chosen else torch.zeros(0, dtype=torch.int64, device=x.device)
+        return x[sel].cpu().numpy(), a_x[sel].cpu().numpy()
+
+
 class OneShotBatchOptimizerKDPPSamplingStrategy(OneShotBatchOptimizerStrategy):
     """k-DPP sample with likelihood kernel(x) + alpha I (bopy/optimizer.py:200-232); needs `dppy`."""
 
@@ -353,5 +405,9 @@ class OneShotBatchOptimizer(Optimizer):
     def _optimize(self) -> Tuple[np.ndarray, np.ndarray]:
         self.acquisition_function.start_optimization()
         self.base_optimizer.optimize()
+        if hasattr(self.strategy, "select_on_device") and hasattr(self.acquisition_function, "get_evaluations_on_device") \
+                and any(not isinstance(a, np.ndarray) for a in self.acquisition_function.xs):
+            xs, a_xs = self.acquisition_function.get_evaluations_on_device()   # a device sweep logged them
+            return self.strategy.select_on_device(xs, a_xs, self.batch_size)
         xs, a_xs = self.acquisition_function.get_evaluations()
         return self.strategy.select(xs, a_xs, self.batch_size)

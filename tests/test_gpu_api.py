@@ -371,3 +371,33 @@ def test_examples_run_end_to_end():
         assert res.f_opt <= -0.9                      # both find at least the Forrester local basin
     one_d = importlib.util.spec_from_file_location("e1", os.path.join(root, "examples", "example_1d.py"))
     assert any("optimum found" in l for l in lines) and any("batch proposed" in l for l in lines)
+
+
+def test_one_shot_batch_from_a_device_sweep():
+    """the one-shot strategies choose from the evaluations one global pass logged
+    (bopy/optimizer.py:271-276) -- here the pass is a fused device sweep of 2^17 candidates and the log stays on
+    the device; the top-k strategy returns the k best evaluations that keep their distance."""
+    from bopy_b200.optimizer import OneShotBatchOptimizerTopKStrategy
+    rng = np.random.default_rng(12)
+    X = rng.random((200, 2))
+    y = np.sin(5 * X[:, 0]) * np.cos(4 * X[:, 1])
+    sur = ScipyGPSurrogate(GaussianProcessRegressor(kernel=ConstantKernel(1.0) * RBF([0.2, 0.2]), alpha=1e-6,
+                                                    normalize_y=True, optimizer=None))
+    sur.fit(X, y)
+    acq = OneShotBatchAcquisitionFunction(LCB(sur))
+    acq.fit(X, y)
+    bounds = Bounds([Bound(0.0, 1.0), Bound(0.0, 1.0)])
+    base = CandidateSweepOptimizer(acq, bounds, n_candidates=1 << 17, seed=2)
+    strategy = OneShotBatchOptimizerTopKStrategy(min_distance=0.15)
+    res = OneShotBatchOptimizer(acq, bounds, base_optimizer=base, batch_size=5, strategy=strategy).optimize()
+    assert res.x_min.shape == (5, 2) and res.f_min.shape == (5,)
+    xs, a_xs = acq.get_evaluations()
+    assert xs.shape == (1 << 17, 2) and a_xs.shape == (1 << 17,)
+    assert res.f_min[0] == a_xs.min() and (np.diff(res.f_min) >= 0).all()
+    d = np.linalg.norm(res.x_min[:, None, :] - res.x_min[None, :, :], axis=2)
+    assert (d[np.triu_indices(5, 1)] >= 0.15).all()
+    hx, hf = strategy.select(xs, a_xs, 5)                       # the host rule picks the same batch
+    assert np.array_equal(hx, res.x_min) and np.array_equal(hf, res.f_min)
+    rnd = OneShotBatchOptimizer(acq, bounds, base_optimizer=base, batch_size=3,
+                                strategy=OneShotBatchOptimizerRandomSamplingStrategy()).optimize()
+    assert rnd.x_min.shape == (3, 2)
