@@ -30,6 +30,7 @@ _SIGNATURES = {
                                   c_double, c_double, c_double, c_void_p]),
     "bopy_gp_fit": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_double, c_double, c_double,
                             c_double, c_double, c_void_p, c_void_p, c_void_p]),
+    "bopy_gp_append": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p]),
     "bopy_gp_lml": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_double, c_double, c_double,
                             POINTER(c_double), POINTER(c_double), c_void_p]),
     "bopy_gp_posterior_acq": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_double, c_void_p, c_void_p,
@@ -205,6 +206,19 @@ class NativeGP:
                                        float(noise_level), float(alpha_reg), float(y_mean), float(y_std), _ptr(L),
                                        _ptr(alpha), _stream(self.device)), "bopy_gp_fit")
         return alpha, L
+
+    def append(self, X, y_normalised, y_mean=0.0, y_std=1.0):
+        """Grow the fitted data set by one point (the last row of X) without refactorising: bopy_gp_append.
+        X (n+1, d), y_normalised (n+1,).  Returns alpha (n+1,) as a device tensor."""
+        torch = require_cuda()
+        Xd = self._dev64(X, (self.n + 1, self.d))
+        yd = self._dev64(y_normalised, (self.n + 1,))
+        alpha = torch.empty(self.n + 1, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.bopy_gp_append(self._handle, _ptr(Xd), _ptr(yd), float(y_mean), float(y_std), _ptr(alpha),
+                                          _stream(self.device)), "bopy_gp_append")
+        self.n += 1
+        return alpha
 
     def lml(self, X, y_normalised, length_scale, amplitude=1.0, noise_level=0.0, alpha_reg=1e-10, want_grad=True):
         """Log marginal likelihood (and gradient w.r.t. [log amplitude, log length_scale..., log noise_level]) on the

@@ -7,21 +7,22 @@
 namespace bopy {
 
 // L with identity padding beyond n (rows/cols >= n): the padded system solves to v = 0 there.
-__device__ __forceinline__ double L_at(const double* __restrict__ L, int n, int r, int c) {
-    return (r < n && c < n) ? L[(size_t)r * n + c] : (r == c ? 1.0 : 0.0);
+// (ld = leading dimension of the row-major matrix: n for a caller's factor, n_pad for the handle's own copy)
+__device__ __forceinline__ double L_at(const double* __restrict__ L, int n, int ld, int r, int c) {
+    return (r < n && c < n) ? L[(size_t)r * ld + c] : (r == c ? 1.0 : 0.0);
 }
 
 // Dinv[I] = inv(L_II), 128 x 128 lower triangular, fp64 forward substitution (column j per thread).
 // Dinv doubles as the column store: thread j only re-reads what it wrote itself.
-__global__ void dinv_kernel(const double* __restrict__ L, int n, double* Dinv) {
+__global__ void dinv_kernel(const double* __restrict__ L, int n, int ld, double* Dinv) {
     const int I = blockIdx.x, j = threadIdx.x, base = I * BM;
     double* D = Dinv + (size_t)I * BM * BM;
     for (int r = 0; r < BM; ++r) {
         double x = 0.0;
         if (r >= j) {
             double s = (r == j) ? 1.0 : 0.0;
-            for (int k = j; k < r; ++k) s = fma(-L_at(L, n, base + r, base + k), D[(size_t)k * BM + j], s);
-            x = s / L_at(L, n, base + r, base + r);
+            for (int k = j; k < r; ++k) s = fma(-L_at(L, n, ld, base + r, base + k), D[(size_t)k * BM + j], s);
+            x = s / L_at(L, n, ld, base + r, base + r);
         }
         D[(size_t)r * BM + j] = x;
     }
@@ -30,7 +31,7 @@ __global__ void dinv_kernel(const double* __restrict__ L, int n, double* Dinv) {
 // Operand tile t of block row I: t < I*CHG is the off-diagonal tile [k][row] = -L[I*BM+row][t*KCG+k] in the GEMM
 // policy's element type and physical layout; the CHD tiles after it hold Dinv[I][row][.] in the diagonal policy's.
 template <class E>
-__global__ void pack_tiles_kernel(const double* __restrict__ L, int n, const double* __restrict__ Dinv,
+__global__ void pack_tiles_kernel(const double* __restrict__ L, int n, int ld, const double* __restrict__ Dinv,
                                   unsigned char* out) {
     using PG = typename E::PG;
     using PD = typename E::PD;
@@ -44,7 +45,7 @@ __global__ void pack_tiles_kernel(const double* __restrict__ L, int n, const dou
         const int r = e / KC, k = e - r * KC;
         double v;
         if (offdiag)
-            v = -L_at(L, n, I * BM + r, t * PG::KC + k);
+            v = -L_at(L, n, ld, I * BM + r, t * PG::KC + k);
         else
             v = Dinv[((size_t)I * BM + r) * BM + (t - I * E::CHG) * PD::KC + k];
         tmp[k][r] = v;
@@ -63,7 +64,7 @@ __global__ void pack_tiles_kernel(const double* __restrict__ L, int n, const dou
 // Latency path: M_I = inv(L_II) L_{I,I-1}, stored NEGATED in the DMMA operand-tile layout ([k = 8][row = 128] per tile,
 // 16 tiles per block row), so that  V_I = inv(L_II) P_I + (-M_I) V_{I-1}.  Block I = blockIdx.x + 1; thread (ty, tx) owns
 // the 8 x 8 patch rows 8 ty.., columns 8 tx.. (= tile tx).  inv(L_II) is lower triangular: k runs to the row only.
-__global__ void __launch_bounds__(256) pack_m_kernel(const double* __restrict__ L, int n, const double* __restrict__ Dinv,
+__global__ void __launch_bounds__(256) pack_m_kernel(const double* __restrict__ L, int n, int ld, const double* __restrict__ Dinv,
                                                     unsigned char* out) {
     const int I = blockIdx.x + 1, ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     const double* const D = Dinv + (size_t)I * BM * BM;
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(256) pack_m_kernel(const double* __restrict__ 
 #pragma unroll
         for (int i = 0; i < 8; ++i) dk[i] = D[(size_t)(8 * ty + i) * BM + k];          // 0 above the diagonal
 #pragma unroll
-        for (int j = 0; j < 8; ++j) lk[j] = L_at(L, n, I * BM + k, (I - 1) * BM + 8 * tx + j);
+        for (int j = 0; j < 8; ++j) lk[j] = L_at(L, n, ld, I * BM + k, (I - 1) * BM + 8 * tx + j);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll

@@ -76,6 +76,10 @@ struct bopy_gp {
     double* grad_part = nullptr;       // [sm_count][n_blocks][2][d][PROBE_MAX_NC]
     double* grad_mv = nullptr;         // [2][sm_count * PROBE_MAX_NC]: mean / var scratch of a chunk
     unsigned grad_epoch = 0;
+    // the factor itself (row-major, leading dimension n_pad), kept by bopy_gp_fit so that bopy_gp_append can grow it
+    double* Lfull = nullptr;
+    bool Lfull_valid = false;
+    double alpha_reg = 0.0;            // the jitter the kept factor was built with
     // staging of the host-buffer entry point (small calls: one point per DIRECT probe)
     double* host_x = nullptr;          // [HOST_CALL_MAX_M][d]
     double* host_out = nullptr;        // [3][HOST_CALL_MAX_M]: acq / mean / var
@@ -433,6 +437,7 @@ void bopy_gp_destroy(bopy_gp* gp) {
     cudaFree(gp->grad_mv);
     cudaFree(gp->host_x);
     cudaFree(gp->host_out);
+    cudaFree(gp->Lfull);
     delete gp;
 }
 
@@ -466,20 +471,20 @@ LsParam store_hyper(bopy_gp* gp, const double* length_scale_host, int n_ls, doub
 }
 
 // pack (L, Dinv, X, alpha) into the sweep layout; gp->Dinv must already hold the inverted diagonal blocks
-int pack_state(bopy_gp* gp, const double* X_dev, const double* L_dev, const double* alpha_dev, const LsParam& ls,
+int pack_state(bopy_gp* gp, const double* X_dev, const double* L_dev, int ld, const double* alpha_dev, const LsParam& ls,
                cudaStream_t st) {
     const int n = (int)gp->n;
     dispatch_engine(gp, [&](auto e) {
         using E = decltype(e);
         dim3 grid((gp->n_blocks - 1) * E::CHG + E::CHD, gp->n_blocks);
-        pack_tiles_kernel<E><<<grid, 256, 0, st>>>(L_dev, n, gp->Dinv, reinterpret_cast<unsigned char*>(gp->Lt));
+        pack_tiles_kernel<E><<<grid, 256, 0, st>>>(L_dev, n, ld, gp->Dinv, reinterpret_cast<unsigned char*>(gp->Lt));
         return BOPY_OK;
     });
     CUDA_TRY(cudaGetLastError());
     pack_x_kernel<<<gp->n_blocks, BM, 0, st>>>(X_dev, alpha_dev, n, gp->d, ls, gp->Xt);
     CUDA_TRY(cudaGetLastError());
     if (gp->probe_capable && gp->n_blocks > 1) {
-        pack_m_kernel<<<gp->n_blocks - 1, 256, 0, st>>>(L_dev, n, gp->Dinv, reinterpret_cast<unsigned char*>(gp->Mt));
+        pack_m_kernel<<<gp->n_blocks - 1, 256, 0, st>>>(L_dev, n, ld, gp->Dinv, reinterpret_cast<unsigned char*>(gp->Mt));
         CUDA_TRY(cudaGetLastError());
     }
     return BOPY_OK;
@@ -531,11 +536,12 @@ int bopy_gp_set_state(bopy_gp* gp, const double* X_dev, const double* L_dev, con
     CUDA_TRY(cudaSetDevice(gp->device));
     gp->ready = false;
     const LsParam ls = store_hyper(gp, length_scale_host, n_ls, amplitude, noise_level, y_mean, y_std);
-    dinv_kernel<<<gp->n_blocks, BM, 0, st>>>(L_dev, (int)gp->n, gp->Dinv);
+    dinv_kernel<<<gp->n_blocks, BM, 0, st>>>(L_dev, (int)gp->n, (int)gp->n, gp->Dinv);
     CUDA_TRY(cudaGetLastError());
-    rc = pack_state(gp, X_dev, L_dev, alpha_dev, ls, st);
+    rc = pack_state(gp, X_dev, L_dev, (int)gp->n, alpha_dev, ls, st);
     if (rc != BOPY_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(st));
+    gp->Lfull_valid = false;   // the caller's factor was packed, not kept
     gp->ready = true;
     return BOPY_OK;
 }
@@ -553,38 +559,37 @@ int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const do
     gp->ready = false;
     const LsParam ls = store_hyper(gp, length_scale_host, n_ls, amplitude, noise_level, y_mean, y_std);
     const int n = (int)gp->n, nb = gp->n_blocks;
-    // scratch: the working matrix (unless the caller wants L), z (n_pad), alpha (n), status
-    double* A = L_out_dev;
-    double *scratch = nullptr, *Aown = nullptr;
+    // the working matrix is the handle's own n_pad x n_pad factor (kept for bopy_gp_append); scratch: z (n_pad),
+    // alpha (n), status
+    const int ld = gp->n_pad;
+    gp->Lfull_valid = false;
+    if (gp->Lfull == nullptr) {
+        CUDA_TRY(cudaMalloc(&gp->Lfull, (size_t)ld * ld * sizeof(double)));
+        CUDA_TRY(cudaMemsetAsync(gp->Lfull, 0, (size_t)ld * ld * sizeof(double), st));   // the upper triangle stays 0
+    }
+    double* const A = gp->Lfull;
+    double* scratch = nullptr;
     int* status = nullptr;
-    if (A == nullptr) {
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&Aown), (size_t)n * n * sizeof(double), st));
-        A = Aown;
-    }
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&scratch), ((size_t)gp->n_pad + n) * sizeof(double) + 16, st);
-    if (e != cudaSuccess) {
-        if (Aown) cudaFreeAsync(Aown, st);
-        return fail(BOPY_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
-    }
+    if (e != cudaSuccess) return fail(BOPY_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
     double* z = scratch;
     double* alpha = alpha_out_dev != nullptr ? alpha_out_dev : scratch + gp->n_pad;
     status = reinterpret_cast<int*>(scratch + gp->n_pad + n);
-    auto cleanup = [&]() {
-        if (Aown) cudaFreeAsync(Aown, st);
-        cudaFreeAsync(scratch, st);
-    };
+    auto cleanup = [&]() { cudaFreeAsync(scratch, st); };
     cudaMemsetAsync(status, 0, sizeof(int), st);
-    if (L_out_dev != nullptr) cudaMemsetAsync(L_out_dev, 0, (size_t)n * n * sizeof(double), st);  // zero upper triangle
     const double diag = (amplitude + noise_level) + alpha_reg;   // kernel_(X) diagonal, then += alpha
-    launch_gram(gp, X_dev, ls, gp->amp, diag, A, n, n, st);
-    launch_cholesky(A, n, n, nb, gp->Dinv, status, st);
-    solve_alpha_kernel<<<1, 1024, 0, st>>>(A, n, n, nb, gp->Dinv, yn_dev, z, alpha);
+    launch_gram(gp, X_dev, ls, gp->amp, diag, A, ld, n, st);
+    launch_cholesky(A, n, ld, nb, gp->Dinv, status, st);
+    solve_alpha_kernel<<<1, 1024, 0, st>>>(A, n, ld, nb, gp->Dinv, yn_dev, z, alpha);
     e = cudaGetLastError();
     if (e == cudaSuccess) {
-        rc = pack_state(gp, X_dev, A, alpha, ls, st);
+        rc = pack_state(gp, X_dev, A, ld, alpha, ls, st);
     } else {
         rc = fail(BOPY_ERR_CUDA, "fit kernels failed to launch: %s", cudaGetErrorString(e));
     }
+    if (rc == BOPY_OK && L_out_dev != nullptr)   // export: (n, n) row-major, zeros above the diagonal
+        e = cudaMemcpy2DAsync(L_out_dev, (size_t)n * sizeof(double), A, (size_t)ld * sizeof(double), (size_t)n * sizeof(double),
+                              (size_t)n, cudaMemcpyDeviceToDevice, st);
     int host_status = 0;
     if (rc == BOPY_OK) e = cudaMemcpyAsync(&host_status, status, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (rc == BOPY_OK && e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -595,6 +600,64 @@ int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const do
         return fail(BOPY_ERR_NOT_POSITIVE_DEFINITE,
                     "K + alpha I is not positive definite (non-positive pivot in block column %d); increase alpha",
                     host_status - 1);
+    gp->Lfull_valid = true;
+    gp->alpha_reg = alpha_reg;
+    gp->ready = true;
+    return BOPY_OK;
+}
+
+int bopy_gp_append(bopy_gp* gp, const double* X_dev, const double* yn_dev, double y_mean, double y_std,
+                   double* alpha_out_dev, void* stream) {
+    int rc = check_ready(gp);
+    if (rc != BOPY_OK) return rc;
+    if (X_dev == nullptr || yn_dev == nullptr) return fail(BOPY_ERR_BAD_ARG, "X_dev and yn_dev must be non-NULL");
+    if (!gp->Lfull_valid || !gp->probe_capable)
+        return fail(BOPY_ERR_NOT_READY, "bopy_gp_append needs a state built by bopy_gp_fit on an fp64 handle");
+    const int n = (int)gp->n, nb = gp->n_blocks, ld = gp->n_pad;
+    if ((n + 1 + BM - 1) / BM != nb)
+        return fail(BOPY_ERR_BAD_ARG, "the grown data set (%d points) needs another 128-row block: refit", n + 1);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    LsParam ls;
+    for (int q = 0; q < MAX_D; ++q) ls.v[q] = q < gp->d ? gp->ls[q] : 1.0;
+    double* scratch = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), ((size_t)gp->n_pad + n + 1) * sizeof(double) + 16, st));
+    double* const z = scratch;
+    double* const alpha = alpha_out_dev != nullptr ? alpha_out_dev : scratch + gp->n_pad;
+    int* const status = reinterpret_cast<int*>(scratch + gp->n_pad + n + 1);
+    cudaMemsetAsync(status, 0, sizeof(int), st);
+    // 1. v = L^-1 k(X, x_new): the latency path's forward solve of the new point against the CURRENT state
+    gp->ready = false;
+    rc = launch_probe(gp, probe_plan(gp, 1), X_dev + (size_t)n * gp->d, 1, BOPY_ACQ_NONE, 0.0, 0.0, nullptr, nullptr, nullptr, 0,
+                      nullptr, 1, st);
+    if (rc != BOPY_OK) {
+        cudaFreeAsync(scratch, st);
+        return rc;
+    }
+    // 2. the new row of the factor, the inverse of the one diagonal block it touches
+    append_row_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const double*>(gp->Vws), n, ld, (gp->amp + gp->noise) + gp->alpha_reg,
+                                         gp->Lfull, status);
+    gp->n = n + 1;
+    gp->y_mean = y_mean;
+    gp->y_std = y_std;
+    const size_t chol_smem = ((size_t)BM * (BM + 1) + BM + 2) * sizeof(double);
+    cudaFuncSetAttribute(dinv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem);
+    dinv_block_kernel<<<1, CHOL_NT, chol_smem, st>>>(gp->Lfull, n + 1, ld, n / BM, gp->Dinv);
+    // 3. alpha for the (re-normalised) targets, then the packed state
+    solve_alpha_kernel<<<1, 1024, 0, st>>>(gp->Lfull, n + 1, ld, nb, gp->Dinv, yn_dev, z, alpha);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) rc = pack_state(gp, X_dev, gp->Lfull, ld, alpha, ls, st);
+    else rc = fail(BOPY_ERR_CUDA, "append kernels failed to launch: %s", cudaGetErrorString(e));
+    int host_status = 0;
+    if (rc == BOPY_OK) e = cudaMemcpyAsync(&host_status, status, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (rc == BOPY_OK && e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeAsync(scratch, st);
+    if (rc != BOPY_OK || e != cudaSuccess || host_status != 0) {
+        gp->Lfull_valid = false;   // row n was written: only a refit restores a consistent state
+        if (rc != BOPY_OK) return rc;
+        if (e != cudaSuccess) return fail(BOPY_ERR_CUDA, "bopy_gp_append failed: %s", cudaGetErrorString(e));
+        return fail(BOPY_ERR_NOT_POSITIVE_DEFINITE, "the grown K + alpha I is not positive definite (new pivot <= 0)");
+    }
     gp->ready = true;
     return BOPY_OK;
 }
@@ -692,6 +755,7 @@ int bopy_gp_posterior_acq(bopy_gp* gp, const double* Xs_dev, int64_t m, int acq,
 }
 
 int bopy_gp_resize(bopy_gp* gp, int64_t n) {
+    if (gp != nullptr) gp->Lfull_valid = false;
     if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
     if (n < 1 || (n + BM - 1) / BM != gp->n_blocks)
         return fail(BOPY_ERR_BAD_ARG, "n = %lld does not fit this handle's %d block rows of %d (create a new handle)",

@@ -42,6 +42,44 @@ __global__ void gram_kernel(const double* __restrict__ X, int n, int d, LsParam 
     A[(size_t)i * ld + j] = v;
 }
 
+// In-place inverse of the lower-triangular block held in sm[BM][BM+1] (rdg[k] = 1 / L[k][k] precomputed), for a CTA of
+// CHOL_NT = 256 threads; on return X[r][j] (r >= j) sits at sm[j][r].  Ends with a block-wide barrier.
+constexpr int CHOL_NT = 256;
+__device__ __forceinline__ void tri_inverse_in_place(double* sm, const double* rdg) {
+    constexpr int LD = BM + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // inverse: X = inv(L), one column j per lane PAIR (lane, lane ^ 16) of a warp -- warp w owns columns 16 w .. 16 w + 15,
+    // the two lanes of a pair take the even / odd k of  X[r][j] = -(sum_{k=j..r-1} L[r][k] X[k][j]) / L[r][r]  and join
+    // by one shuffle.  X[r][j] (r >= j) is parked at sm[j][r] (diagonal and strict upper triangle of row j, which
+    // nobody else touches: L is only read strictly below its diagonal from here on).  The lanes of a warp walk r and k
+    // in lock step, so the reads of L[r][k] are broadcasts and a warp-level barrier per r orders the pair's exchange.
+    {
+        const int j = 16 * warp + (lane & 15), half = lane >> 4;
+        if (half == 0) sm[j * LD + j] = rdg[j];
+        __syncwarp();
+        const int jw = 16 * warp;   // no column of this warp has entries above row jw
+        for (int r = jw + 1; r < BM; ++r) {
+            double s0 = 0.0, s1 = 0.0;
+            int k = jw + half;
+            for (; k + 2 < r; k += 4) {
+                const double x0 = k >= j ? sm[j * LD + k] : 0.0;
+                const double x1 = k + 2 >= j ? sm[j * LD + k + 2] : 0.0;
+                s0 = fma(sm[r * LD + k], x0, s0);
+                s1 = fma(sm[r * LD + k + 2], x1, s1);
+            }
+            if (k < r) {
+                const double x0 = k >= j ? sm[j * LD + k] : 0.0;
+                s0 = fma(sm[r * LD + k], x0, s0);
+            }
+            double sacc = s0 + s1;
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+            if (half == 0 && r > j) sm[j * LD + r] = -sacc * rdg[r];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
 // In-place Cholesky of the diagonal block J (identity padded beyond n) + its inverse, all in shared memory.
 // One CTA of CHOL_NT threads.  status[0] is set to J+1 if a non-positive pivot is met (not positive definite).
 // Panel-blocked (16 columns at a time) so that the 128 columns cost 8 x 3 block-wide barriers instead of 256:
@@ -50,7 +88,6 @@ __global__ void gram_kernel(const double* __restrict__ X, int n, int d, LsParam 
 //   (c) the trailing lower triangle takes the rank-16 update with no barrier between the 16 rank-1 terms.
 // The inverse is column-parallel and barrier-free: thread j forward-substitutes column j of inv(L_JJ), parking it in
 // row j of the (unused) strict upper triangle of the working block.
-constexpr int CHOL_NT = 256;
 constexpr int CHOL_PANEL = 16;
 __global__ void __launch_bounds__(CHOL_NT) chol_block_kernel(double* A, int n, int ld, int J, double* Dinv, int* status) {
     extern __shared__ double sm[];          // [BM][BM+1] working block, then rdg[BM] (1 / L_kk), fail flag
@@ -149,40 +186,57 @@ __global__ void __launch_bounds__(CHOL_NT) chol_block_kernel(double* A, int n, i
     }
     if (tid < BM) rdg[tid] = 1.0 / sm[tid * LD + tid];
     __syncthreads();
-    // inverse: X = inv(L), one column j per lane PAIR (lane, lane ^ 16) of a warp -- warp w owns columns 16 w .. 16 w + 15,
-    // the two lanes of a pair take the even / odd k of  X[r][j] = -(sum_{k=j..r-1} L[r][k] X[k][j]) / L[r][r]  and join
-    // by one shuffle.  X[r][j] (r >= j) is parked at sm[j][r] (diagonal and strict upper triangle of row j, which
-    // nobody else touches: L is only read strictly below its diagonal from here on).  The lanes of a warp walk r and k
-    // in lock step, so the reads of L[r][k] are broadcasts and a warp-level barrier per r orders the pair's exchange.
-    {
-        const int j = 16 * warp + (lane & 15), half = lane >> 4;
-        if (half == 0) sm[j * LD + j] = rdg[j];
-        __syncwarp();
-        const int jw = 16 * warp;   // no column of this warp has entries above row jw
-        for (int r = jw + 1; r < BM; ++r) {
-            double s0 = 0.0, s1 = 0.0;
-            int k = jw + half;
-            for (; k + 2 < r; k += 4) {
-                const double x0 = k >= j ? sm[j * LD + k] : 0.0;
-                const double x1 = k + 2 >= j ? sm[j * LD + k + 2] : 0.0;
-                s0 = fma(sm[r * LD + k], x0, s0);
-                s1 = fma(sm[r * LD + k + 2], x1, s1);
-            }
-            if (k < r) {
-                const double x0 = k >= j ? sm[j * LD + k] : 0.0;
-                s0 = fma(sm[r * LD + k], x0, s0);
-            }
-            double sacc = s0 + s1;
-            sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
-            if (half == 0 && r > j) sm[j * LD + r] = -sacc * rdg[r];
-            __syncwarp();
-        }
-    }
-    __syncthreads();
+    tri_inverse_in_place(sm, rdg);
     double* D = Dinv + (size_t)J * BM * BM;
     for (int e = tid; e < BM * BM; e += CHOL_NT) {
         const int r = e / BM, c = e - r * BM;
         D[e] = c <= r ? sm[c * LD + r] : 0.0;
+    }
+}
+
+// Dinv[I] = inv(L_II) for ONE diagonal block of a factor that is already there (the appended row changed block I only)
+__global__ void __launch_bounds__(CHOL_NT) dinv_block_kernel(const double* __restrict__ L, int n, int ld, int I, double* Dinv) {
+    extern __shared__ double sm[];          // [BM][BM+1], then rdg[BM]
+    constexpr int LD = BM + 1;
+    double* const rdg = sm + BM * LD;
+    const int tid = threadIdx.x, base = I * BM;
+    for (int e = tid; e < BM * BM; e += CHOL_NT) {
+        const int r = e / BM, c = e - r * BM;
+        sm[r * LD + c] = c <= r ? L_at(L, n, ld, base + r, base + c) : 0.0;
+    }
+    __syncthreads();
+    if (tid < BM) rdg[tid] = 1.0 / sm[tid * LD + tid];
+    __syncthreads();
+    tri_inverse_in_place(sm, rdg);
+    double* D = Dinv + (size_t)I * BM * BM;
+    for (int e = tid; e < BM * BM; e += CHOL_NT) {
+        const int r = e / BM, c = e - r * BM;
+        D[e] = c <= r ? sm[c * LD + r] : 0.0;
+    }
+}
+
+// Row n of the factor of the data set grown by one point: L[n][0..n-1] = v = L^-1 k(X, x_new) (the latency path's forward
+// solve of x_new, column 0 of its [n_pad][8] workspace), L[n][n] = sqrt(k(x,x) + noise + alpha - v.v).  One CTA.
+// status[0] = 1 if the new pivot is not positive.
+__global__ void __launch_bounds__(256) append_row_kernel(const double* __restrict__ V, int n, int ld, double diag,
+                                                        double* L, int* status) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < n; k += 256) {
+        const double v = V[(size_t)k * 8];
+        L[(size_t)n * ld + k] = v;
+        s = fma(v, v, s);
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double piv = diag - red[0];
+        if (!(piv > 0.0)) status[0] = 1;
+        L[(size_t)n * ld + n] = sqrt(piv);
     }
 }
 

@@ -177,6 +177,8 @@ class B200GPSurrogate(Surrogate):
         else:
             y_mean, y_std, yn = 0.0, 1.0, yv
         n, d = X.shape
+        if self._try_append(X, yn, y_mean, y_std, spec, kernel_):
+            return
         native = self._native_for(n, d, spec.kernel)
         if gp.optimizer is not None and kernel_.n_dims > 0:
             Xd, yd = native._dev64(X, (n, d)), native._dev64(yn, (n,))
@@ -193,6 +195,38 @@ class B200GPSurrogate(Surrogate):
         gp.alpha_ = alpha.cpu().numpy()
         self.kernel_spec = spec
         self.fitted_on_device = True
+        self._append_key = self._spec_key(spec) if gp.optimizer is None else None
+
+    def _spec_key(self, spec):
+        return (spec.kernel, tuple(np.ravel(spec.length_scale).tolist()), float(spec.amplitude), float(spec.noise_level),
+                float(self.gp.alpha), bool(self.gp.normalize_y))
+
+    def _try_append(self, X, yn, y_mean, y_std, spec, kernel_) -> bool:
+        """A refit whose data are the previous data plus ONE new last point, with the same fixed hyper-parameters, is a
+        one-row extension of the factor (`bopy_gp_append`): the BayesOpt loop's per-trial refit
+        (bopy/bayes_opt.py:239-242) and the Kriging believer's per-member refit (bopy/acquisition.py:188-192)."""
+        gp, native = self.gp, self.native
+        prev = getattr(gp, "X_train_", None)
+        if (native is None or not self.fitted_on_device or gp.optimizer is not None or prev is None
+                or getattr(self, "_append_key", None) != self._spec_key(spec)
+                or X.shape != (prev.shape[0] + 1, prev.shape[1]) or native.n != prev.shape[0]
+                or (native.n + 1 + 127) // 128 != (native.n + 127) // 128
+                or not native.gradient_capable() or not np.array_equal(X[:-1], prev)):
+            return False
+        try:
+            alpha = native.append(X, yn, y_mean=float(y_mean), y_std=float(y_std))
+        except np.linalg.LinAlgError:
+            raise
+        except _native.NativeLibraryError:
+            return False          # the generic path refits from scratch
+        gp.kernel_ = kernel_
+        gp.X_train_ = np.copy(X) if gp.copy_X_train else X
+        gp.y_train_ = np.copy(yn) if gp.copy_X_train else yn
+        gp._y_train_mean, gp._y_train_std = y_mean, y_std
+        gp.alpha_ = alpha.cpu().numpy()
+        self.kernel_spec = spec
+        self.appended_rows = getattr(self, "appended_rows", 0) + 1
+        return True
 
     def export_factor(self) -> np.ndarray:
         """The lower Cholesky factor L_ (n, n) as numpy: refits on the device with the factor exported."""

@@ -105,6 +105,18 @@ int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const do
                 double* L_out_dev, double* alpha_out_dev, void* stream);
 
 /*
+ * Grow the fitted data set by ONE point without refactorising (same hyper-parameters): a BayesOpt trial adds one
+ * observation (bopy/bayes_opt.py:255-262, 239-242), the Kriging believer one fantasy per batch member
+ * (bopy/acquisition.py:188-192).  X_dev (n+1,d): the old points followed by the new one; yn_dev (n+1,): ALL targets after
+ * the caller's (new) normalisation.  The new row of the Cholesky factor is the latency path's forward solve of the new
+ * point, L[n][:n] = L^-1 k(X, x_new), L[n][n] = sqrt(k(x,x) + noise + alpha - |L[n][:n]|^2); only the diagonal block it
+ * touches is re-inverted; alpha_ is re-solved for the new targets.  Needs a state installed by bopy_gp_fit on an fp64
+ * handle and n+1 within the handle's 128-row blocks (BOPY_ERR_BAD_ARG otherwise: refit).  Synchronises the stream.
+ */
+int bopy_gp_append(bopy_gp* gp, const double* X_dev, const double* yn_dev, double y_mean, double y_std,
+                   double* alpha_out_dev, void* stream);
+
+/*
  * Log marginal likelihood of the (normalised) targets under the given hyper-parameters, and optionally its gradient
  * with respect to the LOG hyper-parameters ($SK/_gpr.py:541-656).  Does not touch the
  * installed state.  lml_out_host: one double.  grad_out_host (nullable): n_ls + 2 doubles laid out as

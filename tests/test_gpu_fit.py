@@ -172,3 +172,49 @@ def test_hyper_parameter_optimisation_on_the_device():
     h_mean, h_std = host.predict(grid, return_std=True)
     np.testing.assert_allclose(mean, h_mean, rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(np.sqrt(var), h_std, rtol=1e-3, atol=1e-5)
+
+
+def test_one_point_growth_is_a_row_append_and_matches_a_fresh_fit():
+    """A refit on (previous data + one point) with fixed hyper-parameters extends the factor by one row
+    (bopy_gp_append); it must give what a fit from scratch gives, also through a chain of appends, across a
+    128-row block edge (where it falls back to the full fit) and after the Kriging believer's shrink."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import Matern, RBF, ConstantKernel, WhiteKernel
+
+    from bopy_b200.surrogate import B200GPSurrogate
+    rng = np.random.default_rng(77)
+    X = rng.random((400, 3))
+    y = np.sin(4 * X[:, 0]) + X[:, 1] * X[:, 2] + 0.05 * rng.standard_normal(400)
+    xs = rng.random((200, 3))
+    kernels = [ConstantKernel(1.3) * RBF([0.3, 0.4, 0.5]), ConstantKernel(0.8) * Matern(0.5, nu=2.5) + WhiteKernel(1e-3)]
+    for kernel in kernels:
+        def make():
+            return B200GPSurrogate(GaussianProcessRegressor(kernel=kernel, alpha=1e-6, normalize_y=True, optimizer=None))
+        sur = make()
+        n0 = 370
+        sur.fit(X[:n0], y[:n0])
+        assert getattr(sur, "appended_rows", 0) == 0
+        for n in range(n0 + 1, n0 + 20):                         # 371 .. 389: crosses 384 = 3 * 128
+            sur.fit(X[:n], y[:n])
+            if n in (n0 + 1, 384, 385, n0 + 19):
+                fresh = make()
+                fresh.fit(X[:n], y[:n])
+                m_a, v_a = sur.predict_diag(xs)
+                m_f, v_f = fresh.predict_diag(xs)
+                scale = np.abs(m_f).max()
+                np.testing.assert_allclose(m_a, m_f, rtol=0, atol=1e-9 * scale)
+                np.testing.assert_allclose(v_a, v_f, rtol=1e-8, atol=1e-10 * np.abs(v_f).max())
+                np.testing.assert_allclose(sur.gp.alpha_, fresh.gp.alpha_, rtol=0, atol=1e-7 * np.abs(fresh.gp.alpha_).max())
+        # 19 growth steps, all but the one that needed a fourth block (384 -> 385) were appends
+        assert sur.appended_rows == 18
+        # shrinking back (what KriggingBeliever.finish_batch does) is a plain refit and still right
+        sur.fit(X[:n0], y[:n0])
+        fresh = make()
+        fresh.fit(X[:n0], y[:n0])
+        assert np.array_equal(sur.predict_diag(xs)[0], fresh.predict_diag(xs)[0])
+        # a changed point in the middle is not an append
+        Xc = X[:n0 + 1].copy()
+        Xc[5] += 0.01
+        before = sur.appended_rows
+        sur.fit(Xc, y[:n0 + 1])
+        assert sur.appended_rows == before

@@ -15,6 +15,11 @@ from bopy_b200.optimizer import CandidateSweepOptimizer, DirectOptimizer, MultiS
 from bopy_b200.surrogate import B200GPSurrogate  # noqa: E402
 
 
+def torch_sync():
+    import torch
+    torch.cuda.synchronize()
+
+
 def wall(fn, reps=5):
     import torch
     fn()
@@ -31,10 +36,20 @@ def main():
         X, y, gp = bench.make_problem(n, d)
         sur = B200GPSurrogate(gp)
         t_fit, _ = wall(lambda: sur.fit(X, y))
+        # the per-trial refit: one more observation, same hyper-parameters -> one-row extension of the factor
+        Xg, yg = np.vstack([X, np.random.default_rng(1).random((8, d))]), np.concatenate([y, y[:8]])
+        t_app = []
+        for k in range(1, 7):
+            t0 = time.perf_counter()
+            sur.fit(Xg[:n + k], yg[:n + k])
+            torch_sync()
+            t_app.append(1e3 * (time.perf_counter() - t0))
+        sur.fit(X, y)
         ei = EI(sur)
         ei.fit(X, y)
         bounds = Bounds([Bound(0.0, 1.0)] * d)
-        row = dict(n=n, d=d, surrogate_fit_ms=t_fit)
+        row = dict(n=n, d=d, surrogate_fit_ms=t_fit, surrogate_refit_one_more_point_ms=float(np.median(t_app[1:])),
+                   appended_rows=int(getattr(sur, "appended_rows", 0)))
         ncand = 1 << 20 if n <= 2048 else 1 << 18
         row["sweep_ms"], r0 = wall(lambda: CandidateSweepOptimizer(ei, bounds, n_candidates=ncand, seed=1).optimize(), 3)
         row["sweep_pruned_ms"], r1 = wall(lambda: CandidateSweepOptimizer(ei, bounds, n_candidates=ncand, seed=1, prune=True).optimize(), 3)
