@@ -92,6 +92,12 @@ __global__ void __launch_bounds__(256) pack_m_kernel(const double* __restrict__ 
         for (int j = 0; j < 8; ++j) dst[DmmaPolicy::a_index(j, 8 * ty + i)] = -acc[i][j];
 }
 
+// out[i] = W[i][0]: column 0 of a latency-path workspace ([n_pad][8]) as a plain vector
+__global__ void extract_column_kernel(const double* __restrict__ W, int n, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = W[(size_t)i * 8];
+}
+
 struct LsParam {
     double v[MAX_D];
 };

@@ -193,7 +193,7 @@ int check_ready(const bopy_gp* gp) {
 // one launch of the latency path (probe_kernel) over m candidates laid out by `pl`
 int launch_probe(bopy_gp* gp, const ProbePlan& pl, const double* Xs, long long m, int acq, double eta, double kappa,
                  double* mean_out, double* var_out, double* acq_out, long long index_base, MinLoc* records, int keep_v,
-                 cudaStream_t st) {
+                 cudaStream_t st, const double* rhs = nullptr) {
     ProbeParams q;
     std::memset(&q, 0, sizeof(q));
     q.Lt = reinterpret_cast<const unsigned char*>(gp->Lt);
@@ -232,6 +232,7 @@ int launch_probe(bopy_gp* gp, const ProbePlan& pl, const double* Xs, long long m
     }
     q.epoch = gp->probe_epoch;
     q.keep_v = keep_v;
+    q.rhs = rhs;
     q.trace = gp->probe_trace;
     int rc = pl.na == 1 ? launch_probe_k<1>(gp->kernel, q, pl.grid, st)
                         : (pl.na == 2 ? launch_probe_k<2>(gp->kernel, q, pl.grid, st)
@@ -286,6 +287,70 @@ void launch_mean_bound(const bopy_gp* gp, const double* Xs, long long m, double 
         case BOPY_KERNEL_MATERN32: launch_mean_bound_k<K_M32>(gp, Xs, m, ls, sd_max, acq, eta, kappa, mean_out, bound_out, st); break;
         default: launch_mean_bound_k<K_M52>(gp, Xs, m, ls, sd_max, acq, eta, kappa, mean_out, bound_out, st); break;
     }
+}
+
+// flags / partial sums / moment scratch of grad_kernel, allocated on first use (chunks of up to sm_count batches)
+int ensure_grad_buffers(bopy_gp* gp) {
+    if (gp->grad_flags != nullptr) return BOPY_OK;
+    const int gb = gp->sm_count, nb = gp->n_blocks;
+    const size_t nflags = (size_t)2 * gb * nb;
+    CUDA_TRY(cudaMalloc(&gp->grad_flags, nflags * sizeof(unsigned)));
+    CUDA_TRY(cudaMemset(gp->grad_flags, 0, nflags * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&gp->grad_part, (size_t)gb * nb * 2 * gp->d * PROBE_MAX_NC * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&gp->grad_mv, (size_t)2 * gb * PROBE_MAX_NC * sizeof(double)));
+    return BOPY_OK;
+}
+
+// alpha_ = L^-T (L^-1 yn) on the PACKED factor, spread over the block rows: the latency path's forward solve with yn as
+// right-hand side (probe_kernel, rhs mode), then its mirror image (grad_kernel, solve-only mode).  ~n/128 hops of a few
+// microseconds each way instead of one thread block walking the whole factor twice (solve_alpha_kernel).
+int solve_alpha_chain(bopy_gp* gp, const double* yn_dev, double* alpha_dev, cudaStream_t st) {
+    int rc = ensure_grad_buffers(gp);
+    if (rc != BOPY_OK) return rc;
+    const int gb = gp->sm_count, nb = gp->n_blocks;
+    const long long chunk = (long long)gb * PROBE_MAX_NC;
+    const ProbePlan pl = probe_plan(gp, 1);
+    rc = launch_probe(gp, pl, gp->Xt /* any d doubles: the candidate is not used */, 1, BOPY_ACQ_NONE, 0.0, 0.0, nullptr,
+                      nullptr, nullptr, 0, nullptr, 1, st, yn_dev);
+    if (rc != BOPY_OK) return rc;
+    GradParams q;
+    std::memset(&q, 0, sizeof(q));
+    q.Lt = reinterpret_cast<const unsigned char*>(gp->Lt);
+    q.Xt = gp->Xt;
+    q.V = reinterpret_cast<const double*>(gp->Vws);
+    q.W = reinterpret_cast<double*>(gp->Vws) + chunk * gp->n_pad;
+    q.Xs = gp->Xt;
+    q.m = 1;
+    q.nbatch = pl.nbatch;
+    q.groups = pl.groups;
+    q.n = (int)gp->n;
+    q.n_blocks = nb;
+    q.d = gp->d;
+    for (int k = 0; k < gp->d; ++k) q.ls[k] = gp->ls[k];
+    q.amp = gp->amp;
+    q.y_std = gp->y_std;
+    q.y_var = gp->y_std * gp->y_std;
+    q.acq = A_LCB;
+    q.flags = gp->grad_flags;
+    q.flags2 = gp->grad_flags + (size_t)gb * nb;
+    q.gpart = gp->grad_part;
+    q.mean = gp->grad_mv;
+    q.var = gp->grad_mv;
+    q.grad_out = gp->grad_part;
+    q.ticket = gp->probe_flags;
+    q.ticket_base = gp->probe_ticket_base;
+    if (++gp->grad_epoch == 0) {
+        CUDA_TRY(cudaMemsetAsync(gp->grad_flags, 0, (size_t)2 * gb * nb * sizeof(unsigned), st));
+        gp->grad_epoch = 1;
+    }
+    q.epoch = gp->grad_epoch;
+    q.solve_only = 1;
+    rc = launch_grad_k<1>(gp->kernel, q, pl.grid, st);
+    if (rc != BOPY_OK) return rc;
+    gp->probe_ticket_base += (unsigned)pl.grid;
+    extract_column_kernel<<<(unsigned)((gp->n + 255) / 256), 256, 0, st>>>(q.W, (int)gp->n, alpha_dev);
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
 }
 
 // the one place the sweep is launched from
@@ -471,8 +536,16 @@ LsParam store_hyper(bopy_gp* gp, const double* length_scale_host, int n_ls, doub
 }
 
 // pack (L, Dinv, X, alpha) into the sweep layout; gp->Dinv must already hold the inverted diagonal blocks
+int pack_factor(bopy_gp* gp, const double* L_dev, int ld, cudaStream_t st);
+int pack_x(bopy_gp* gp, const double* X_dev, const double* alpha_dev, const LsParam& ls, cudaStream_t st);
+
 int pack_state(bopy_gp* gp, const double* X_dev, const double* L_dev, int ld, const double* alpha_dev, const LsParam& ls,
                cudaStream_t st) {
+    int rc = pack_factor(gp, L_dev, ld, st);
+    return rc != BOPY_OK ? rc : pack_x(gp, X_dev, alpha_dev, ls, st);
+}
+
+int pack_factor(bopy_gp* gp, const double* L_dev, int ld, cudaStream_t st) {
     const int n = (int)gp->n;
     dispatch_engine(gp, [&](auto e) {
         using E = decltype(e);
@@ -481,12 +554,16 @@ int pack_state(bopy_gp* gp, const double* X_dev, const double* L_dev, int ld, co
         return BOPY_OK;
     });
     CUDA_TRY(cudaGetLastError());
-    pack_x_kernel<<<gp->n_blocks, BM, 0, st>>>(X_dev, alpha_dev, n, gp->d, ls, gp->Xt);
-    CUDA_TRY(cudaGetLastError());
     if (gp->probe_capable && gp->n_blocks > 1) {
         pack_m_kernel<<<gp->n_blocks - 1, 256, 0, st>>>(L_dev, n, ld, gp->Dinv, reinterpret_cast<unsigned char*>(gp->Mt));
         CUDA_TRY(cudaGetLastError());
     }
+    return BOPY_OK;
+}
+
+int pack_x(bopy_gp* gp, const double* X_dev, const double* alpha_dev, const LsParam& ls, cudaStream_t st) {
+    pack_x_kernel<<<gp->n_blocks, BM, 0, st>>>(X_dev, alpha_dev, (int)gp->n, gp->d, ls, gp->Xt);
+    CUDA_TRY(cudaGetLastError());
     return BOPY_OK;
 }
 
@@ -580,12 +657,17 @@ int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const do
     const double diag = (amplitude + noise_level) + alpha_reg;   // kernel_(X) diagonal, then += alpha
     launch_gram(gp, X_dev, ls, gp->amp, diag, A, ld, n, st);
     launch_cholesky(A, n, ld, nb, gp->Dinv, status, st);
-    solve_alpha_kernel<<<1, 1024, 0, st>>>(A, n, ld, nb, gp->Dinv, yn_dev, z, alpha);
     e = cudaGetLastError();
-    if (e == cudaSuccess) {
-        rc = pack_state(gp, X_dev, A, ld, alpha, ls, st);
-    } else {
+    if (e != cudaSuccess) {
         rc = fail(BOPY_ERR_CUDA, "fit kernels failed to launch: %s", cudaGetErrorString(e));
+    } else if (gp->probe_capable) {
+        // the packed factor first: alpha_ is then solved on it by the chained kernels
+        rc = pack_factor(gp, A, ld, st);
+        if (rc == BOPY_OK) rc = solve_alpha_chain(gp, yn_dev, alpha, st);
+        if (rc == BOPY_OK) rc = pack_x(gp, X_dev, alpha, ls, st);
+    } else {
+        solve_alpha_kernel<<<1, 1024, 0, st>>>(A, n, ld, nb, gp->Dinv, yn_dev, z, alpha);
+        rc = pack_state(gp, X_dev, A, ld, alpha, ls, st);
     }
     if (rc == BOPY_OK && L_out_dev != nullptr)   // export: (n, n) row-major, zeros above the diagonal
         e = cudaMemcpy2DAsync(L_out_dev, (size_t)n * sizeof(double), A, (size_t)ld * sizeof(double), (size_t)n * sizeof(double),
@@ -643,11 +725,13 @@ int bopy_gp_append(bopy_gp* gp, const double* X_dev, const double* yn_dev, doubl
     const size_t chol_smem = ((size_t)BM * (BM + 1) + BM + 2) * sizeof(double);
     cudaFuncSetAttribute(dinv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem);
     dinv_block_kernel<<<1, CHOL_NT, chol_smem, st>>>(gp->Lfull, n + 1, ld, n / BM, gp->Dinv);
-    // 3. alpha for the (re-normalised) targets, then the packed state
-    solve_alpha_kernel<<<1, 1024, 0, st>>>(gp->Lfull, n + 1, ld, nb, gp->Dinv, yn_dev, z, alpha);
+    // 3. the packed factor, alpha for the (re-normalised) targets solved on it, then X / alpha
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) rc = pack_state(gp, X_dev, gp->Lfull, ld, alpha, ls, st);
-    else rc = fail(BOPY_ERR_CUDA, "append kernels failed to launch: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) rc = fail(BOPY_ERR_CUDA, "append kernels failed to launch: %s", cudaGetErrorString(e));
+    if (rc == BOPY_OK) rc = pack_factor(gp, gp->Lfull, ld, st);
+    if (rc == BOPY_OK) rc = solve_alpha_chain(gp, yn_dev, alpha, st);
+    if (rc == BOPY_OK) rc = pack_x(gp, X_dev, alpha, ls, st);
+    (void)z;
     int host_status = 0;
     if (rc == BOPY_OK) e = cudaMemcpyAsync(&host_status, status, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (rc == BOPY_OK && e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -803,13 +887,8 @@ int bopy_acq_value_and_grad(bopy_gp* gp, int acq, double eta, double kappa, cons
     CUDA_TRY(cudaSetDevice(gp->device));
     const int gb = gp->sm_count, nb = gp->n_blocks;            // batches per chunk
     const long long chunk = (long long)gb * PROBE_MAX_NC;       // candidates per chunk: V and W share the sweep workspace
-    if (gp->grad_flags == nullptr) {
-        const size_t nflags = (size_t)2 * gb * nb;
-        CUDA_TRY(cudaMalloc(&gp->grad_flags, nflags * sizeof(unsigned)));
-        CUDA_TRY(cudaMemset(gp->grad_flags, 0, nflags * sizeof(unsigned)));
-        CUDA_TRY(cudaMalloc(&gp->grad_part, (size_t)gb * nb * 2 * gp->d * PROBE_MAX_NC * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&gp->grad_mv, (size_t)2 * chunk * sizeof(double)));
-    }
+    rc = ensure_grad_buffers(gp);
+    if (rc != BOPY_OK) return rc;
     for (long long off = 0; off < m; off += chunk) {
         const long long mc = std::min<long long>(chunk, m - off);
         const ProbePlan pl = probe_plan(gp, mc);

@@ -43,6 +43,7 @@ struct GradParams {
     double* gpart;             // [nbatch][n_blocks][2][d][NC]
     unsigned* ticket;
     unsigned ticket_base, epoch;
+    int solve_only;            // 1: just the backward solve W = L^-T V, every block stored (alpha_ = L^-T L^-1 y); no gradient
 };
 
 template <int NA> constexpr size_t grad_smem_bytes(int d) {
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(PROBE_NT, 1) grad_kernel(const GradParams p) {
             for (int a = 0; a < NA; ++a) {
                 const double2 w = make_double2(acc[i][a][0][0] + acc[i][a][1][0], acc[i][a][0][1] + acc[i][a][1][1]);
                 *reinterpret_cast<double2*>(&Rs[a * 1024 + roff[i]]) = w;
-                if (I > 0)
+                if (I > 0 || p.solve_only)
                     *reinterpret_cast<double2*>(&p.W[(((long long)b * NA + a) * n_pad + (long long)I * BM) * 8 + roff[i]]) = w;
             }
         consumer_sync();
@@ -267,6 +268,10 @@ __global__ void __launch_bounds__(PROBE_NT, 1) grad_kernel(const GradParams p) {
             st_release_gpu(p.flags + (long long)b * nb + I, p.epoch);
         }
 
+        if (p.solve_only) {
+            consumer_sync();
+            continue;
+        }
         // ---- this block's share of sum_i alpha_i dk_i/dx and sum_i w_i dk_i/dx (off the chain's critical path) -----
         double* const UT = Wb;   // [2][128][NC]: t = alpha kd, u = w kd  (W_J buffers are free after the chain step)
         {

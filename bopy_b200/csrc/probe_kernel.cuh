@@ -58,6 +58,7 @@ struct ProbeParams {
     unsigned* ticket;          // role counter (monotonic over launches)
     unsigned ticket_base, epoch;
     int keep_v;                // 1: the last block row of V is stored too (the gradient's backward solve reads all of V)
+    const double* rhs;         // optional (n,): solve L v = rhs for candidate 0 instead of a kernel column (alpha_ solve)
     long long* trace;          // optional [n_blocks][8] %globaltimer stamps of batch 0 (tools/probe_trace.py), or nullptr
 };
 
@@ -211,7 +212,9 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
 #pragma unroll
             for (int j = 0; j < HC; ++j) {
                 const int c = h * HC + j;
-                const double kv = __dmul_rn(amp_i, base_kernel<KIND>(d2[j]));
+                double kv = __dmul_rn(amp_i, base_kernel<KIND>(d2[j]));
+                if (p.rhs != nullptr)   // right-hand-side mode: column 0 of the batch is the given vector, the rest 0
+                    kv = (c == 0 && I * BM + row < p.n) ? p.rhs[I * BM + row] : 0.0;
                 Rs[(c >> 3) * 1024 + row * 8 + (c & 7)] = kv;
                 mp[j] = kv * a_i;
             }
