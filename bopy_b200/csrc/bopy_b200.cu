@@ -584,17 +584,71 @@ void launch_gram(const bopy_gp* gp, const double* X, const LsParam& ls, double a
 }
 
 // in-place blocked Cholesky of the lower triangle of A (n x n, leading dimension ld); Dinv receives inv(L_JJ)
+// Look-ahead of depth one: the serial chain chol(J) -> panel(J) -> trailing update of block column J+1 runs on a
+// HIGH-priority side stream, the bulk of the trailing update of step J (block columns >= J+2) stays on the caller's
+// stream, so that the chain of step J+1 runs beside it (thread blocks of the higher-priority stream are dispatched
+// first as multiprocessors free up; with equal priorities the bulk's queue starves the chain and nothing overlaps).
+struct CholStreams {
+    cudaStream_t chain = nullptr;
+    cudaEvent_t start = nullptr, end = nullptr, panel_done[2] = {nullptr, nullptr}, rest_done[2] = {nullptr, nullptr};
+    bool ok = false;
+};
+CholStreams& chol_streams() {
+    static thread_local CholStreams per_device[64];   // a stream belongs to the device that was current at its creation
+    int dev = 0;
+    cudaGetDevice(&dev);
+    CholStreams& cs = per_device[dev & 63];
+    if (!cs.ok) {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        bool good = cudaStreamCreateWithPriority(&cs.chain, cudaStreamNonBlocking, greatest) == cudaSuccess;
+        good = good && cudaEventCreateWithFlags(&cs.start, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&cs.end, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 2 && good; ++i)
+            good = cudaEventCreateWithFlags(&cs.panel_done[i], cudaEventDisableTiming) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&cs.rest_done[i], cudaEventDisableTiming) == cudaSuccess;
+        cs.ok = good;
+    }
+    return cs;
+}
+
 void launch_cholesky(double* A, int n, int ld, int nb, double* Dinv, int* status, cudaStream_t st) {
     const size_t chol_smem = ((size_t)BM * (BM + 1) + BM + 2) * sizeof(double);
     cudaFuncSetAttribute(chol_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem);
+    CholStreams& cs = chol_streams();
+    if (!(cs.ok && nb >= 4)) {   // plain right-looking order on one stream
+        for (int J = 0; J < nb; ++J) {
+            chol_block_kernel<<<1, CHOL_NT, chol_smem, st>>>(A, n, ld, J, Dinv, status);
+            const int below = nb - J - 1;
+            if (below > 0) {
+                gemm_nt_kernel<<<below, NT, 0, st>>>(A, n, ld, J, Dinv, 0);
+                gemm_nt_kernel<<<below * (below + 1) / 2, NT, 0, st>>>(A, n, ld, J, Dinv, 1);
+            }
+        }
+        return;
+    }
+    cudaStream_t hi = cs.chain;
+    cudaEventRecord(cs.start, st);            // everything queued on st so far (the Gram matrix) comes first
+    cudaStreamWaitEvent(hi, cs.start, 0);
+    bool rest_pending = false;
     for (int J = 0; J < nb; ++J) {
-        chol_block_kernel<<<1, CHOL_NT, chol_smem, st>>>(A, n, ld, J, Dinv, status);
+        chol_block_kernel<<<1, CHOL_NT, chol_smem, hi>>>(A, n, ld, J, Dinv, status);
         const int below = nb - J - 1;
-        if (below > 0) {
-            gemm_nt_kernel<<<below, NT, 0, st>>>(A, n, ld, J, Dinv, 0);
-            gemm_nt_kernel<<<below * (below + 1) / 2, NT, 0, st>>>(A, n, ld, J, Dinv, 1);
+        if (below <= 0) break;
+        gemm_nt_kernel<<<below, NT, 0, hi>>>(A, n, ld, J, Dinv, 0);
+        cudaEventRecord(cs.panel_done[J & 1], hi);
+        if (rest_pending) cudaStreamWaitEvent(hi, cs.rest_done[(J - 1) & 1], 0);   // step J-1 also updated block column J+1
+        gemm_nt_kernel<<<below, NT, 0, hi>>>(A, n, ld, J, Dinv, 2);
+        rest_pending = false;
+        if (below > 1) {
+            cudaStreamWaitEvent(st, cs.panel_done[J & 1], 0);
+            gemm_nt_kernel<<<(below - 1) * below / 2, NT, 0, st>>>(A, n, ld, J, Dinv, 3);
+            cudaEventRecord(cs.rest_done[J & 1], st);
+            rest_pending = true;
         }
     }
+    cudaEventRecord(cs.end, hi);
+    cudaStreamWaitEvent(st, cs.end, 0);       // the caller's stream continues after the whole factorisation
 }
 
 }  // namespace

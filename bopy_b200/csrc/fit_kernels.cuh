@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(256) append_row_kernel(const double* __restric
 // C_tile = beta * C_tile + sign * A_tile * B_tile^T on 128 x 128 x 128 tiles of row-major matrices, fp64 DMMA.
 //   mode 0 (panel):    tile I in (J, nb):   A = Amat[I][J] (input), B = Dinv_J, C = Amat[I][J] (in place), beta 0
 //   mode 1 (trailing): tiles I >= K > J:    A = Amat[I][J], B = Amat[K][J], C = Amat[I][K], beta 1, sign -1
+//   mode 2 / 3: the same restricted to K = J+1 / to K >= J+2 (look-ahead: see launch_cholesky)
 // Rows / columns beyond n are treated as zero on load and skipped on store.
 __global__ void __launch_bounds__(NT) gemm_nt_kernel(double* Amat, int n, int ld, int J, const double* Dinv, int mode) {
     __shared__ __align__(16) double As[2][DmmaPolicy::KC * BM];
@@ -251,14 +252,21 @@ __global__ void __launch_bounds__(NT) gemm_nt_kernel(double* Amat, int n, int ld
     if (mode == 0) {
         I = J + 1 + blockIdx.x;
         K = J;
+    } else if (mode == 2) {   // trailing update of block column J+1 only (what the next diagonal block / panel needs)
+        I = J + 1 + blockIdx.x;
+        K = J + 1;
+        mode = 1;
     } else {
-        // enumerate the lower-triangular tile set {(I, K): J < K <= I < nb} with a linear index
+        // enumerate the lower-triangular tile set {(I, K): K0 <= K <= I < nb} with a linear index; K0 = J+1 (mode 1: the
+        // whole trailing matrix) or J+2 (mode 3: everything but block column J+1)
+        const int K0 = mode == 3 ? J + 2 : J + 1;
         const int idx = blockIdx.x;
         int rrow = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
         while ((rrow + 1) * (rrow + 2) / 2 <= idx) ++rrow;
         while (rrow * (rrow + 1) / 2 > idx) --rrow;
-        I = J + 1 + rrow;
-        K = J + 1 + (idx - rrow * (rrow + 1) / 2);
+        I = K0 + rrow;
+        K = K0 + (idx - rrow * (rrow + 1) / 2);
+        mode = 1;
     }
     const int tid = threadIdx.x;
     const DmmaPolicy pol(tid);
