@@ -104,26 +104,35 @@ __global__ void __launch_bounds__(CHOL_NT) chol_block_kernel(double* A, int n, i
     if (tid == 0) *fail = 0;
     __syncthreads();
     for (int k0 = 0; k0 < BM; k0 += PW) {
-        // (a) unblocked right-looking Cholesky of the PW x PW diagonal block, one warp
+        // (a) Cholesky of the PW x PW diagonal block in REGISTERS: lane r of warp 0 holds row r, column entries travel
+        //     by shuffles (no shared-memory round trip inside the 16 dependent steps)
         if (warp == 0) {
+            const int r = lane & (PW - 1);          // lanes 16..31 mirror lanes 0..15 and do not store
+            double a[PW];
+#pragma unroll
+            for (int c = 0; c < PW; ++c) a[c] = c <= r ? sm[(k0 + r) * LD + k0 + c] : 0.0;
+            bool bad = false;
+            double pivot = 1.0;                     // this lane's own diagonal entry L[r][r]
+#pragma unroll
             for (int k = 0; k < PW; ++k) {
-                const int kk = k0 + k;
-                const double akk = sm[kk * LD + kk];
-                if (!(akk > 0.0)) {           // warp-uniform
-                    if (lane == 0) *fail = 1;
-                    break;
-                }
+                const double akk = __shfl_sync(0xffffffffu, a[k], k);
+                bad = bad || !(akk > 0.0);
                 const double lkk = sqrt(akk);
-                __syncwarp();
-                if (lane == k) sm[kk * LD + kk] = lkk;
-                if (lane > k && lane < PW) sm[(k0 + lane) * LD + kk] /= lkk;
-                __syncwarp();
-                for (int e = lane; e < PW * PW; e += 32) {
-                    const int r = e / PW, c = e - r * PW;
-                    if (c > k && c <= r)
-                        sm[(k0 + r) * LD + k0 + c] = fma(-sm[(k0 + r) * LD + kk], sm[(k0 + c) * LD + kk], sm[(k0 + r) * LD + k0 + c]);
+                if (r == k) a[k] = pivot = lkk;
+                else if (r > k) a[k] = a[k] / lkk;
+#pragma unroll
+                for (int c = k + 1; c < PW; ++c) {
+                    const double lck = __shfl_sync(0xffffffffu, a[k], c);   // L[c][k]
+                    if (r >= c) a[c] = fma(-a[k], lck, a[c]);
                 }
-                __syncwarp();
+            }
+            if (bad) {
+                if (lane == 0) *fail = 1;
+            } else if (lane < PW) {
+#pragma unroll
+                for (int c = 0; c < PW; ++c)
+                    if (c <= r) sm[(k0 + r) * LD + k0 + c] = a[c];
+                rdg[k0 + r] = 1.0 / pivot;          // reciprocal of the pivot: the panel rows multiply by it
             }
         }
         __syncthreads();
@@ -139,7 +148,7 @@ __global__ void __launch_bounds__(CHOL_NT) chol_block_kernel(double* A, int n, i
                 double sacc = sm[tid * LD + k0 + c];
 #pragma unroll
                 for (int k = 0; k < c; ++k) sacc = fma(-x[k], sm[(k0 + c) * LD + k0 + k], sacc);
-                x[c] = sacc / sm[(k0 + c) * LD + k0 + c];
+                x[c] = sacc * rdg[k0 + c];
             }
 #pragma unroll
             for (int c = 0; c < PW; ++c) sm[tid * LD + k0 + c] = x[c];
