@@ -76,3 +76,29 @@ def test_random_pruned_argmin(seed):
     minv, mini, stats = gp.argmin_pruned(xs, acq, eta=eta, kappa=2.0)
     if not np.isnan(float(full["min_val"].item())):
         assert int(mini.item()) == int(full["min_idx"].item()) and float(minv.item()) == float(full["min_val"].item()), stats
+
+
+@pytest.mark.parametrize("m", [600, 2000])
+def test_largest_dimensionality_through_every_batch_shape(m):
+    """d = 32 (the supported maximum) with 16- and 32-candidate batches: the shared-memory budgets of the latency path
+    and the gradient kernel at their tightest."""
+    rng = np.random.default_rng(m)
+    n, d = 257, 32
+    X = rng.random((n, d))
+    y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(n)
+    spec = O.KernelSpec(kind="rbf", length_scale=1.5 + rng.random(d), amplitude=1.2)
+    st = O.fit_state(X, y, spec, 1e-6, normalize_y=True)
+    gp = select_path(native_for(st, "f64"), "latency")
+    xs = rng.random((m, d))
+    out = gp.sweep(gp.candidates(xs), acq="lcb", kappa=2.0, want_mean=True, want_var=True, want_acq=True, want_min=True)
+    o_mean, o_var, o_a, (o_idx, _) = O.acquisition_sweep(st, "lcb", xs, kappa=2.0)
+    err, bound = check_mean(out["mean"].cpu().numpy(), o_mean, st, "f64")
+    dot_cond = st.y_std * (np.abs(O.kernel_cross(st.kernel, xs, st.X_train)) @ np.abs(st.alpha))
+    assert (err <= bound + 16 * np.finfo(np.float64).eps * dot_cond).all()
+    err, bound = check_var(out["var"].cpu().numpy(), o_var, st, "f64")
+    assert (err <= bound).all()
+    assert is_stated_tie(o_a, o_idx, int(out["min_idx"].item()), "f64")
+    val, grad, _, _ = (t.cpu().numpy() for t in gp.value_and_grad(gp.candidates(xs), "lcb", kappa=2.0))
+    _, o_grad, _, _ = O.acquisition_value_and_grad(st, "lcb", xs, kappa=2.0)
+    scale = np.abs(o_grad).max()
+    assert (np.abs(grad - o_grad) <= 1e-6 * np.abs(o_grad) + 1e-9 * scale).all()
