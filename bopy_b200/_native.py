@@ -31,6 +31,7 @@ _SIGNATURES = {
     "bopy_gp_fit": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_double, c_double, c_double,
                             c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "bopy_gp_append": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p]),
+    "bopy_gp_truncate": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p]),
     "bopy_gp_lml": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_double, c_double, c_double,
                             POINTER(c_double), POINTER(c_double), c_void_p]),
     "bopy_gp_posterior_acq": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_double, c_void_p, c_void_p,
@@ -218,6 +219,20 @@ class NativeGP:
             check(self.lib.bopy_gp_append(self._handle, _ptr(Xd), _ptr(yd), float(y_mean), float(y_std), _ptr(alpha),
                                           _stream(self.device)), "bopy_gp_append")
         self.n += 1
+        return alpha
+
+    def truncate(self, X, y_normalised, y_mean=0.0, y_std=1.0):
+        """Keep only the first len(X) points of the fitted data set (a leading subset): bopy_gp_truncate.
+        Returns alpha (n_new,) as a device tensor."""
+        torch = require_cuda()
+        n_new = len(X)
+        Xd = self._dev64(X, (n_new, self.d))
+        yd = self._dev64(y_normalised, (n_new,))
+        alpha = torch.empty(n_new, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.bopy_gp_truncate(self._handle, n_new, _ptr(Xd), _ptr(yd), float(y_mean), float(y_std),
+                                            _ptr(alpha), _stream(self.device)), "bopy_gp_truncate")
+        self.n = n_new
         return alpha
 
     def lml(self, X, y_normalised, length_scale, amplitude=1.0, noise_level=0.0, alpha_reg=1e-10, want_grad=True):

@@ -800,6 +800,48 @@ int bopy_gp_append(bopy_gp* gp, const double* X_dev, const double* yn_dev, doubl
     return BOPY_OK;
 }
 
+int bopy_gp_truncate(bopy_gp* gp, int64_t n_new, const double* X_dev, const double* yn_dev, double y_mean, double y_std,
+                     double* alpha_out_dev, void* stream) {
+    int rc = check_ready(gp);
+    if (rc != BOPY_OK) return rc;
+    if (X_dev == nullptr || yn_dev == nullptr) return fail(BOPY_ERR_BAD_ARG, "X_dev and yn_dev must be non-NULL");
+    if (!gp->Lfull_valid || !gp->probe_capable)
+        return fail(BOPY_ERR_NOT_READY, "bopy_gp_truncate needs a state built by bopy_gp_fit on an fp64 handle");
+    if (n_new < 1 || n_new >= gp->n || (n_new + BM - 1) / BM != gp->n_blocks)
+        return fail(BOPY_ERR_BAD_ARG, "n_new = %lld must be in [1, n) and keep the handle's %d block rows: refit",
+                    (long long)n_new, gp->n_blocks);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    LsParam ls;
+    for (int q = 0; q < MAX_D; ++q) ls.v[q] = q < gp->d ? gp->ls[q] : 1.0;
+    double* scratch = nullptr;
+    if (alpha_out_dev == nullptr) CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (size_t)n_new * sizeof(double), st));
+    double* const alpha = alpha_out_dev != nullptr ? alpha_out_dev : scratch;
+    // the factor of the first n_new points is the leading block of the kept factor: only the padding of the last
+    // diagonal block, the targets and their normalisation change
+    gp->ready = false;
+    gp->n = n_new;
+    gp->y_mean = y_mean;
+    gp->y_std = y_std;
+    const int ld = gp->n_pad;
+    const size_t chol_smem = ((size_t)BM * (BM + 1) + BM + 2) * sizeof(double);
+    cudaFuncSetAttribute(dinv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem);
+    dinv_block_kernel<<<1, CHOL_NT, chol_smem, st>>>(gp->Lfull, (int)n_new, ld, gp->n_blocks - 1, gp->Dinv);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(BOPY_ERR_CUDA, "truncate kernels failed to launch: %s", cudaGetErrorString(e));
+    if (rc == BOPY_OK) rc = pack_factor(gp, gp->Lfull, ld, st);
+    if (rc == BOPY_OK) rc = solve_alpha_chain(gp, yn_dev, alpha, st);
+    if (rc == BOPY_OK) rc = pack_x(gp, X_dev, alpha, ls, st);
+    if (rc == BOPY_OK) e = cudaStreamSynchronize(st);
+    if (scratch) cudaFreeAsync(scratch, st);
+    if (rc != BOPY_OK || e != cudaSuccess) {
+        gp->Lfull_valid = false;
+        return rc != BOPY_OK ? rc : fail(BOPY_ERR_CUDA, "bopy_gp_truncate failed: %s", cudaGetErrorString(e));
+    }
+    gp->ready = true;
+    return BOPY_OK;
+}
+
 int bopy_gp_lml(bopy_gp* gp, const double* X_dev, const double* yn_dev, const double* length_scale_host, int n_ls,
                 double amplitude, double noise_level, double alpha_reg, double* lml_out_host, double* grad_out_host,
                 void* stream) {

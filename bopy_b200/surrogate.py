@@ -208,13 +208,17 @@ class B200GPSurrogate(Surrogate):
         gp, native = self.gp, self.native
         prev = getattr(gp, "X_train_", None)
         if (native is None or not self.fitted_on_device or gp.optimizer is not None or prev is None
-                or getattr(self, "_append_key", None) != self._spec_key(spec)
-                or X.shape != (prev.shape[0] + 1, prev.shape[1]) or native.n != prev.shape[0]
-                or (native.n + 1 + 127) // 128 != (native.n + 127) // 128
-                or not native.gradient_capable() or not np.array_equal(X[:-1], prev)):
+                or getattr(self, "_append_key", None) != self._spec_key(spec) or native.n != prev.shape[0]
+                or X.shape[1] != prev.shape[1] or not native.gradient_capable()
+                or (X.shape[0] + 127) // 128 != (native.n + 127) // 128):
+            return False
+        grow = X.shape[0] == prev.shape[0] + 1 and np.array_equal(X[:-1], prev)
+        # a leading subset of the previous data (the Kriging believer's restore): the factor is the leading block
+        shrink = X.shape[0] < prev.shape[0] and np.array_equal(X, prev[:X.shape[0]])
+        if not (grow or shrink):
             return False
         try:
-            alpha = native.append(X, yn, y_mean=float(y_mean), y_std=float(y_std))
+            alpha = (native.append if grow else native.truncate)(X, yn, y_mean=float(y_mean), y_std=float(y_std))
         except np.linalg.LinAlgError:
             raise
         except _native.NativeLibraryError:
@@ -225,7 +229,10 @@ class B200GPSurrogate(Surrogate):
         gp._y_train_mean, gp._y_train_std = y_mean, y_std
         gp.alpha_ = alpha.cpu().numpy()
         self.kernel_spec = spec
-        self.appended_rows = getattr(self, "appended_rows", 0) + 1
+        if grow:
+            self.appended_rows = getattr(self, "appended_rows", 0) + 1
+        else:
+            self.truncations = getattr(self, "truncations", 0) + 1
         return True
 
     def export_factor(self) -> np.ndarray:

@@ -116,6 +116,13 @@ int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const do
 int bopy_gp_append(bopy_gp* gp, const double* X_dev, const double* yn_dev, double y_mean, double y_std,
                    double* alpha_out_dev, void* stream);
 
+/* The reverse: keep only the first n_new points (the Kriging believer restores the real data when a batch is finished,
+ * bopy/acquisition.py:194-197).  The factor of a leading subset is the leading block of the kept factor, so nothing is
+ * refactorised: the last diagonal block is re-inverted for its new padding, alpha_ re-solved for yn_dev (n_new,), the
+ * state repacked.  Same preconditions as bopy_gp_append; n_new must keep the handle's number of 128-row blocks. */
+int bopy_gp_truncate(bopy_gp* gp, int64_t n_new, const double* X_dev, const double* yn_dev, double y_mean, double y_std,
+                     double* alpha_out_dev, void* stream);
+
 /*
  * Log marginal likelihood of the (normalised) targets under the given hyper-parameters, and optionally its gradient
  * with respect to the LOG hyper-parameters ($SK/_gpr.py:541-656).  Does not touch the

@@ -207,8 +207,18 @@ def test_one_point_growth_is_a_row_append_and_matches_a_fresh_fit():
                 np.testing.assert_allclose(sur.gp.alpha_, fresh.gp.alpha_, rtol=0, atol=1e-7 * np.abs(fresh.gp.alpha_).max())
         # 19 growth steps, all but the one that needed a fourth block (384 -> 385) were appends
         assert sur.appended_rows == 18
-        # shrinking back (what KriggingBeliever.finish_batch does) is a plain refit and still right
+        # shrinking back to a leading subset (what KriggingBeliever.finish_batch does): 389 -> 370 needs one block row
+        # less, a plain refit; 370 -> 366 keeps the blocks and truncates the kept factor
         sur.fit(X[:n0], y[:n0])
+        assert getattr(sur, "truncations", 0) == 0
+        sur.fit(X[:n0 + 3], y[:n0 + 3])
+        sur.fit(X[:n0 - 4], y[:n0 - 4])
+        assert sur.truncations == 1
+        fresh = make()
+        fresh.fit(X[:n0 - 4], y[:n0 - 4])
+        for a, b in zip(sur.predict_diag(xs), fresh.predict_diag(xs)):
+            np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-10 * np.abs(b).max())
+        sur.fit(X[:n0], y[:n0])              # neither a one-point growth nor a subset: refit
         fresh = make()
         fresh.fit(X[:n0], y[:n0])
         assert np.array_equal(sur.predict_diag(xs)[0], fresh.predict_diag(xs)[0])
