@@ -50,6 +50,8 @@ _SIGNATURES = {
                                        POINTER(c_int64), c_void_p]),
     "bopy_acq_segment_argmin": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_int64, c_int64,
                                         c_void_p, c_void_p, c_void_p]),
+    "bopy_acq_segment_argmin_pruned": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_int64, c_int64,
+                                               c_void_p, c_void_p, POINTER(c_int64), c_void_p]),
     "bopy_candidates_around": (c_int, [c_uint64, c_void_p, c_int64, c_int, c_int, POINTER(c_double), POINTER(c_double),
                                        POINTER(c_double), c_void_p, c_void_p]),
     "bopy_multistart_step": (c_int, [c_int64, c_int, POINTER(c_double), POINTER(c_double), c_void_p, c_void_p, c_void_p,
@@ -370,6 +372,20 @@ class NativeGP:
                                                    int(seg_len), int(index_base), _ptr(vals), _ptr(idxs),
                                                    _stream(self.device)), "bopy_acq_segment_argmin")
         return vals, idxs
+
+    def segment_argmin_pruned(self, Xs, seg_len, acq, eta=0.0, kappa=2.0, index_base=0):
+        """segment_argmin by branch and bound: (values, indices, stats).  Xs.shape[0] must be a multiple of seg_len."""
+        torch = require_cuda()
+        m = Xs.shape[0]
+        nseg = m // seg_len
+        vals = torch.empty(nseg, dtype=torch.float64, device=self.device)
+        idxs = torch.empty(nseg, dtype=torch.int64, device=self.device)
+        stats = (c_int64 * 3)()
+        with torch.cuda.device(self.device):
+            check(self.lib.bopy_acq_segment_argmin_pruned(self._handle, ACQ_IDS[acq], float(eta), float(kappa), _ptr(Xs), m,
+                                                          int(seg_len), int(index_base), _ptr(vals), _ptr(idxs), stats,
+                                                          _stream(self.device)), "bopy_acq_segment_argmin_pruned")
+        return vals, idxs, {"candidates": stats[0], "sample": stats[1], "swept": stats[2]}
 
     def predict_cov(self, Xs):
         torch = require_cuda()

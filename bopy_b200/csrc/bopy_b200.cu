@@ -1128,7 +1128,7 @@ int bopy_acq_argmin_pruned(bopy_gp* gp, int acq, double eta, double kappa, const
         return rc;
     }
     // 3. survivors = {bound <= incumbent}, ascending order kept
-    compact_count_kernel<<<nblocks, PRUNE_NT, 0, st>>>(bound, m, thr, counts);
+    compact_count_kernel<<<nblocks, PRUNE_NT, 0, st>>>(bound, m, thr, m, counts);
     compact_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, total);
     long long count = 0;
     cudaError_t e = cudaMemcpyAsync(&count, total, sizeof(long long), cudaMemcpyDeviceToHost, st);
@@ -1151,7 +1151,7 @@ int bopy_acq_argmin_pruned(bopy_gp* gp, int acq, double eta, double kappa, const
         return fail(BOPY_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
     }
     double* const rows = reinterpret_cast<double*>(idx_list + count);
-    compact_scatter_kernel<<<nblocks, PRUNE_NT, 0, st>>>(bound, m, thr, counts, Xs_dev, d, idx_list, rows);
+    compact_scatter_kernel<<<nblocks, PRUNE_NT, 0, st>>>(bound, m, thr, m, counts, Xs_dev, d, idx_list, rows);
     // 4. the full fused sweep over the survivors only; local index -> original index
     rc = run_sweep(gp, rows, count, acq, eta, kappa, nullptr, nullptr, nullptr, 0, min_val_out, min_idx, gp->Vws, 0, st, nullptr, false);
     if (rc == BOPY_OK) {
@@ -1187,6 +1187,79 @@ int bopy_acq_segment_argmin(bopy_gp* gp, int acq, double eta, double kappa, cons
         if (cudaGetLastError() != cudaSuccess) rc = fail(BOPY_ERR_CUDA, "segment_minloc_kernel failed to launch");
     }
     cudaFreeAsync(records, st);
+    return rc;
+}
+
+int bopy_acq_segment_argmin_pruned(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
+                                   int64_t seg_len, int64_t index_base, double* seg_val_out, int64_t* seg_idx_out,
+                                   int64_t* stats_out_host, void* stream) {
+    int rc = check_ready(gp);
+    if (rc != BOPY_OK) return rc;
+    if (Xs_dev == nullptr || seg_val_out == nullptr || seg_idx_out == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "Xs_dev / seg_val_out / seg_idx_out is NULL");
+    if (acq < BOPY_ACQ_LCB || acq > BOPY_ACQ_POI) return fail(BOPY_ERR_BAD_ARG, "unknown acquisition id %d", acq);
+    const long long stride = 16;   // one candidate in 16 of every segment is evaluated up front: the segment's incumbent
+    if (seg_len < BN || seg_len % BN != 0)
+        return fail(BOPY_ERR_BAD_ARG, "seg_len must be a positive multiple of %d (got %lld)", BN, (long long)seg_len);
+    if (m < seg_len || m % seg_len != 0)
+        return fail(BOPY_ERR_BAD_ARG, "m must be a positive multiple of seg_len for the pruned segmented arg-min");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    const int d = gp->d;
+    const long long nseg = m / seg_len, nsample = m / stride, per_seg = seg_len / stride;
+    const long long per_block = (long long)PRUNE_NT * COMPACT_ITEMS;
+    const int nblocks = (int)((m + per_block - 1) / per_block);
+    double* bound = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&bound),
+                             ((size_t)m + (size_t)nseg + 2 + (size_t)nsample * (d + 1)) * sizeof(double) +
+                                 ((size_t)nblocks + 4) * sizeof(unsigned) + 16, st));
+    double* const inc = bound + m;                         // [nseg] incumbents
+    long long* const total = reinterpret_cast<long long*>(inc + nseg);
+    double* const svals = inc + nseg + 2;                  // [nsample] sample values
+    double* const srows = svals + nsample;                 // [nsample][d] sample rows
+    unsigned* const counts = reinterpret_cast<unsigned*>(srows + (size_t)nsample * d);
+    auto cleanup = [&]() { cudaFreeAsync(bound, st); };
+    const double sd_max = std::sqrt((gp->amp + gp->noise)) * std::fabs(gp->y_std);
+    launch_mean_bound(gp, Xs_dev, m, sd_max, acq, eta, kappa, nullptr, bound, st);
+    strided_rows_kernel<<<(unsigned)((nsample * d + 255) / 256), 256, 0, st>>>(Xs_dev, d, stride, nsample, srows);
+    rc = run_sweep(gp, srows, nsample, acq, eta, kappa, nullptr, nullptr, svals, 0, nullptr, nullptr, gp->Vws, 0, st, nullptr, false);
+    if (rc != BOPY_OK) {
+        cleanup();
+        return rc;
+    }
+    segment_incumbent_kernel<<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(svals, nsample, per_seg, nseg, inc);
+    compact_count_kernel<<<nblocks, PRUNE_NT, 0, st>>>(bound, m, inc, seg_len, counts);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, total);
+    long long count = 0;
+    cudaError_t e = cudaMemcpyAsync(&count, total, sizeof(long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(BOPY_ERR_CUDA, "pruned segmented argmin failed: %s", cudaGetErrorString(e));
+    }
+    if (stats_out_host) stats_out_host[0] = m, stats_out_host[1] = nsample, stats_out_host[2] = count;
+    if (count <= 0 || count > m / 2) {   // not selective: the plain segmented sweep
+        cleanup();
+        if (stats_out_host) stats_out_host[2] = m;
+        return bopy_acq_segment_argmin(gp, acq, eta, kappa, Xs_dev, m, seg_len, index_base, seg_val_out, seg_idx_out, stream);
+    }
+    long long* idx_list = nullptr;
+    e = cudaMallocAsync(reinterpret_cast<void**>(&idx_list), (size_t)count * (sizeof(long long) + (size_t)(d + 1) * sizeof(double)), st);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(BOPY_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    double* const rows = reinterpret_cast<double*>(idx_list + count);
+    double* const vals = rows + (size_t)count * d;
+    compact_scatter_kernel<<<nblocks, PRUNE_NT, 0, st>>>(bound, m, inc, seg_len, counts, Xs_dev, d, idx_list, rows);
+    rc = run_sweep(gp, rows, count, acq, eta, kappa, nullptr, nullptr, vals, 0, nullptr, nullptr, gp->Vws, 0, st, nullptr, false);
+    if (rc == BOPY_OK) {
+        segment_argmin_survivors_kernel<<<(unsigned)((nseg + 127) / 128), 128, 0, st>>>(
+            idx_list, vals, count, seg_len, nseg, index_base, seg_val_out, reinterpret_cast<long long*>(seg_idx_out));
+        if (cudaGetLastError() != cudaSuccess) rc = fail(BOPY_ERR_CUDA, "segment_argmin_survivors_kernel failed to launch");
+    }
+    cudaFreeAsync(idx_list, st);
+    cleanup();
     return rc;
 }
 

@@ -85,14 +85,14 @@ constexpr int COMPACT_ITEMS = 8;   // candidates per thread
 __device__ __forceinline__ bool prune_keep(double b, double thr) { return !(b > thr); }
 
 __global__ void __launch_bounds__(PRUNE_NT) compact_count_kernel(const double* __restrict__ bound, long long m, const double* __restrict__ thr_dev,
-                                                                unsigned* __restrict__ block_counts) {
+                                                                long long seg_len, unsigned* __restrict__ block_counts) {
     __shared__ unsigned warp_sums[PRUNE_NT / 32];
-    const double thr = *thr_dev;   // the incumbent value, still on the device (NaN: everything survives)
+    // thr_dev[i / seg_len]: the incumbent of candidate i's segment, still on the device (NaN: the segment survives whole)
     const long long base = ((long long)blockIdx.x * PRUNE_NT + threadIdx.x) * COMPACT_ITEMS;
     unsigned cnt = 0;
 #pragma unroll
     for (int k = 0; k < COMPACT_ITEMS; ++k)
-        if (base + k < m && prune_keep(bound[base + k], thr)) ++cnt;
+        if (base + k < m && prune_keep(bound[base + k], thr_dev[(base + k) / seg_len])) ++cnt;
 #pragma unroll
     for (int mask = 16; mask > 0; mask >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, mask);
     if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = cnt;
@@ -130,18 +130,17 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(unsigned* block_coun
 
 // idx_out[offset...] = ascending indices of the survivors of this block; rows_out (optional) = their candidate rows
 __global__ void __launch_bounds__(PRUNE_NT) compact_scatter_kernel(const double* __restrict__ bound, long long m, const double* __restrict__ thr_dev,
-                                                                  const unsigned* __restrict__ block_offsets,
+                                                                  long long seg_len, const unsigned* __restrict__ block_offsets,
                                                                   const double* __restrict__ Xs, int d,
                                                                   long long* __restrict__ idx_out,
                                                                   double* __restrict__ rows_out) {
     __shared__ unsigned warp_offs[PRUNE_NT / 32];
-    const double thr = *thr_dev;
     const long long base = ((long long)blockIdx.x * PRUNE_NT + threadIdx.x) * COMPACT_ITEMS;
     bool keep[COMPACT_ITEMS];
     unsigned cnt = 0;
 #pragma unroll
     for (int k = 0; k < COMPACT_ITEMS; ++k) {
-        keep[k] = base + k < m && prune_keep(bound[base + k], thr);
+        keep[k] = base + k < m && prune_keep(bound[base + k], thr_dev[(base + k) / seg_len]);
         cnt += keep[k] ? 1u : 0u;
     }
     // exclusive scan of cnt over the block: within the warp by shuffles, across warps through shared memory
@@ -180,6 +179,50 @@ __global__ void strided_rows_kernel(const double* __restrict__ Xs, int d, long l
     if (e >= S * d) return;
     const long long s = e / d;
     out[e] = Xs[s * stride * d + (e - s * d)];
+}
+
+// inc[s] = minimum (np.argmin ordering: a NaN wins) of the per_seg consecutive sample values of segment s
+__global__ void segment_incumbent_kernel(const double* __restrict__ vals, long long nvals, long long per_seg, long long nseg,
+                                         double* inc) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    MinLoc best;
+    best.val = 0.0;
+    best.idx = -1;
+    for (long long j = s * per_seg; j < (s + 1) * per_seg && j < nvals; ++j) {
+        MinLoc c;
+        c.val = vals[j];
+        c.idx = j;
+        if (minloc_better(c, best)) best = c;
+    }
+    inc[s] = best.idx >= 0 ? best.val : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// per-segment arg-min over the survivors (idx_list ascending, vals[i] = acquisition of candidate idx_list[i]): one thread
+// per segment finds its slice of the list by bisection and scans it with np.argmin's rules
+__global__ void segment_argmin_survivors_kernel(const long long* __restrict__ idx_list, const double* __restrict__ vals,
+                                                long long count, long long seg_len, long long nseg, long long index_base,
+                                                double* val_out, long long* idx_out) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const long long first = s * seg_len, last = first + seg_len;
+    long long lo = 0, hi = count;
+    while (lo < hi) {   // first position with idx_list[pos] >= first
+        const long long mid = (lo + hi) >> 1;
+        if (idx_list[mid] < first) lo = mid + 1;
+        else hi = mid;
+    }
+    MinLoc best;
+    best.val = 0.0;
+    best.idx = -1;
+    for (long long pos = lo; pos < count && idx_list[pos] < last; ++pos) {
+        MinLoc c;
+        c.val = vals[pos];
+        c.idx = index_base + idx_list[pos];
+        if (minloc_better(c, best)) best = c;
+    }
+    val_out[s] = best.val;
+    idx_out[s] = best.idx;
 }
 
 // min_idx (local index into the survivor list) -> original index

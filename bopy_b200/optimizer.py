@@ -135,7 +135,7 @@ class MultiStartOptimizer(Optimizer):
     def __init__(self, acquisition_function: AcquisitionFunction, bounds: Bounds, n_starts: int = 256,
                  n_candidates: int = 1 << 20, rounds: int = 6, points_per_start: int = 256, shrink: float = 0.5,
                  initial_halfwidth: Optional[float] = None, seed: int = 0, process_group=None,
-                 distributed: bool = False, method: str = "auto", iterations: int = 40):
+                 distributed: bool = False, method: str = "auto", iterations: int = 40, prune: bool = False):
         super().__init__(acquisition_function, bounds)
         if n_starts < 1 or rounds < 0 or iterations < 0:
             raise ValueError("`n_starts` must be positive and `rounds` / `iterations` non-negative.")
@@ -143,6 +143,7 @@ class MultiStartOptimizer(Optimizer):
             raise ValueError("`method` must be 'auto', 'gradient' or 'cloud'.")
         self.method = method
         self.iterations = int(iterations)
+        self.prune = bool(prune)    # branch and bound inside the global sweep (same starts; see acquisition_argmin)
         if points_per_start % 128 != 0 or points_per_start < 128:
             raise ValueError("`points_per_start` must be a positive multiple of 128.")
         self.n_starts = int(n_starts)
@@ -195,7 +196,8 @@ class MultiStartOptimizer(Optimizer):
         if s1 > s0:
             base = s0 * self.segment
             xs = _native.candidates_uniform(seed, base, (s1 - s0) * self.segment, lo, hi)
-            vals, idxs = sur.acquisition_segment_argmin(acq.kind, xs, self.segment, index_base=base, **args)
+            vals, idxs = sur.acquisition_segment_argmin(acq.kind, xs, self.segment, index_base=base, prune=self.prune,
+                                                        **args)
             starts = _native.gather_rows(xs, idxs, index_base=base)
             del xs
             method = self.method

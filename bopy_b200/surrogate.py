@@ -318,9 +318,14 @@ class B200GPSurrogate(Surrogate):
         return val.cpu().numpy(), grad.cpu().numpy()
 
     def acquisition_segment_argmin(self, kind: str, xs, seg_len: int, eta: float = 0.0, kappa: float = 2.0,
-                                   index_base: int = 0):
+                                   index_base: int = 0, prune: bool = False):
         """Per-segment fused argmin over consecutive segments of `seg_len` rows (a multiple of 128) of the device
-        tensor / array `xs`: (values (nseg,), indices (nseg,)) as device tensors.  One launch for all segments."""
+        tensor / array `xs`: (values (nseg,), indices (nseg,)) as device tensors.  One launch for all segments.
+        prune=True: branch and bound per segment (`bopy_acq_segment_argmin_pruned`), same results."""
+        if prune and len(xs) % seg_len == 0:
+            vals, idxs, self.last_prune_stats = self.native.segment_argmin_pruned(
+                self.native.candidates(xs), seg_len, kind, eta=eta, kappa=kappa, index_base=index_base)
+            return vals, idxs
         return self.native.segment_argmin(self.native.candidates(xs), seg_len, kind, eta=eta, kappa=kappa,
                                           index_base=index_base)
 

@@ -210,6 +210,14 @@ int bopy_acq_segment_argmin(bopy_gp* gp, int acq, double eta, double kappa, cons
                             int64_t seg_len, int64_t index_base, double* seg_val_out, int64_t* seg_idx_out,
                             void* stream);
 
+/* The segmented arg-min by branch and bound (opt-in; same caveat as bopy_acq_argmin_pruned): every 16th candidate of a
+ * segment is evaluated up front, their minimum is the segment's incumbent, and only candidates whose mean-only lower bound
+ * does not exceed the incumbent of THEIR segment go through the fused sweep.  Per-segment index and value equal
+ * bopy_acq_segment_argmin's bit for bit.  m must be a multiple of seg_len.  stats_out_host as above. */
+int bopy_acq_segment_argmin_pruned(bopy_gp* gp, int acq, double eta, double kappa, const double* Xs_dev, int64_t m,
+                                   int64_t seg_len, int64_t index_base, double* seg_val_out, int64_t* seg_idx_out,
+                                   int64_t* stats_out_host, void* stream);
+
 /* Local candidate clouds around S starts (S,d): out_dev (S*P, d); row s*P is the start itself, the other P-1 rows
  * are start + U(-halfwidth, halfwidth) clipped to [lowers, uppers] (counter-based, seed). */
 int bopy_candidates_around(uint64_t seed, const double* starts_dev, int64_t S, int P, int d,

@@ -25,7 +25,8 @@ def main():
         for name, acq in (("lcb", LCB(sur, kappa=2.0)), ("ei", EI(sur))):
             acq.fit(X, y)
             bounds = Bounds([Bound(0.0, 1.0)] * d)
-            for method, kw in (("cloud", dict(rounds=6)), ("gradient", dict(iterations=40))):
+            for method, kw in (("cloud", dict(rounds=6)), ("gradient", dict(iterations=40)),
+                               ("gradient", dict(iterations=40, prune=True))):
                 opt = MultiStartOptimizer(acq, bounds, n_starts=1024, n_candidates=ncand, seed=1, method=method, **kw)
                 opt.optimize()
                 torch.cuda.synchronize()
