@@ -291,12 +291,15 @@ void launch_mean_bound(const bopy_gp* gp, const double* Xs, long long m, double 
 
 // flags / partial sums / moment scratch of grad_kernel, allocated on first use (chunks of up to sm_count batches)
 int ensure_grad_buffers(bopy_gp* gp) {
-    if (gp->grad_flags != nullptr) return BOPY_OK;
+    if (gp->grad_mv != nullptr) return BOPY_OK;   // grad_mv is allocated last: its presence means all three are there
     const int gb = gp->sm_count, nb = gp->n_blocks;
     const size_t nflags = (size_t)2 * gb * nb;
-    CUDA_TRY(cudaMalloc(&gp->grad_flags, nflags * sizeof(unsigned)));
-    CUDA_TRY(cudaMemset(gp->grad_flags, 0, nflags * sizeof(unsigned)));
-    CUDA_TRY(cudaMalloc(&gp->grad_part, (size_t)gb * nb * 2 * gp->d * PROBE_MAX_NC * sizeof(double)));
+    if (gp->grad_flags == nullptr) {
+        CUDA_TRY(cudaMalloc(&gp->grad_flags, nflags * sizeof(unsigned)));
+        CUDA_TRY(cudaMemset(gp->grad_flags, 0, nflags * sizeof(unsigned)));
+    }
+    if (gp->grad_part == nullptr)
+        CUDA_TRY(cudaMalloc(&gp->grad_part, (size_t)gb * nb * 2 * gp->d * PROBE_MAX_NC * sizeof(double)));
     CUDA_TRY(cudaMalloc(&gp->grad_mv, (size_t)2 * gb * PROBE_MAX_NC * sizeof(double)));
     return BOPY_OK;
 }
