@@ -234,3 +234,17 @@ def test_theta_gradient_follows_sklearn_hyperparameter_order():
     assert theta_gradient(k, np.array([10.0, 7.0, 0.0])).tolist() == [10.0, 10.0, 7.0]
     with pytest.raises(UnsupportedKernelError):
         theta_gradient(ConstantKernel(2.0) * RBF([0.1, 0.2]), flat)            # layout mismatch
+
+
+def test_bounds_helpers():
+    from bopy_b200.bounds import unit_box
+    b = Bounds([Bound(-1.0, 2.0), Bound(10.0, 11.0)])
+    lo, hi = b.as_arrays()
+    assert lo.tolist() == [-1.0, 10.0] and hi.tolist() == [2.0, 11.0] and len(b) == 2 and b[1] == Bound(10.0, 11.0)
+    x = np.array([[0.0, 10.5], [-2.0, 10.5], [0.0, 12.0]])
+    assert b.contains(x).tolist() == [True, False, False]
+    assert np.array_equal(b.clip(x), [[0.0, 10.5], [-1.0, 10.5], [0.0, 11.0]])
+    assert b == Bounds([Bound(-1.0, 2.0), Bound(10.0, 11.0)]) and b != unit_box(2)
+    assert unit_box(3).lowers == [0.0, 0.0, 0.0] and Bound(0.0, 2.5).width == 2.5
+    with pytest.raises(ValueError, match="`lower` must be less than `upper`"):
+        Bound(float("nan"), 1.0)
