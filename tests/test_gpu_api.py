@@ -401,3 +401,25 @@ def test_one_shot_batch_from_a_device_sweep():
     rnd = OneShotBatchOptimizer(acq, bounds, base_optimizer=base, batch_size=3,
                                 strategy=OneShotBatchOptimizerRandomSamplingStrategy()).optimize()
     assert rnd.x_min.shape == (3, 2)
+
+
+def test_hartmann6_example_runs_end_to_end():
+    """BASELINE config C4 in miniature (examples/example_hartmann6.py): pruned sweeps, one-row appends of the factor,
+    a Kriging-believer batch with its truncation, the gradient multi-start."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("example_hartmann6", os.path.join(root, "examples", "example_hartmann6.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lines = []
+    result, batch, ms = mod.main(n_initial=300, n_trials=6, out=lines.append)
+    assert result.x_opt.shape == (1, 6) and len(result.trial_results) == 6
+    assert result.f_opt <= min(r.f_opt_so_far for r in [result.initial_design_result]) + 1e-12
+    assert batch.x_min.shape == (4, 6) and batch.f_min.shape == (4,)
+    assert len({tuple(np.round(x, 9)) for x in batch.x_min}) == 4          # the believer moves on after each pick
+    assert ms.x_min.shape == (1, 6) and ms.f_min[0] <= 0.0
+    text = "\n".join(lines)
+    import re
+    assert int(re.search(r"one-row appends: (\d+)", text).group(1)) >= 5       # every trial but a block-edge one
+    assert "truncations 1" in text
