@@ -248,3 +248,16 @@ def test_bounds_helpers():
     assert unit_box(3).lowers == [0.0, 0.0, 0.0] and Bound(0.0, 2.5).width == 2.5
     with pytest.raises(ValueError, match="`lower` must be less than `upper`"):
         Bound(float("nan"), 1.0)
+
+
+def test_top_k_strategy_host_rule():
+    from bopy_b200.optimizer import OneShotBatchOptimizerTopKStrategy
+    x = np.array([[0.0, 0.0], [0.01, 0.0], [0.5, 0.5], [0.52, 0.5], [1.0, 1.0], [0.2, 0.9]])
+    a = np.array([-5.0, -4.9, -4.0, -4.5, np.nan, -1.0])
+    xs, fs = OneShotBatchOptimizerTopKStrategy(min_distance=0.1).select(x, a, 3)
+    assert fs.tolist() == [-5.0, -4.5, -1.0]            # -4.9 and -4.0 sit too close to better picks; NaN never chosen
+    assert np.array_equal(xs, x[[0, 3, 5]])
+    xs, fs = OneShotBatchOptimizerTopKStrategy().select(x, a, 2)
+    assert fs.tolist() == [-5.0, -4.9]
+    xs, fs = OneShotBatchOptimizerTopKStrategy(min_distance=10.0).select(x, a, 4)
+    assert fs.tolist() == [-5.0]                        # fewer than asked for when the distance rule leaves no more
