@@ -11,13 +11,14 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int64, c_uint64,
 from .exceptions import NativeLibraryError
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libbopy_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
-OK, ERR_BAD_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_READY, ERR_NOT_POSITIVE_DEFINITE = 0, -1, -2, -3, -4, -5
+OK, ERR_BAD_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_READY, ERR_NOT_POSITIVE_DEFINITE, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
 F64, F32 = 0, 1
 KERNEL_IDS = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3}
 ACQ_IDS = {None: -1, "none": -1, "lcb": 0, "ei": 1, "poi": 2}
-PEAK_IDS = {"fp64_fma": 0, "fp32_fma": 1, "fp64_mma": 2, "tf32_mma_sync": 3}
+PEAK_IDS = {"fp64_fma": 0, "fp32_fma": 1, "fp64_mma": 2, "tf32_mma_sync": 3, "tf32_tcgen05": 4}
+NAN_POLICY_IDS = {"first": 0, "skip": 1}
 
 # name -> (restype, argtypes); mirrors include/bopy_b200.h line by line
 _SIGNATURES = {
@@ -63,6 +64,15 @@ _SIGNATURES = {
     "bopy_candidates_uniform": (c_int, [c_uint64, c_int64, c_int64, c_int, POINTER(c_double), POINTER(c_double),
                                         c_void_p, c_void_p]),
     "bopy_measure_peak": (c_int, [c_int, POINTER(c_double)]),
+    "bopy_gp_set_nan_policy": (c_int, [c_void_p, c_int]),
+    "bopy_multistart_refine": (c_int, [c_void_p, c_int, c_double, c_double, c_int64, POINTER(c_double), POINTER(c_double),
+                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bopy_topk_min_distance": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_double, POINTER(c_double), c_void_p,
+                                       c_void_p, c_void_p]),
+    "bopy_comm_unique_id": (c_int, [c_void_p, c_int64]),
+    "bopy_comm_create": (c_int, [POINTER(c_void_p), c_void_p, c_int, c_int, c_int]),
+    "bopy_comm_destroy": (None, [c_void_p]),
+    "bopy_minloc_allreduce": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "bopy_gp_launch_info": (c_int, [c_void_p, c_int64, POINTER(c_int), POINTER(c_int), POINTER(c_int64)]),
 }
 

@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libbopy_b200.so")
 SOURCES = [os.path.join(CSRC, "bopy_b200.cu")]
 HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "sweep_kernel.cuh", "aux_kernels.cuh", "fit_kernels.cuh", "probe_kernel.cuh",
-                                             "grad_kernel.cuh", "prune_kernels.cuh")] + [
+                                             "grad_kernel.cuh", "prune_kernels.cuh", "sweep_tc_kernel.cuh", "tc_common.cuh", "minloc_comm.cuh")] + [
     os.path.join(ROOT, "include", "bopy_b200.h")]
 
 NVCC_FLAGS = [
@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES + ["-ldl"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)

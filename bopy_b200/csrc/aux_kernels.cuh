@@ -2,7 +2,7 @@
 // counter-based candidate generator and the FMA/MMA peak microbenchmarks.
 #pragma once
 #include "common.cuh"
-#include "sweep_kernel.cuh"
+#include "sweep_tc_kernel.cuh"
 
 namespace bopy {
 
@@ -54,9 +54,17 @@ __global__ void pack_tiles_kernel(const double* __restrict__ L, int n, int ld, c
     unsigned char* dst = out + (E::row_base(I) + t) * (long long)TILE_BYTES;
     for (int e = threadIdx.x; e < BM * KC; e += blockDim.x) {
         const int k = e / BM, r = e - k * BM;
-        if (offdiag)
-            reinterpret_cast<typename PG::Elem*>(dst)[PG::a_index(k, r)] = static_cast<typename PG::Elem>(tmp[k][r]);
-        else
+        if (offdiag) {
+            if constexpr (std::is_same<PG, TcPolicy>::value) {
+                // tensor-core operand tile: [hi 4 KB | lo 4 KB], K-major canonical layout, both halves rounded to nearest
+                float hi, lo;
+                tc::tf32_pair(tmp[k][r], hi, lo);
+                reinterpret_cast<float*>(dst)[tc::tile_index(k, r)] = hi;
+                reinterpret_cast<float*>(dst)[tc::TF32_TILE_FLOATS + tc::tile_index(k, r)] = lo;
+            } else {
+                reinterpret_cast<typename PG::Elem*>(dst)[PG::a_index(k, r)] = static_cast<typename PG::Elem>(tmp[k][r]);
+            }
+        } else
             reinterpret_cast<typename PD::Elem*>(dst)[PD::a_index(k, r)] = static_cast<typename PD::Elem>(tmp[k][r]);
     }
 }
@@ -116,15 +124,14 @@ template <class E, int KIND>
 __global__ void cov_kernel(const typename E::TG* __restrict__ Vws, int n_pad, int n, const double* __restrict__ Xs,
                            long long m, int d, LsParam ls, double amp, double kss, double y_var, double* cov) {
     using T = typename E::TG;
-    using P = typename E::PG;   // V is published in the GEMM policy's B layout
     const long long a = (long long)blockIdx.y * blockDim.y + threadIdx.y;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= m || b >= m) return;
-    const T* Va = Vws + (a / BN) * (long long)n_pad * BN;
-    const T* Vb = Vws + (b / BN) * (long long)n_pad * BN;
+    const T* Va = Vws + (a / BN) * (long long)n_pad * BN * v_elems_per_entry<E>();
+    const T* Vb = Vws + (b / BN) * (long long)n_pad * BN * v_elems_per_entry<E>();
     const int ca = (int)(a % BN), cb = (int)(b % BN);
     double s = 0.0;
-    for (int i = 0; i < n; ++i) s = fma((double)Va[P::b_index(i, ca)], (double)Vb[P::b_index(i, cb)], s);
+    for (int i = 0; i < n; ++i) s = fma(v_value<E>(Va, i, ca), v_value<E>(Vb, i, cb), s);
     double prior = kss;
     if (a != b) {
         double d2 = 0.0;
@@ -358,6 +365,97 @@ __global__ void __launch_bounds__(256) peak_tf32_mma_kernel(float* out, int iter
 #pragma unroll
     for (int k = 0; k < 16; ++k) s += c[k][0] + c[k][1] + c[k][2] + c[k][3];
     if (s == -1.2345f) out[0] = s;
+}
+
+__global__ void fill_kernel(double* dst, long long n, double v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
+}
+
+// tcgen05.mma kind::tf32 M=128 N=128 K=8 from shared-memory operands into two tensor-memory accumulators, one CTA per SM:
+// the rate the fp32-mode engine's off-diagonal products can be issued at (its roofline denominator).
+__global__ void __launch_bounds__(128, 1) peak_tcgen05_tf32_kernel(int iters) {
+    extern __shared__ __align__(128) unsigned char psm[];
+    float* const ops = reinterpret_cast<float*>(psm);          // 2 A tiles + 2 B tiles of 4 KB
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(psm + 4 * tc::TF32_TILE_BYTES);
+    uint32_t* const slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 4 * tc::TF32_TILE_FLOATS; i += blockDim.x) ops[i] = 0.0f;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc(slot, 256);
+    fence_proxy_async();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem = *slot;
+    if (tid == 0) {
+        constexpr uint32_t idesc = tc::idesc_tf32(BM, BN, false, false);
+        const uint32_t base = smem_u32(ops);
+        const uint64_t ah = tc::smem_desc(base, tc::TILE_LBO, tc::TILE_SBO), al = tc::smem_desc(base + tc::TF32_TILE_BYTES, tc::TILE_LBO, tc::TILE_SBO);
+        const uint64_t bh = tc::smem_desc(base + 2 * tc::TF32_TILE_BYTES, tc::TILE_LBO, tc::TILE_SBO),
+                       bl = tc::smem_desc(base + 3 * tc::TF32_TILE_BYTES, tc::TILE_LBO, tc::TILE_SBO);
+        for (int it = 0; it < iters; ++it) {
+            tc::mma_tf32(tmem + 128u, al, bh, idesc, it > 0);
+            tc::mma_tf32(tmem + 128u, ah, bl, idesc, 1);
+            tc::mma_tf32(tmem, ah, bh, idesc, it > 0);
+        }
+        tc::mma_commit(bar);
+        mbar_wait(bar, 0);
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+// ---- one-shot batch selection on the device (bopy/optimizer.py:186-232, 271-276): the k best evaluations that keep a
+// minimum distance.  One pass per pick: candidates closer than min_distance to the newest pick die, the best survivor is
+// the next pick (np.argmin ordering among the living, NaN values never picked).
+__global__ void topk_pass_kernel(const double* __restrict__ x, const double* __restrict__ a, long long N, int d, LsParam scale,
+                                 double min_dist2, const long long* __restrict__ picked, int npicked, unsigned char* alive,
+                                 MinLoc* partials) {
+    __shared__ MinLoc red[32];
+    double newest[MAX_D];
+    bool have = false;
+    if (npicked > 0) {
+        const long long pi = picked[npicked - 1];
+        have = pi >= 0;
+        if (have)
+            for (int q = 0; q < d; ++q) newest[q] = x[pi * d + q];
+    }
+    MinLoc v;
+    v.val = 0.0;
+    v.idx = -1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        unsigned char al = npicked == 0 ? (unsigned char)1 : alive[i];
+        const double ai = a[i];
+        if (npicked == 0 && ai != ai) al = 0;
+        if (al && have) {
+            double d2 = 0.0;
+            for (int q = 0; q < d; ++q) {
+                const double df = (x[i * d + q] - newest[q]) / scale.v[q];
+                d2 = fma(df, df, d2);
+            }
+            if (d2 < min_dist2 || i == picked[npicked - 1]) al = 0;
+        }
+        alive[i] = al;
+        if (al) {
+            MinLoc c;
+            c.val = ai;
+            c.idx = i;
+            if (minloc_better(c, v)) v = c;
+        }
+    }
+    v = minloc_warp_reduce(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (minloc_better(red[w], v)) v = red[w];
+        partials[blockIdx.x] = v;
+    }
 }
 
 }  // namespace bopy

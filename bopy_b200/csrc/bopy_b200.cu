@@ -10,14 +10,17 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "aux_kernels.cuh"
 #include "common.cuh"
 #include "fit_kernels.cuh"
 #include "grad_kernel.cuh"
+#include "minloc_comm.cuh"
 #include "probe_kernel.cuh"
 #include "prune_kernels.cuh"
 #include "sweep_kernel.cuh"
+#include "sweep_tc_kernel.cuh"
 
 using namespace bopy;
 
@@ -38,12 +41,13 @@ int fail(int code, const char* fmt, ...) {
 #define CUDA_TRY(expr)                                                                             \
     do {                                                                                           \
         cudaError_t err__ = (expr);                                                                \
-        if (err__ != cudaSuccess)                                                                  \
+        if (err__ != cudaSuccess) {                                                                \
+            cudaGetLastError(); /* reported here: do not leave it for the next call to trip over */ \
             return fail(BOPY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__),  \
                         __FILE__, __LINE__);                                                       \
+        }                                                                                          \
     } while (0)
 
-size_t elem_size(int dtype) { return dtype == BOPY_F64 ? sizeof(double) : sizeof(float); }
 
 }  // namespace
 
@@ -60,7 +64,9 @@ struct bopy_gp {
     double amp = 1.0, noise = 0.0, y_mean = 0.0, y_std = 1.0;
     bool ready = false;
     bool fma64 = false;        // fp64 solve with the register-tiled FMA engine instead of DMMA (BOPY_B200_F64_ENGINE=fma)
-    bool fma32 = false;        // fp32 solve with register-tiled FFMA instead of 3xTF32 MMAs (BOPY_B200_F32_ENGINE=fma)
+    int f32_engine = 0;        // fp32 solve: 0 = tcgen05.mma kind::tf32 + TMEM (default), 1 = warp-level mma.sync 3xTF32
+                               // (BOPY_B200_F32_ENGINE=mma_sync), 2 = register-tiled FFMA (BOPY_B200_F32_ENGINE=fma)
+    int nan_skip = 0;          // arg-min policy for NaN acquisition values: 0 = np.argmin (first NaN wins), 1 = np.nanargmin
     // latency path (probe_kernel): used for m <= probe_max_m on fp64 handles whose block rows fit one wave of CTAs
     bool probe_capable = false;
     long long probe_max_m = 0;
@@ -97,12 +103,60 @@ template <class E, int KIND> int launch_sweep_t(SweepParams p, int grid, cudaStr
     return BOPY_OK;
 }
 
+template <int KIND> int launch_sweep_tc_t(SweepParams p, int grid, cudaStream_t st) {
+    p.tc_stages = tc_stages_for(p.d);
+    {   // tuning knobs of the accumulation scheme (defaults: sweep_tc_kernel.cuh)
+        const char* f = std::getenv("BOPY_B200_TC_FOLD");
+        const char* fl = std::getenv("BOPY_B200_TC_FLUSH");
+        const int fv = f ? std::atoi(f) : TC_FOLD_TILES, flv = fl ? std::atoi(fl) : FLUSH_BLOCKS;
+        p.tc_fold = (fv == 1 || fv == 2 || fv == 4 || fv == 8 || fv == 16) ? fv : TC_FOLD_TILES;
+        p.tc_flush = flv >= 1 ? flv : FLUSH_BLOCKS;
+        const char* pf = std::getenv("BOPY_B200_TC_PREFETCH");
+        p.tc_prefetch = pf ? std::max(0, std::atoi(pf)) : TC_PREFETCH_STAGES;
+        const char* ns = std::getenv("BOPY_B200_TC_STAGES");
+        if (ns && std::atoi(ns) >= 2 && std::atoi(ns) <= p.tc_stages) p.tc_stages = std::atoi(ns);
+    }
+    p.xrow_separate = tc_xrow_separate(p.d, p.tc_stages) ? 1 : 0;
+    const size_t smem = tc_smem_bytes(p.d, p.tc_stages);
+    CUDA_TRY(cudaFuncSetAttribute(sweep_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool prof = std::getenv("BOPY_B200_TC_PROF") != nullptr;   // development aid: per-phase cycle counters to stderr
+    if (prof) {
+        CUDA_TRY(cudaMalloc(&p.tc_prof, (size_t)grid * 16 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(p.tc_prof, 0, (size_t)grid * 16 * sizeof(long long)));
+    }
+    sweep_tc_kernel<KIND><<<grid, TC_NT_ALL, smem, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    if (prof) {
+        std::vector<long long> h((size_t)grid * 16);
+        CUDA_TRY(cudaMemcpy(h.data(), p.tc_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(p.tc_prof);
+        double a[16] = {0};
+        for (int b = 0; b < grid; ++b)
+            for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)b * 16 + k] / grid;
+        std::fprintf(stderr,
+                     "[tc_prof] cycles per CTA: compute tid0: K* %.0f | wait accfull %.0f | fold %.0f | flush %.0f | diag %.0f | publish %.0f | "
+                     "total %.0f ;  MMA warp: wait full %.0f | wait accempty %.0f | wait loempty %.0f | total %.0f  (tiles/CTA %.1f)\n",
+                     a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[8], a[9], a[10], a[11], (double)p.ntiles / grid);
+    }
+    return BOPY_OK;
+}
+
 template <class E> int launch_sweep_k(int kernel, const SweepParams& p, int grid, cudaStream_t st) {
     switch (kernel) {
         case BOPY_KERNEL_RBF: return launch_sweep_t<E, K_RBF>(p, grid, st);
         case BOPY_KERNEL_MATERN12: return launch_sweep_t<E, K_M12>(p, grid, st);
         case BOPY_KERNEL_MATERN32: return launch_sweep_t<E, K_M32>(p, grid, st);
         case BOPY_KERNEL_MATERN52: return launch_sweep_t<E, K_M52>(p, grid, st);
+    }
+    return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
+}
+
+template <> int launch_sweep_k<EngineTc>(int kernel, const SweepParams& p, int grid, cudaStream_t st) {
+    switch (kernel) {
+        case BOPY_KERNEL_RBF: return launch_sweep_tc_t<K_RBF>(p, grid, st);
+        case BOPY_KERNEL_MATERN12: return launch_sweep_tc_t<K_M12>(p, grid, st);
+        case BOPY_KERNEL_MATERN32: return launch_sweep_tc_t<K_M32>(p, grid, st);
+        case BOPY_KERNEL_MATERN52: return launch_sweep_tc_t<K_M52>(p, grid, st);
     }
     return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
 }
@@ -152,7 +206,7 @@ template <class P> int launch_cov_k(const bopy_gp* gp, const void* Vws, const do
                                     const LsParam& ls, double* cov, cudaStream_t st) {   // P: an Engine
     dim3 block(16, 16), grid((unsigned)((m + 15) / 16), (unsigned)((m + 15) / 16));
     const double kss = gp->amp + gp->noise, yv = gp->y_std * gp->y_std;
-    const typename P::TG* V = reinterpret_cast<const typename P::TG*>(Vws);
+    const typename P::TG* V = reinterpret_cast<const typename P::TG*>(Vws);   // (TG = float for every fp32 engine)
     switch (gp->kernel) {
         case BOPY_KERNEL_RBF:
             cov_kernel<P, K_RBF><<<grid, block, 0, st>>>(V, gp->n_pad, (int)gp->n, Xs, m, gp->d, ls, gp->amp, kss, yv, cov);
@@ -173,9 +227,16 @@ template <class P> int launch_cov_k(const bopy_gp* gp, const void* Vws, const do
 
 // engine selection: f64 -> DMMA warp tiles (FMA thread tiles on request, for A/B runs); f32 -> mixed engine
 template <class F> int dispatch_engine(const bopy_gp* gp, F&& f) {
-    if (gp->dtype == BOPY_F32) return gp->fma32 ? f(EngineMixedFma()) : f(EngineMixed());
+    if (gp->dtype == BOPY_F32)
+        return gp->f32_engine == 2 ? f(EngineMixedFma()) : (gp->f32_engine == 1 ? f(EngineMixed()) : f(EngineTc()));
     if (gp->fma64) return f(EngineF64Fma());
     return f(EngineF64());
+}
+
+// bytes of one V entry in the solve workspace: fp64, an fp32, or a TF32 (hi, lo) pair
+size_t v_entry_bytes(const bopy_gp* gp) {
+    if (gp->dtype == BOPY_F64) return sizeof(double);
+    return gp->f32_engine == 0 ? 2 * sizeof(float) : sizeof(float);
 }
 
 long long packed_tiles(const bopy_gp* gp) {
@@ -219,6 +280,7 @@ int launch_probe(bopy_gp* gp, const ProbePlan& pl, const double* Xs, long long m
     q.var_out = var_out;
     q.acq_out = acq_out;
     q.index_base = index_base;
+    q.nan_skip = gp->nan_skip;
     q.records = records;
     q.Mt = reinterpret_cast<const unsigned char*>(gp->Mt);
     q.flags = gp->probe_flags + 1;
@@ -385,6 +447,7 @@ int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, d
     p.var_out = var_out;
     p.acq_out = acq_out;
     p.index_base = index_base;
+    p.nan_skip = gp->nan_skip;
     const bool want_min = (min_val != nullptr || min_idx != nullptr);
     if (allow_probe && probe_applies(gp, m, slot_per_tile, tile_records)) {
         // small m: latency path, the forward substitution spread over the block rows of L (probe_kernel.cuh)
@@ -456,8 +519,8 @@ int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, 
     const char* engine = std::getenv("BOPY_B200_F64_ENGINE");
     gp->fma64 = engine != nullptr && std::strcmp(engine, "fma") == 0;
     const char* engine32 = std::getenv("BOPY_B200_F32_ENGINE");
-    gp->fma32 = engine32 != nullptr && std::strcmp(engine32, "fma") == 0;
-    const size_t es = elem_size(dtype);
+    gp->f32_engine = engine32 == nullptr ? 0 : (std::strcmp(engine32, "fma") == 0 ? 2 : (std::strcmp(engine32, "mma_sync") == 0 ? 1 : 0));
+    const size_t es = v_entry_bytes(gp);
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&gp->Lt, (size_t)packed_tiles(gp) * TILE_BYTES);
     if (e == cudaSuccess) e = cudaMalloc(&gp->Xt, (size_t)gp->n_blocks * (d + 1) * BM * sizeof(double));
@@ -1340,7 +1403,7 @@ int bopy_gp_predict_cov(bopy_gp* gp, const double* Xs_dev, int64_t m, double* me
     CUDA_TRY(cudaSetDevice(gp->device));
     const long long ntiles = (m + BN - 1) / BN;
     void* Vall = nullptr;
-    CUDA_TRY(cudaMalloc(&Vall, (size_t)ntiles * gp->n_pad * BN * elem_size(gp->dtype)));
+    CUDA_TRY(cudaMalloc(&Vall, (size_t)ntiles * gp->n_pad * BN * v_entry_bytes(gp)));
     rc = run_sweep(gp, Xs_dev, m, BOPY_ACQ_NONE, 0.0, 0.0, mean_out, nullptr, nullptr, 0, nullptr, nullptr, Vall, 1, st);
     if (rc == BOPY_OK) {
         LsParam ls;
@@ -1405,6 +1468,11 @@ int bopy_measure_peak(int what, double* tflops_out) {
             const int g2 = prop.multiProcessorCount * 4;
             peak_tf32_mma_kernel<<<g2, block>>>(reinterpret_cast<float*>(sink), iters, 1.0000001f, 1e-9f);
             flops = 2.0 * g2 * (block / 32) * (double)iters * 16 * 1024;
+        } else if (what == BOPY_PEAK_TF32_TCGEN05) {
+            const int iters = 4096;
+            const size_t smem = 4 * tc::TF32_TILE_BYTES + 64;
+            peak_tcgen05_tf32_kernel<<<prop.multiProcessorCount, 128, smem>>>(iters);
+            flops = 2.0 * prop.multiProcessorCount * (double)iters * 3 * BM * BN * 8;
         } else {
             cudaFree(sink);
             return fail(BOPY_ERR_BAD_ARG, "unknown peak id %d", what);
@@ -1423,6 +1491,144 @@ int bopy_measure_peak(int what, double* tflops_out) {
     return BOPY_OK;
 }
 
+int bopy_gp_set_nan_policy(bopy_gp* gp, int policy) {
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    if (policy != BOPY_NAN_FIRST && policy != BOPY_NAN_SKIP) return fail(BOPY_ERR_BAD_ARG, "unknown NaN policy %d", policy);
+    gp->nan_skip = policy == BOPY_NAN_SKIP ? 1 : 0;
+    return BOPY_OK;
+}
+
+int bopy_multistart_refine(bopy_gp* gp, int acq, double eta, double kappa, int64_t S, const double* lowers_host,
+                           const double* uppers_host, int iterations, double* xt_dev, double* xc_dev, double* fc_dev,
+                           double* work_dev, void* stream) {
+    int rc = check_ready(gp);
+    if (rc != BOPY_OK) return rc;
+    if (lowers_host == nullptr || uppers_host == nullptr || xt_dev == nullptr || xc_dev == nullptr || fc_dev == nullptr ||
+        work_dev == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "bopy_multistart_refine: NULL argument");
+    if (S < 1 || iterations < 0) return fail(BOPY_ERR_BAD_ARG, "need S >= 1 and iterations >= 0");
+    const int d = gp->d;
+    // work_dev: gc (S,d) | gt (S,d) | ft (S) | alpha (S)
+    double* const gc = work_dev;
+    double* const gt = gc + (size_t)S * d;
+    double* const ft = gt + (size_t)S * d;
+    double* const alpha = ft + S;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(gp->device));
+    fill_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(alpha, S, 1.0);
+    CUDA_TRY(cudaGetLastError());
+    for (int k = 0; k <= iterations; ++k) {
+        rc = bopy_acq_value_and_grad(gp, acq, eta, kappa, xt_dev, S, ft, gt, nullptr, nullptr, stream);
+        if (rc != BOPY_OK) return rc;
+        rc = bopy_multistart_step(S, d, lowers_host, uppers_host, xc_dev, fc_dev, gc, xt_dev, ft, gt, alpha, k == 0 ? 1 : 0, stream);
+        if (rc != BOPY_OK) return rc;
+    }
+    return BOPY_OK;
+}
+
+int bopy_topk_min_distance(const double* x_dev, const double* a_dev, int64_t N, int d, int k, double min_distance,
+                           const double* scale_host, int64_t* idx_out_dev, double* val_out_dev, void* stream) {
+    if (x_dev == nullptr || a_dev == nullptr || idx_out_dev == nullptr || val_out_dev == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "bopy_topk_min_distance: NULL argument");
+    if (N < 1 || d < 1 || d > MAX_D || k < 1) return fail(BOPY_ERR_BAD_ARG, "need N, k >= 1 and 1 <= d <= %d", MAX_D);
+    if (!(min_distance >= 0.0)) return fail(BOPY_ERR_BAD_ARG, "min_distance must be >= 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LsParam scale;
+    for (int q = 0; q < MAX_D; ++q) scale.v[q] = (scale_host != nullptr && q < d) ? scale_host[q] : 1.0;
+    for (int q = 0; q < d; ++q)
+        if (!(scale.v[q] > 0.0)) return fail(BOPY_ERR_BAD_ARG, "scale[%d] must be positive", q);
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<long long>((N + 255) / 256, (long long)sms * 8);
+    unsigned char* scratch = nullptr;
+    const size_t alive_bytes = ((size_t)N + 255) / 256 * 256;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), alive_bytes + (size_t)grid * sizeof(MinLoc), st));
+    MinLoc* const partials = reinterpret_cast<MinLoc*>(scratch + alive_bytes);
+    for (int c = 0; c < k; ++c) {
+        topk_pass_kernel<<<grid, 256, 0, st>>>(x_dev, a_dev, N, d, scale, min_distance * min_distance,
+                                               reinterpret_cast<const long long*>(idx_out_dev), c, scratch, partials);
+        minloc_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, val_out_dev + c, reinterpret_cast<long long*>(idx_out_dev) + c);
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return fail(BOPY_ERR_CUDA, "bopy_topk_min_distance launch failed: %s", cudaGetErrorString(e));
+    return BOPY_OK;
+}
+
+// ---- the sharded sweep's single exchange step -----------------------------------------------------------------------
+
+struct bopy_comm {
+    NcclApi::comm_t nccl = nullptr;
+    int world = 1, rank = 0, device = 0;
+    MinLoc* send = nullptr;   // this rank's record
+    MinLoc* recv = nullptr;   // [world]
+};
+
+int bopy_comm_unique_id(void* id_out, int64_t id_bytes) {
+    if (id_out == nullptr || id_bytes < (int64_t)sizeof(NcclApi::unique_id))
+        return fail(BOPY_ERR_BAD_ARG, "id_out must hold %d bytes", (int)sizeof(NcclApi::unique_id));
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(BOPY_ERR_UNSUPPORTED, "NCCL is not available: %s", api.error.c_str());
+    NcclApi::unique_id id;
+    const int r = api.GetUniqueId(&id);
+    if (r != 0) return fail(BOPY_ERR_NCCL, "ncclGetUniqueId failed: %s", api.GetErrorString(r));
+    std::memcpy(id_out, &id, sizeof(id));
+    return BOPY_OK;
+}
+
+int bopy_comm_create(bopy_comm** out, const void* unique_id, int world_size, int rank, int device) {
+    if (out == nullptr || unique_id == nullptr) return fail(BOPY_ERR_BAD_ARG, "out / unique_id is NULL");
+    *out = nullptr;
+    if (world_size < 1 || rank < 0 || rank >= world_size) return fail(BOPY_ERR_BAD_ARG, "bad rank %d of %d", rank, world_size);
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(BOPY_ERR_UNSUPPORTED, "NCCL is not available: %s", api.error.c_str());
+    CUDA_TRY(cudaSetDevice(device));
+    bopy_comm* c = new (std::nothrow) bopy_comm();
+    if (c == nullptr) return fail(BOPY_ERR_BAD_ARG, "out of host memory");
+    c->world = world_size;
+    c->rank = rank;
+    c->device = device;
+    NcclApi::unique_id id;
+    std::memcpy(&id, unique_id, sizeof(id));
+    const int r = api.CommInitRank(&c->nccl, world_size, id, rank);
+    if (r != 0) {
+        delete c;
+        return fail(BOPY_ERR_NCCL, "ncclCommInitRank failed: %s", api.GetErrorString(r));
+    }
+    cudaError_t e = cudaMalloc(&c->send, sizeof(MinLoc));
+    if (e == cudaSuccess) e = cudaMalloc(&c->recv, (size_t)world_size * sizeof(MinLoc));
+    if (e != cudaSuccess) {
+        bopy_comm_destroy(c);
+        return fail(BOPY_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return BOPY_OK;
+}
+
+void bopy_comm_destroy(bopy_comm* comm) {
+    if (comm == nullptr) return;
+    cudaSetDevice(comm->device);
+    if (comm->nccl != nullptr) nccl_api().CommDestroy(comm->nccl);
+    cudaFree(comm->send);
+    cudaFree(comm->recv);
+    delete comm;
+}
+
+int bopy_minloc_allreduce(bopy_comm* comm, double* val_dev, int64_t* idx_dev, int nan_policy, void* stream) {
+    if (comm == nullptr || val_dev == nullptr || idx_dev == nullptr) return fail(BOPY_ERR_BAD_ARG, "comm / val_dev / idx_dev is NULL");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(comm->device));
+    minloc_pack_kernel<<<1, 1, 0, st>>>(val_dev, reinterpret_cast<const long long*>(idx_dev), comm->send);
+    CUDA_TRY(cudaGetLastError());
+    const int r = nccl_api().AllGather(comm->send, comm->recv, sizeof(MinLoc), NCCL_INT8, comm->nccl, st);
+    if (r != 0) return fail(BOPY_ERR_NCCL, "ncclAllGather failed: %s", nccl_api().GetErrorString(r));
+    minloc_gathered_kernel<<<1, 32, 0, st>>>(comm->recv, comm->world, nan_policy == BOPY_NAN_SKIP ? 1 : 0, val_dev,
+                                              reinterpret_cast<long long*>(idx_dev));
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
 int bopy_gp_launch_info(const bopy_gp* gp, int64_t m, int* grid_out, int* launches_out, int64_t* workspace_bytes_out) {
     if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
     const long long ntiles = (m + BN - 1) / BN;
@@ -1432,7 +1638,7 @@ int bopy_gp_launch_info(const bopy_gp* gp, int64_t m, int* grid_out, int* launch
         *grid_out = (int)std::min<long long>(ntiles, gp->sm_count);
     }
     if (launches_out) *launches_out = 2;  // sweep_kernel + minloc_finalize_kernel (argmin); 1 without argmin
-    if (workspace_bytes_out) *workspace_bytes_out = (int64_t)gp->sm_count * gp->n_pad * BN * (int64_t)elem_size(gp->dtype);
+    if (workspace_bytes_out) *workspace_bytes_out = (int64_t)gp->sm_count * gp->n_pad * BN * (int64_t)v_entry_bytes(gp);
     return BOPY_OK;
 }
 

@@ -57,6 +57,7 @@ struct ProbeParams {
     double* part;              // [nbatch][n_blocks][2][NC]: mean / sum v^2 partials of block row I
     unsigned* ticket;          // role counter (monotonic over launches)
     unsigned ticket_base, epoch;
+    int nan_skip;              // 1: NaN acquisition values never win the arg-min (np.nanargmin)
     int keep_v;                // 1: the last block row of V is stored too (the gradient's backward solve reads all of V)
     const double* rhs;         // optional (n,): solve L v = rhs for candidate 0 instead of a kernel column (alpha_ solve)
     long long* trace;          // optional [n_blocks][8] %globaltimer stamps of batch 0 (tools/probe_trace.py), or nullptr
@@ -406,8 +407,10 @@ __global__ void __launch_bounds__(PROBE_NT, 1) probe_kernel(const ProbeParams p)
                     if (p.acq != A_NONE) {
                         const double av = acquisition_value(p.acq, mean, var, p.eta, p.kappa);
                         if (p.acq_out) p.acq_out[gcand] = av;
-                        mine.val = av;
-                        mine.idx = p.index_base + gcand;
+                        if (!(p.nan_skip && av != av)) {
+                            mine.val = av;
+                            mine.idx = p.index_base + gcand;
+                        }
                     }
                 }
             }

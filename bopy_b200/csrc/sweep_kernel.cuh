@@ -21,6 +21,8 @@
 //   DmmaPolicy      fp64, mma.sync.m8n8k4.f64 (DMMA), warp tile 32 rows x 64 candidates, XOR-swizzled tiles
 //   FmaPolicy<T>    register-tiled FMA, thread tile 8 x 8 (used for the fp32 solve)
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace bopy {
@@ -50,6 +52,12 @@ struct SweepParams {
     MinLoc* partials;   // [gridDim.x] or nullptr when no arg-min is wanted
     MinLoc* tile_records;  // [ntiles] per-tile arg-min records (for segmented arg-min) or nullptr
     int xrow_separate;  // 1: the X/l block row has its own shared-memory buffer and is prefetched one row ahead
+    int tc_fold;        // tensor-core engine: operand tiles (8 columns of L each) per hi.hi accumulation chain (divides 16)
+    int tc_flush;       // tensor-core engine: 128-column blocks of L per fp32 running sum before it is folded into fp64
+    long long* tc_prof; // tensor-core engine: optional [gridDim.x][16] cycle counters per phase (BOPY_B200_TC_PROF=1), else nullptr
+    int tc_prefetch;    // tensor-core engine: stages the L2 prefetch of the V tiles runs ahead of their bulk loads
+    int tc_stages;      // tensor-core engine: depth of the (L_IJ, V_J) ring (4, or 3 / 2 when d is large)
+    int nan_skip;       // 1: candidates whose acquisition value is NaN never win the arg-min (np.nanargmin); 0: np.argmin (first NaN wins)
 };
 
 // exp(x) for x <= 0, branch-free so that the 64 evaluations a thread makes per block row interleave instead of
@@ -676,8 +684,10 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
                 if (p.acq != A_NONE) {
                     const double a = acquisition_value(p.acq, mean, var, p.eta, p.kappa);
                     if (p.acq_out) p.acq_out[gc] = a;
-                    mine.val = a;
-                    mine.idx = p.index_base + gc;
+                    if (!(p.nan_skip && a != a)) {
+                        mine.val = a;
+                        mine.idx = p.index_base + gc;
+                    }
                 }
             }
         }

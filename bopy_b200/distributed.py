@@ -42,8 +42,92 @@ def reduce_minloc(records: Sequence[Tuple[float, int]]) -> Tuple[float, int]:
     return best
 
 
-def all_reduce_minloc(value: float, index: int, group=None, device=None) -> Tuple[float, int]:
-    """Min-loc over all ranks of `group` (default group if None).  Works with nccl and gloo."""
+_COMMS = {}      # id(process group) -> NativeComm (one NCCL communicator of the library per group)
+
+
+class NativeComm:
+    """The library's own communicator for the min-loc exchange (`bopy_comm_*`, include/bopy_b200.h): an ncclComm_t
+    created from a unique id that rank 0 draws and torch.distributed ships to the other ranks once.  The exchange itself
+    (`bopy_minloc_allreduce`) is an ncclAllGather of one 16-byte record per rank plus a one-warp kernel on the sweep's
+    stream: the winner lands in the caller's device buffers without any host synchronisation."""
+
+    ID_BYTES = 128
+
+    def __init__(self, group=None, device=None):
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _native
+        self.lib = _native.load()
+        self.device = _native.resolve_device(device)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        uid = ctypes.create_string_buffer(self.ID_BYTES)
+        if self.rank == 0:
+            _native.check(self.lib.bopy_comm_unique_id(uid, self.ID_BYTES), "bopy_comm_unique_id")
+        t = torch.frombuffer(bytearray(uid.raw), dtype=torch.uint8).clone()
+        if dist.get_backend(group) != "gloo":
+            t = t.to(self.device)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(t, src=src, group=group)
+        raw = bytes(t.cpu().numpy().tobytes())
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.bopy_comm_create(ctypes.byref(handle), raw, self.world, self.rank, self.device.index),
+                          "bopy_comm_create")
+        self._handle = handle
+
+    def minloc_(self, val_dev, idx_dev, nan_policy="first"):
+        """In place: (val_dev (1,) fp64, idx_dev (1,) int64) device tensors become the winner over all ranks."""
+        import torch
+
+        from . import _native
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.bopy_minloc_allreduce(self._handle, _native._ptr(val_dev), _native._ptr(idx_dev),
+                                                         _native.NAN_POLICY_IDS[nan_policy], _native._stream(self.device)),
+                          "bopy_minloc_allreduce")
+        return val_dev, idx_dev
+
+    def close(self):
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            try:
+                self.lib.bopy_comm_destroy(handle)
+            except Exception:
+                pass
+
+    def __del__(self):
+        self.close()
+
+
+def native_comm(group=None, device=None):
+    """The NativeComm of `group` (created on first use; collective), or None when the group is not an NCCL group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_backend(group) != "nccl":
+        return None
+    key = id(group) if group is not None else 0
+    if key not in _COMMS:
+        _COMMS[key] = NativeComm(group, device)
+    return _COMMS[key]
+
+
+def all_reduce_minloc_device(val_dev, idx_dev, group=None, nan_policy="first"):
+    """Min-loc over all ranks on DEVICE buffers (val (1,) fp64, idx (1,) int64), in place, no host synchronisation:
+    `bopy_minloc_allreduce` on NCCL groups.  On a gloo group (CPU tests) it falls back to the host exchange."""
+    comm = native_comm(group, val_dev.device)
+    if comm is not None:
+        return comm.minloc_(val_dev, idx_dev, nan_policy)
+    v, i = all_reduce_minloc(float(val_dev.item()), int(idx_dev.item()), group=group, nan_policy=nan_policy)
+    val_dev.fill_(v)
+    idx_dev.fill_(i)
+    return val_dev, idx_dev
+
+
+def all_reduce_minloc(value: float, index: int, group=None, device=None, nan_policy: str = "first") -> Tuple[float, int]:
+    """Min-loc over all ranks of `group` (default group if None), host values in and out.  NCCL groups go through the
+    library's collective (`bopy_minloc_allreduce`, one D2H of the winner); gloo groups (CPU tests) through
+    torch.distributed.all_gather and the same ordering restated in `reduce_minloc`."""
     import torch
     import torch.distributed as dist
 
@@ -51,6 +135,14 @@ def all_reduce_minloc(value: float, index: int, group=None, device=None) -> Tupl
         return float(value), int(index)
     world = dist.get_world_size(group)
     backend = dist.get_backend(group)
+    if backend == "nccl":
+        from . import _native
+        dev = _native.resolve_device(device)
+        rec_v = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+        rec_i = torch.tensor([int(index)], dtype=torch.int64, device=dev)
+        native_comm(group, dev).minloc_(rec_v, rec_i, nan_policy)
+        both = torch.stack([rec_v.view(torch.int64)[0], rec_i[0]]).cpu().numpy()     # ONE device-to-host copy
+        return float(both[:1].view(np.float64)[0]), int(both[1])
     dev = torch.device("cpu") if backend == "gloo" else (device or torch.device("cuda", torch.cuda.current_device()))
     # one 16-byte record per rank: the value's bit pattern and the index, both as int64 (NaN-safe)
     rec = torch.tensor([np.float64(value).view(np.int64).item(), int(index)], dtype=torch.int64, device=dev)
@@ -58,6 +150,8 @@ def all_reduce_minloc(value: float, index: int, group=None, device=None) -> Tupl
     dist.all_gather(gathered, rec, group=group)
     rows = torch.stack(gathered).cpu().numpy()
     records = [(float(np.int64(r[0]).view(np.float64)), int(r[1])) for r in rows]
+    if nan_policy == "skip":
+        records = [(v, (-1 if v != v else i)) for v, i in records]
     return reduce_minloc(records)
 
 

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define BOPY_B200_ABI_VERSION 1
+#define BOPY_B200_ABI_VERSION 2
 
 typedef struct bopy_gp bopy_gp;
 
@@ -52,7 +52,8 @@ enum bopy_status {
     BOPY_ERR_CUDA = -2,
     BOPY_ERR_UNSUPPORTED = -3,
     BOPY_ERR_NOT_READY = -4,
-    BOPY_ERR_NOT_POSITIVE_DEFINITE = -5
+    BOPY_ERR_NOT_POSITIVE_DEFINITE = -5,
+    BOPY_ERR_NCCL = -6
 };
 
 enum bopy_dtype { BOPY_F64 = 0, BOPY_F32 = 1 };
@@ -64,7 +65,21 @@ enum bopy_kernel { BOPY_KERNEL_RBF = 0, BOPY_KERNEL_MATERN12 = 1, BOPY_KERNEL_MA
 enum bopy_acq { BOPY_ACQ_NONE = -1, BOPY_ACQ_LCB = 0, BOPY_ACQ_EI = 1, BOPY_ACQ_POI = 2 };
 
 /* what bopy_measure_peak times */
-enum bopy_peak { BOPY_PEAK_FP64_FMA = 0, BOPY_PEAK_FP32_FMA = 1, BOPY_PEAK_FP64_MMA = 2, BOPY_PEAK_TF32_MMA_SYNC = 3 };
+enum bopy_peak {
+    BOPY_PEAK_FP64_FMA = 0,
+    BOPY_PEAK_FP32_FMA = 1,
+    BOPY_PEAK_FP64_MMA = 2,
+    BOPY_PEAK_TF32_MMA_SYNC = 3,
+    BOPY_PEAK_TF32_TCGEN05 = 4 /* tcgen05.mma kind::tf32 M=128 N=128 K=8, operands in shared memory, accumulators in TMEM */
+};
+
+/* what the arg-min does with NaN acquisition values (posterior variance rounded to <= 0: sqrt / scipy's scale > 0 rule) */
+enum bopy_nan_policy {
+    BOPY_NAN_FIRST = 0, /* np.argmin: the first NaN wins -- what `np.argmin(acq(X*))` over the reference's values returns */
+    BOPY_NAN_SKIP = 1   /* np.nanargmin: a NaN never wins; index -1 if every value is NaN (what an optimiser wants) */
+};
+
+typedef struct bopy_comm bopy_comm;
 
 int bopy_abi_version(void);
 const char* bopy_last_error(void);
@@ -258,6 +273,41 @@ int bopy_candidates_uniform(uint64_t seed, int64_t index_base, int64_t m, int d,
 /* Register-resident FMA / MMA microbenchmark on the current device: the roofline denominator of the
  * solve.  Synchronous.  Writes TFLOP/s (2 flops per FMA). */
 int bopy_measure_peak(int what, double* tflops_out);
+
+/* Arg-min policy of this handle for NaN acquisition values (default BOPY_NAN_FIRST = np.argmin, the parity rule).
+ * Applies to bopy_gp_posterior_acq / bopy_acq_argmin / bopy_acq_segment_argmin and the sweeps inside the pruned variants. */
+int bopy_gp_set_nan_policy(bopy_gp* gp, int policy);
+
+/* The whole gradient refinement of the batched multi-start behind Optimizer._optimize (bopy/optimizer.py:65-67) in ONE
+ * call: iterations + 1 rounds of (bopy_acq_value_and_grad at the trial points, bopy_multistart_step), queued back to back
+ * on the stream with no host round trip.  xt_dev (S,d): the starts on entry, scratch afterwards; xc_dev (S,d) / fc_dev (S,):
+ * the refined points and their acquisition values; work_dev: 2*S*d + 2*S doubles of scratch. */
+int bopy_multistart_refine(bopy_gp* gp, int acq, double eta, double kappa, int64_t S, const double* lowers_host,
+                           const double* uppers_host, int iterations, double* xt_dev, double* xc_dev, double* fc_dev,
+                           double* work_dev, void* stream);
+
+/* One-shot batch selection on the device-resident evaluation log of a sweep (bopy/optimizer.py:186-232, 271-276; the
+ * log itself: bopy/acquisition.py:200-242): the k best evaluations a_dev (N,) at points x_dev (N,d) such that any two
+ * picks are at least min_distance apart after dividing coordinate j by scale_host[j] (NULL: 1).  Greedy, best first,
+ * np.argmin's tie rule, NaN values never picked.  idx_out_dev / val_out_dev (k,): picks in order; -1 / 0.0 where fewer
+ * than k evaluations qualify. */
+int bopy_topk_min_distance(const double* x_dev, const double* a_dev, int64_t N, int d, int k, double min_distance,
+                           const double* scale_host, int64_t* idx_out_dev, double* val_out_dev, void* stream);
+
+/* The sharded sweep's ONE exchange step: candidates are cut into contiguous index ranges, one
+ * process per GPU runs bopy_acq_argmin with index_base = range start, and the per-rank 16-byte (value, global index)
+ * records are reduced to the global winner.  A bopy_comm wraps an ncclComm_t (NCCL is bound at run time: the libnccl.so.2
+ * already loaded into the process, else the system one; BOPY_ERR_UNSUPPORTED if there is none):
+ *   rank 0:      bopy_comm_unique_id(id, 128)           -> ship the 128 bytes to every rank (any out-of-band channel)
+ *   every rank:  bopy_comm_create(&comm, id, world, rank, device)          (collective: ncclCommInitRank)
+ *   per sweep:   bopy_minloc_allreduce(comm, val_dev, idx_dev, policy, stream)
+ * bopy_minloc_allreduce replaces *val_dev / *idx_dev on every rank by the winner under np.argmin's ordering (NaN first
+ * -- or never, with BOPY_NAN_SKIP --, then the smaller value, then the lower index): ncclAllGather of the records on
+ * `stream` + a one-warp kernel; no host synchronisation. */
+int bopy_comm_unique_id(void* id_out, int64_t id_bytes);
+int bopy_comm_create(bopy_comm** out, const void* unique_id, int world_size, int rank, int device);
+void bopy_comm_destroy(bopy_comm* comm);
+int bopy_minloc_allreduce(bopy_comm* comm, double* val_dev, int64_t* idx_dev, int nan_policy, void* stream);
 
 /* Introspection used by bench.py / tests: thread blocks one sweep launches and kernels per sweep. */
 int bopy_gp_launch_info(const bopy_gp* gp, int64_t m, int* grid_out, int* launches_out, int64_t* workspace_bytes_out);
