@@ -407,6 +407,30 @@ class NativeGP:
                   "bopy_gp_predict_cov")
         return mean, cov
 
+    def set_nan_policy(self, policy):
+        """'first': np.argmin's rule (a NaN acquisition value wins, the first one) -- the parity rule and the default;
+        'skip': np.nanargmin's (a NaN never wins; index -1 when every value is NaN) -- what the optimisers use."""
+        if getattr(self, "_nan_policy", "first") != policy:
+            check(self.lib.bopy_gp_set_nan_policy(self._handle, NAN_POLICY_IDS[policy]), "bopy_gp_set_nan_policy")
+            self._nan_policy = policy
+
+    def multistart_refine(self, starts, acq, lowers, uppers, iterations, eta=0.0, kappa=2.0):
+        """All `iterations` + 1 rounds of (value + gradient at the trial points, projected-gradient step) in ONE native call
+        (`bopy_multistart_refine`): returns (x (S, d), f (S,)) device tensors.  fp64 handles only."""
+        torch = require_cuda()
+        S, d = starts.shape
+        xt = starts.clone()
+        xc = torch.empty_like(xt)
+        fc = torch.empty(S, dtype=torch.float64, device=self.device)
+        work = torch.empty(2 * S * d + 2 * S, dtype=torch.float64, device=self.device)
+        lo = (c_double * d)(*[float(v) for v in lowers])
+        hi = (c_double * d)(*[float(v) for v in uppers])
+        with torch.cuda.device(self.device):
+            check(self.lib.bopy_multistart_refine(self._handle, ACQ_IDS[acq], float(eta), float(kappa), S, lo, hi,
+                                                  int(iterations), _ptr(xt), _ptr(xc), _ptr(fc), _ptr(work),
+                                                  _stream(self.device)), "bopy_multistart_refine")
+        return xc, fc
+
     def launch_info(self, m):
         g, l, w = c_int(), c_int(), c_int64()
         check(self.lib.bopy_gp_launch_info(self._handle, int(m), byref(g), byref(l), byref(w)), "bopy_gp_launch_info")
@@ -481,6 +505,22 @@ def gather_rows(xs, idx, index_base=0):
         check(lib.bopy_gather_rows(_ptr(xs), xs.shape[0], d, _ptr(idx), S, int(index_base), _ptr(out),
                                    _stream(xs.device)), "bopy_gather_rows")
     return out
+
+
+def topk_min_distance(x, a, k, min_distance=0.0, scale=None):
+    """Indices (k,) int64 and values (k,) of the k best evaluations a (N,) at points x (N, d) that keep `min_distance`
+    from each other (coordinates divided by `scale`), greedy best first, on the device (`bopy_topk_min_distance`).
+    Picks that do not exist (fewer than k qualify) have index -1."""
+    torch = require_cuda()
+    lib = load()
+    N, d = x.shape
+    idx = torch.empty(int(k), dtype=torch.int64, device=x.device)
+    val = torch.empty(int(k), dtype=torch.float64, device=x.device)
+    sc = None if scale is None else (c_double * d)(*[float(v) for v in scale])
+    with torch.cuda.device(x.device):
+        check(lib.bopy_topk_min_distance(_ptr(x), _ptr(a), N, d, int(k), float(min_distance), sc, _ptr(idx), _ptr(val),
+                                         _stream(x.device)), "bopy_topk_min_distance")
+    return idx, val
 
 
 def measure_peak(what):

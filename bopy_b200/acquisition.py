@@ -78,17 +78,28 @@ class _MomentAcquisition(AcquisitionFunction):
             raise TypeError("value_and_grad needs a B200GPSurrogate")
         return sur.acquisition_value_and_grad(self.kind, x, **self.native_args())
 
-    def argmin(self, x, index_base: int = 0, prune: bool = False) -> Tuple[int, float]:
-        """Index and value of the smallest acquisition value over the rows of `x` (fused on the device;
-        np.argmin's rules: first minimum, first NaN wins).  prune=True: branch and bound on a B200 surrogate (see
-        B200GPSurrogate.acquisition_argmin)."""
+    def argmin(self, x, index_base: int = 0, prune: bool = False, nan_policy: str = "first",
+               on_device: bool = False):
+        """Index and value of the smallest acquisition value over the rows of `x` (fused on the device).
+        nan_policy='first': np.argmin's rules (first minimum, first NaN wins) -- what np.argmin over the reference's
+        values gives; 'skip': np.nanargmin's (a NaN -- posterior variance rounded to <= 0 -- never wins; index -1 if
+        all values are NaN): what the optimisers of this package use.  prune=True: branch and bound on a B200 surrogate
+        (see B200GPSurrogate.acquisition_argmin).  on_device=True (B200 surrogates): (index, value) as (1,) device
+        tensors, nothing synchronised."""
         self._validate_ok_for_predicting(x)
         sur = self.surrogate
         if hasattr(sur, "acquisition_argmin"):
-            return sur.acquisition_argmin(self.kind, x, index_base=index_base, prune=prune, **self.native_args())
+            return sur.acquisition_argmin(self.kind, x, index_base=index_base, prune=prune, nan_policy=nan_policy,
+                                          on_device=on_device, **self.native_args())
         mean_d, var_d = self._foreign_moments(x if isinstance(x, np.ndarray) else x.cpu().numpy())
-        _, minv, mini = _native.acquisition_from_moments(self.kind, mean_d, var_d, want_min=True,
-                                                         index_base=index_base, **self.native_args())
+        out, minv, mini = _native.acquisition_from_moments(self.kind, mean_d, var_d, want_min=True,
+                                                           index_base=index_base, **self.native_args())
+        if nan_policy == "skip":
+            v = out.cpu().numpy()
+            if np.isnan(v).all():
+                return -1, 0.0
+            i = int(np.nanargmin(v))
+            return index_base + i, float(v[i])
         return int(mini.item()), float(minv.item())
 
 
@@ -159,8 +170,8 @@ class KriggingBeliever(SequentialBatchAcquisitionFunction):
     def _f(self, x: np.ndarray) -> np.ndarray:
         return self.base_acquisition(x)
 
-    def argmin(self, x, index_base: int = 0, prune: bool = False):
-        return self.base_acquisition.argmin(x, index_base=index_base, prune=prune)
+    def argmin(self, x, index_base: int = 0, prune: bool = False, **kwargs):
+        return self.base_acquisition.argmin(x, index_base=index_base, prune=prune, **kwargs)
 
     def start_batch(self) -> None:
         self.n_data = len(self.surrogate.x)
@@ -196,22 +207,30 @@ class OneShotBatchAcquisitionFunction(AcquisitionFunction):
         self.a_xs.append(np.array(values))
         return values
 
-    def argmin(self, x, index_base: int = 0, prune: bool = False) -> Tuple[int, float]:
+    def argmin(self, x, index_base: int = 0, prune: bool = False, nan_policy: str = "first", on_device: bool = False):
         """The sweep optimisers' entry: one fused device pass evaluates ALL rows of `x` (numpy or device tensor),
-        which are logged like any other evaluation; the arg-min follows np.argmin's rules.  (`prune` is ignored: a
-        one-shot strategy chooses from every evaluation, so none may be skipped.)"""
+        which are logged like any other evaluation; the arg-min follows `nan_policy` (see _MomentAcquisition.argmin).
+        (`prune` is ignored: a one-shot strategy chooses from every evaluation, so none may be skipped.)"""
         self._validate_ok_for_predicting(x)
         base = self.base_acquisition
         sur = base.surrogate
         if hasattr(sur, "native") and hasattr(base, "kind"):
             xs = sur.native.candidates(x)
-            out = sur.native.sweep(xs, acq=base.kind, want_acq=True, want_min=True, index_base=index_base,
-                                   **base.native_args())
+            sur.native.set_nan_policy(nan_policy)
+            try:
+                out = sur.native.sweep(xs, acq=base.kind, want_acq=True, want_min=True, index_base=index_base,
+                                       **base.native_args())
+            finally:
+                sur.native.set_nan_policy("first")
             self.xs.append(xs)                 # stay on the device until a strategy asks for them
             self.a_xs.append(out["acq"])
+            if on_device:
+                return out["min_idx"], out["min_val"]
             return int(out["min_idx"].item()), float(out["min_val"].item())
         values = self._f(x if isinstance(x, np.ndarray) else x.cpu().numpy())
-        i = int(np.argmin(values))
+        if nan_policy == "skip" and np.isnan(values).all():
+            return -1, 0.0
+        i = int(np.nanargmin(values)) if nan_policy == "skip" else int(np.argmin(values))
         return index_base + i, float(values[i])
 
     def start_optimization(self) -> None:

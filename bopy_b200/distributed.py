@@ -155,8 +155,14 @@ def all_reduce_minloc(value: float, index: int, group=None, device=None, nan_pol
     return reduce_minloc(records)
 
 
-def sharded_argmin(acquisition, seed: int, lowers, uppers, m: int, group=None, incumbent=None, prune: bool = False):
-    """Each rank sweeps its slice of the m counter-based candidates; returns (x (d,), value) on every rank."""
+def sharded_argmin(acquisition, seed: int, lowers, uppers, m: int, group=None, incumbent=None, prune: bool = False,
+                   nan_policy: str = "skip"):
+    """Each rank sweeps its slice of the m counter-based candidates; returns (x (d,), value) on every rank.
+
+    On NCCL groups nothing touches the host between the sweep and the winner: the rank's (value, index) stay on the
+    device, `bopy_minloc_allreduce` (ncclAllGather of 16-byte records + a one-warp kernel on the sweep's stream) replaces
+    them by the global winner, and ONE device-to-host copy fetches it.  `nan_policy` as in `AcquisitionFunction.argmin`
+    (default 'skip': an optimiser never proposes a NaN point; falls back to 'first' if every candidate is NaN)."""
     import torch
     import torch.distributed as dist
 
@@ -164,17 +170,41 @@ def sharded_argmin(acquisition, seed: int, lowers, uppers, m: int, group=None, i
 
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(group), dist.get_world_size(group)
+        host_exchange = dist.get_backend(group) == "gloo"
     else:
-        rank, world = 0, 1
+        rank, world, host_exchange = 0, 1, False
     start, stop = shard_range(m, rank, world)
-    value, index = 0.0, -1
-    if stop > start:
-        xs = _native.candidates_uniform(seed, start, stop - start, lowers, uppers)
-        if incumbent is not None and start == 0:
-            xs[0] = torch.as_tensor(incumbent, dtype=torch.float64, device=xs.device)
-        index, value = (acquisition.argmin(xs, index_base=start, prune=True) if prune
-                        else acquisition.argmin(xs, index_base=start))
-    value, index = all_reduce_minloc(value, index, group=group)
+    if host_exchange:
+        # CPU groups (the gloo tests; the device pieces are stand-ins there): host records, torch all_gather
+        value, index = 0.0, -1
+        if stop > start:
+            xs = _native.candidates_uniform(seed, start, stop - start, lowers, uppers)
+            if incumbent is not None and start == 0:
+                xs[0] = torch.as_tensor(incumbent, dtype=torch.float64, device=xs.device)
+            index, value = acquisition.argmin(xs, index_base=start, prune=prune, nan_policy=nan_policy)
+        value, index = all_reduce_minloc(value, index, group=group, nan_policy=nan_policy)
+    else:
+        dev = _native.resolve_device(getattr(getattr(acquisition, "surrogate", None), "device", None))
+        if stop > start:
+            xs = _native.candidates_uniform(seed, start, stop - start, lowers, uppers, device=dev)
+            if incumbent is not None and start == 0:
+                xs[0] = torch.as_tensor(incumbent, dtype=torch.float64, device=xs.device)
+            got = acquisition.argmin(xs, index_base=start, prune=prune, nan_policy=nan_policy, on_device=True)
+            if isinstance(got[0], torch.Tensor):
+                idx_d, val_d = got
+            else:                   # an acquisition without a device arg-min (foreign surrogate): host values
+                idx_d = torch.tensor([int(got[0])], dtype=torch.int64, device=dev)
+                val_d = torch.tensor([float(got[1])], dtype=torch.float64, device=dev)
+        else:
+            idx_d = torch.full((1,), -1, dtype=torch.int64, device=dev)
+            val_d = torch.zeros(1, dtype=torch.float64, device=dev)
+        if world > 1:
+            all_reduce_minloc_device(val_d, idx_d, group=group, nan_policy=nan_policy)
+        both = torch.stack([idx_d[0], val_d.view(torch.int64)[0]]).cpu().numpy()          # the one device-to-host copy
+        index, value = int(both[0]), float(both[1:].view(np.float64)[0])
+    if index < 0 and nan_policy == "skip":     # every candidate of every rank was NaN: np.argmin's answer
+        return sharded_argmin(acquisition, seed, lowers, uppers, m, group=group, incumbent=incumbent, prune=False,
+                              nan_policy="first")
     if incumbent is not None and index == 0:
         x = np.asarray(incumbent, dtype=np.float64)
     else:

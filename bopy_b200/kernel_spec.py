@@ -41,7 +41,9 @@ def flatten_sklearn_kernel(kernel) -> FlatKernel:
                 raise UnsupportedKernelError("products of two stationary kernels are not supported")
             base = node
         else:
-            raise UnsupportedKernelError(f"unsupported kernel component: {node!r}")
+            raise UnsupportedKernelError(
+                f"unsupported kernel component {node!r}: the B200 path implements Constant x RBF / Matern (+ White) "
+                f"and has no CPU fallback")
 
     if isinstance(kernel, sk.Sum):
         terms = (kernel.k1, kernel.k2)
@@ -57,8 +59,11 @@ def flatten_sklearn_kernel(kernel) -> FlatKernel:
         raise UnsupportedKernelError(f"no RBF / Matern component in {kernel!r}")
     if isinstance(base, sk.Matern):
         nu = float(base.nu)
+        if nu == float("inf"):            # scikit-learn evaluates Matern(nu=inf) with the RBF formula ($SK/kernels.py:1730-1731)
+            ls = np.atleast_1d(np.asarray(base.length_scale, dtype=np.float64)).copy()
+            return FlatKernel(kernel="rbf", length_scale=ls, amplitude=amplitude, noise_level=noise)
         if nu not in _MATERN_IDS:
-            raise UnsupportedKernelError(f"Matern nu={nu} is not supported (0.5, 1.5, 2.5 are)")
+            raise UnsupportedKernelError(f"Matern nu={nu} is not supported on the device (0.5, 1.5, 2.5 and inf are)")
         name = _MATERN_IDS[nu]
     else:
         name = "rbf"

@@ -94,7 +94,11 @@ class CandidateSweepOptimizer(Optimizer):
         xs = _native.candidates_uniform(seed, 0, m, lowers, uppers)
         if incumbent is not None:
             xs[0] = torch.as_tensor(incumbent, dtype=torch.float64, device=xs.device)
-        idx, val = acq.argmin(xs, prune=True) if self.prune else acq.argmin(xs)
+        # an optimiser never proposes a candidate whose acquisition value is NaN (posterior variance rounded to <= 0 on
+        # top of a training point): np.nanargmin's rule; np.argmin's (first NaN) only if every candidate is NaN
+        idx, val = acq.argmin(xs, prune=self.prune, nan_policy="skip")
+        if idx < 0:
+            idx, val = acq.argmin(xs, nan_policy="first")
         return xs[idx].cpu().numpy(), val
 
     def _optimize(self) -> Tuple[np.ndarray, np.ndarray]:
@@ -197,23 +201,30 @@ class MultiStartOptimizer(Optimizer):
             base = s0 * self.segment
             xs = _native.candidates_uniform(seed, base, (s1 - s0) * self.segment, lo, hi)
             vals, idxs = sur.acquisition_segment_argmin(acq.kind, xs, self.segment, index_base=base, prune=self.prune,
-                                                        **args)
+                                                        nan_policy="skip", **args)
+            # a segment whose candidates are all NaN has no arg-min (index -1): start from its first candidate
+            seg_first = base + torch.arange(idxs.shape[0], dtype=torch.int64, device=idxs.device) * self.segment
+            idxs = torch.where(idxs < 0, seg_first, idxs)
             starts = _native.gather_rows(xs, idxs, index_base=base)
             del xs
             method = self.method
             if method == "auto":
                 method = "gradient" if getattr(sur, "supports_gradient", lambda: False)() else "cloud"
             if method == "gradient":
-                # all starts advance together: one value+gradient call and one step kernel per iteration
+                # all starts advance together, every iteration = one value+gradient pass and one step kernel; the whole
+                # loop is ONE native call (bopy_multistart_refine): its launches queue back to back, no host round trips
                 native = sur.native
-                xt = starts.clone()
-                xc, gc = torch.empty_like(xt), torch.empty_like(xt)
-                fc = torch.empty(xt.shape[0], dtype=torch.float64, device=xt.device)
-                alpha = torch.ones_like(fc)
-                for k in range(self.iterations + 1):
-                    ft, gt, _, _ = native.value_and_grad(xt, acq.kind, **args)
-                    _native.multistart_step(lo, hi, xc, fc, gc, xt, ft, gt, alpha, first=(k == 0))
-                starts, vals = xc, fc
+                if hasattr(native, "multistart_refine"):
+                    starts, vals = native.multistart_refine(starts, acq.kind, lo, hi, self.iterations, **args)
+                else:       # a surrogate that only offers value_and_grad: the same loop, one call pair per iteration
+                    xt = starts.clone()
+                    xc, gc = torch.empty_like(xt), torch.empty_like(xt)
+                    fc = torch.empty(xt.shape[0], dtype=torch.float64, device=xt.device)
+                    alpha = torch.ones_like(fc)
+                    for k in range(self.iterations + 1):
+                        ft, gt, _, _ = native.value_and_grad(xt, acq.kind, **args)
+                        _native.multistart_step(lo, hi, xc, fc, gc, xt, ft, gt, alpha, first=(k == 0))
+                    starts, vals = xc, fc
             else:
                 # a start owns ~1/n_starts of the box: begin with a cloud of that size
                 frac = self.initial_halfwidth if self.initial_halfwidth is not None else \
@@ -222,12 +233,14 @@ class MultiStartOptimizer(Optimizer):
                 P = self.points_per_start
                 for k in range(self.rounds):
                     cloud = _native.candidates_around(seed + 1 + k + 1000 * rank, starts, P, half, lo, hi)
-                    vals, idxs = sur.acquisition_segment_argmin(acq.kind, cloud, P, **args)
+                    vals, idxs = sur.acquisition_segment_argmin(acq.kind, cloud, P, nan_policy="skip", **args)
+                    own = torch.arange(idxs.shape[0], dtype=torch.int64, device=idxs.device) * P    # row s*P is start s
+                    idxs = torch.where(idxs < 0, own, idxs)
                     starts = _native.gather_rows(cloud, idxs)
                     half = half * self.shrink
             v = vals.cpu().numpy()
             self._last = (starts.cpu().numpy(), v)
-            j = int(np.argmin(v))
+            j = int(np.argmin(v)) if np.isnan(v).all() else int(np.nanargmin(v))     # a NaN start never wins
             value, index, x_best = float(v[j]), s0 + j, self._last[0][j]
         if world > 1:
             value, index = all_reduce_minloc(value, index, group=self.process_group)
@@ -348,30 +361,15 @@ class OneShotBatchOptimizerTopKStrategy(OneShotBatchOptimizerStrategy):
         return x[chosen], a_x[chosen]
 
     def select_on_device(self, x, a_x, batch_size):
-        """Same rule on device tensors: candidates are examined best first in chunks of the sorted order."""
+        """Same rule on the device-resident log (x (N, d), a_x (N,) device tensors): `bopy_topk_min_distance` -- one pass
+        over the log per pick (candidates too close to the newest pick die, the best survivor is next), no host round
+        trip until the batch itself is copied back."""
         import torch
-        scale = torch.ones(x.shape[1], dtype=torch.float64, device=x.device) if self.scale is None else \
-            torch.as_tensor(np.asarray(self.scale, dtype=np.float64), device=x.device)
-        vals = torch.where(torch.isnan(a_x), torch.full_like(a_x, float("inf")), a_x)
-        order = torch.argsort(vals, stable=True)
-        chosen = []
-        chunk = max(64, 16 * batch_size)
-        for s0 in range(0, len(order), chunk):
-            idx = order[s0:s0 + chunk]
-            pts = x[idx] / scale
-            for r in range(len(idx)):
-                if not torch.isfinite(vals[idx[r]]):
-                    break
-                if chosen:
-                    kept = x[torch.stack(chosen)] / scale
-                    if float(torch.min(torch.linalg.norm(kept - pts[r], dim=1))) < self.min_distance:
-                        continue
-                chosen.append(idx[r])
-                if len(chosen) == batch_size:
-                    sel = torch.stack(chosen)
-                    return x[sel].cpu().numpy(), a_x[sel].cpu().numpy()
-        sel = torch.stack(chosen) if chosen else torch.zeros(0, dtype=torch.int64, device=x.device)
-        return x[sel].cpu().numpy(), a_x[sel].cpu().numpy()
+        x = x.contiguous()
+        a_x = a_x.contiguous()
+        idx, _ = _native.topk_min_distance(x, a_x, batch_size, self.min_distance, self.scale)
+        idx = idx[idx >= 0]
+        return x[idx].cpu().numpy(), a_x[idx].cpu().numpy()
 
 
 class OneShotBatchOptimizerKDPPSamplingStrategy(OneShotBatchOptimizerStrategy):

@@ -291,20 +291,33 @@ class B200GPSurrogate(Surrogate):
         return out["acq"].cpu().numpy()
 
     def acquisition_argmin(self, kind: str, x, eta: float = 0.0, kappa: float = 2.0, index_base: int = 0,
-                           prune: bool = False):
+                           prune: bool = False, nan_policy: str = "first", on_device: bool = False):
         """Fused posterior -> acquisition -> argmin over the rows of x (numpy or device tensor).
 
-        Returns (index, value) with np.argmin's rules (first minimum; first NaN wins).
+        Returns (index, value).  nan_policy='first': np.argmin's rules (first minimum; a NaN value -- posterior variance
+        rounded to <= 0 -- wins, the first one): what `np.argmin(acq(X*))` over the reference's values returns, and the
+        parity rule.  nan_policy='skip': np.nanargmin's (a NaN never wins; index -1 if everything is NaN): what an
+        optimiser wants, so that it never proposes a point on top of a training point because its variance cancelled.
         prune=True: branch and bound (`bopy_acq_argmin_pruned`): a lower bound from the posterior mean discards most
-        candidates before the full sweep; same index and value, except that candidates with a NaN acquisition (posterior
-        variance rounded to <= 0) may be skipped.  `last_prune_stats` holds how many candidates were fully evaluated."""
-        if prune:
-            minv, mini, self.last_prune_stats = self.native.argmin_pruned(self.native.candidates(x), kind, eta=eta,
-                                                                          kappa=kappa, index_base=index_base)
-            return int(mini.item()), float(minv.item())
-        out = self.native.sweep(self.native.candidates(x), acq=kind, eta=eta, kappa=kappa, want_min=True,
-                                index_base=index_base)
-        return int(out["min_idx"].item()), float(out["min_val"].item())
+        candidates before the full sweep; same index and value, except that candidates with a NaN acquisition may be
+        skipped (with nan_policy='skip' the two routes agree).  `last_prune_stats` holds how many were fully evaluated.
+        on_device=True: (index, value) stay on the device as (1,) tensors (no synchronisation)."""
+        self.native.set_nan_policy(nan_policy)
+        try:
+            if prune:
+                minv, mini, self.last_prune_stats = self.native.argmin_pruned(self.native.candidates(x), kind, eta=eta,
+                                                                              kappa=kappa, index_base=index_base)
+            else:
+                out = self.native.sweep(self.native.candidates(x), acq=kind, eta=eta, kappa=kappa, want_min=True,
+                                        index_base=index_base)
+                minv, mini = out["min_val"], out["min_idx"]
+        finally:
+            self.native.set_nan_policy("first")
+        if on_device:
+            return mini, minv
+        import torch
+        both = torch.stack([mini[0], minv.view(torch.int64)[0]]).cpu().numpy()       # one device-to-host copy
+        return int(both[0]), float(both[1:].view(np.float64)[0])
 
 
     def supports_gradient(self) -> bool:
@@ -318,16 +331,21 @@ class B200GPSurrogate(Surrogate):
         return val.cpu().numpy(), grad.cpu().numpy()
 
     def acquisition_segment_argmin(self, kind: str, xs, seg_len: int, eta: float = 0.0, kappa: float = 2.0,
-                                   index_base: int = 0, prune: bool = False):
+                                   index_base: int = 0, prune: bool = False, nan_policy: str = "first"):
         """Per-segment fused argmin over consecutive segments of `seg_len` rows (a multiple of 128) of the device
         tensor / array `xs`: (values (nseg,), indices (nseg,)) as device tensors.  One launch for all segments.
-        prune=True: branch and bound per segment (`bopy_acq_segment_argmin_pruned`), same results."""
-        if prune and len(xs) % seg_len == 0:
-            vals, idxs, self.last_prune_stats = self.native.segment_argmin_pruned(
-                self.native.candidates(xs), seg_len, kind, eta=eta, kappa=kappa, index_base=index_base)
-            return vals, idxs
-        return self.native.segment_argmin(self.native.candidates(xs), seg_len, kind, eta=eta, kappa=kappa,
-                                          index_base=index_base)
+        prune=True: branch and bound per segment (`bopy_acq_segment_argmin_pruned`), same results.
+        nan_policy: as in `acquisition_argmin` (a segment of NaNs only has index -1 under 'skip')."""
+        self.native.set_nan_policy(nan_policy)
+        try:
+            if prune and len(xs) % seg_len == 0:
+                vals, idxs, self.last_prune_stats = self.native.segment_argmin_pruned(
+                    self.native.candidates(xs), seg_len, kind, eta=eta, kappa=kappa, index_base=index_base)
+                return vals, idxs
+            return self.native.segment_argmin(self.native.candidates(xs), seg_len, kind, eta=eta, kappa=kappa,
+                                              index_base=index_base)
+        finally:
+            self.native.set_nan_policy("first")
 
 
 class GPyGPSurrogate(B200GPSurrogate):
@@ -390,5 +408,49 @@ class GPyGPSurrogate(B200GPSurrogate):
         self.kernel_spec = spec
 
 
-# Drop-in name: code written against the reference keeps working and runs on the B200.
-ScipyGPSurrogate = B200GPSurrogate
+class ScipyGPSurrogate(B200GPSurrogate):
+    """The reference's class name (bopy/surrogate.py:72-91), same constructor argument: a scikit-learn
+    `GaussianProcessRegressor`.  What differs from the reference, and is reported instead of silently approximated:
+
+    * kernels: Constant x {RBF, Matern nu in 0.5 / 1.5 / 2.5 / inf} (+ White), isotropic or ARD.  Anything else
+      (RationalQuadratic, DotProduct, ExpSineSquared, sums / products of two stationary kernels) raises
+      `UnsupportedKernelError` at `fit` -- there is no CPU route behind this class (the reference's own
+      `gp.predict(return_cov=True)` is one `pip install bopy` away for such kernels);
+    * one target column, a CUDA device;
+    * after a fit that ran on the device the scikit-learn object holds `X_train_`, `alpha_`, `kernel_` and the
+      normalisation as its own fit would, and `L_` is fetched from the device the first time it is read (so
+      `gp.predict(..., return_std / return_cov=True)` on the wrapped object keeps working)."""
+
+    def _fit_on_device(self, x, y):
+        super()._fit_on_device(x, y)
+        _attach_lazy_factor(self)
+
+    def _try_append(self, X, yn, y_mean, y_std, spec, kernel_):
+        done = super()._try_append(X, yn, y_mean, y_std, spec, kernel_)
+        if done:
+            self.gp.__dict__.pop("L_", None)       # stale: re-fetched on next read
+        return done
+
+
+def _attach_lazy_factor(sur):
+    """Give the wrapped scikit-learn object an `L_` that is downloaded from the device on first read."""
+    gp = sur.gp
+    cls = type(gp)
+    if not getattr(cls, "_bopy_b200_lazy_factor", False):
+        def L_(self):
+            owner = self.__dict__.get("_bopy_b200_owner")
+            if owner is None:
+                raise AttributeError("L_")
+            val = owner.export_factor()
+            self.__dict__["L_"] = val
+            return val
+        # a non-data descriptor: an instance attribute `L_` (set by a host fit, or cached above) takes precedence
+        class _Lazy:
+            def __get__(self, obj, objtype=None):
+                if obj is None:
+                    return self
+                return L_(obj)
+        lazy_cls = type(cls.__name__, (cls,), {"L_": _Lazy(), "_bopy_b200_lazy_factor": True, "__module__": cls.__module__})
+        gp.__class__ = lazy_cls
+    gp.__dict__.pop("L_", None)
+    gp.__dict__["_bopy_b200_owner"] = sur

@@ -71,7 +71,7 @@ def test_no_cpu_fallback_without_cuda():
 
 
 def test_drop_in_names_and_constructors():
-    assert ScipyGPSurrogate is B200GPSurrogate and issubclass(B200GPSurrogate, Surrogate)
+    assert issubclass(ScipyGPSurrogate, B200GPSurrogate) and issubclass(B200GPSurrogate, Surrogate)
     sur = make_surrogate()
     assert LCB(sur).kappa == 2.0 and LCB(sur, kappa=0.5).kappa == 0.5
     assert EI(sur)._eta == np.inf and POI(sur)._eta == np.inf

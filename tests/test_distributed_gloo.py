@@ -34,7 +34,7 @@ def test_minloc_ordering_is_np_argmin():
 class FakeAcquisition:
     """argmin over candidate rows with the numpy oracle of a toy acquisition (a(x) = |x - 0.3|_1)."""
 
-    def argmin(self, xs, index_base=0):
+    def argmin(self, xs, index_base=0, **kwargs):
         v = np.abs(xs.numpy() - 0.3).sum(1)
         i = int(np.argmin(v))
         return index_base + i, float(v[i])
