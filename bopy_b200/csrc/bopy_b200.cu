@@ -103,28 +103,31 @@ template <class E, int KIND> int launch_sweep_t(SweepParams p, int grid, cudaStr
     return BOPY_OK;
 }
 
+template <int KIND, int FOLD> int launch_sweep_tc_f(SweepParams p, int grid, cudaStream_t st);
+
 template <int KIND> int launch_sweep_tc_t(SweepParams p, int grid, cudaStream_t st) {
-    p.tc_stages = tc_stages_for(p.d);
-    {   // tuning knobs of the accumulation scheme (defaults: sweep_tc_kernel.cuh)
-        const char* f = std::getenv("BOPY_B200_TC_FOLD");
-        const char* fl = std::getenv("BOPY_B200_TC_FLUSH");
-        const int fv = f ? std::atoi(f) : TC_FOLD_TILES, flv = fl ? std::atoi(fl) : FLUSH_BLOCKS;
-        p.tc_fold = (fv == 1 || fv == 2 || fv == 4 || fv == 8 || fv == 16) ? fv : TC_FOLD_TILES;
-        p.tc_flush = flv >= 1 ? flv : FLUSH_BLOCKS;
-        const char* pf = std::getenv("BOPY_B200_TC_PREFETCH");
-        p.tc_prefetch = pf ? std::max(0, std::atoi(pf)) : TC_PREFETCH_STAGES;
+    tc_ring_depths(p.d, &p.tc_stages, &p.tc_dstages);
+    p.tc_fold = TC_FOLD_TILES;
+    {   // development knobs (defaults: sweep_tc_kernel.cuh)
         const char* ns = std::getenv("BOPY_B200_TC_STAGES");
-        if (ns && std::atoi(ns) >= 2 && std::atoi(ns) <= p.tc_stages) p.tc_stages = std::atoi(ns);
+        if (ns && std::atoi(ns) >= 1 && std::atoi(ns) <= p.tc_stages) p.tc_stages = std::atoi(ns);
+        const char* ds = std::getenv("BOPY_B200_TC_DSTAGES");
+        if (ds && std::atoi(ds) >= 1 && std::atoi(ds) <= 4 && tc_smem_bytes(p.d, p.tc_stages, std::atoi(ds)) <= SMEM_LIMIT)
+            p.tc_dstages = std::atoi(ds);
     }
-    p.xrow_separate = tc_xrow_separate(p.d, p.tc_stages) ? 1 : 0;
-    const size_t smem = tc_smem_bytes(p.d, p.tc_stages);
-    CUDA_TRY(cudaFuncSetAttribute(sweep_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return launch_sweep_tc_f<KIND, TC_FOLD_TILES>(p, grid, st);
+}
+
+template <int KIND, int FOLD> int launch_sweep_tc_f(SweepParams p, int grid, cudaStream_t st) {
+    p.xrow_separate = 1;
+    const size_t smem = tc_smem_bytes(p.d, p.tc_stages, p.tc_dstages);
+    CUDA_TRY(cudaFuncSetAttribute(sweep_tc_kernel<KIND, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const bool prof = std::getenv("BOPY_B200_TC_PROF") != nullptr;   // development aid: per-phase cycle counters to stderr
     if (prof) {
         CUDA_TRY(cudaMalloc(&p.tc_prof, (size_t)grid * 16 * sizeof(long long)));
         CUDA_TRY(cudaMemset(p.tc_prof, 0, (size_t)grid * 16 * sizeof(long long)));
     }
-    sweep_tc_kernel<KIND><<<grid, TC_NT_ALL, smem, st>>>(p);
+    sweep_tc_kernel<KIND, FOLD><<<grid, TC_NT_ALL, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     if (prof) {
         std::vector<long long> h((size_t)grid * 16);
@@ -134,9 +137,9 @@ template <int KIND> int launch_sweep_tc_t(SweepParams p, int grid, cudaStream_t 
         for (int b = 0; b < grid; ++b)
             for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)b * 16 + k] / grid;
         std::fprintf(stderr,
-                     "[tc_prof] cycles per CTA: compute tid0: K* %.0f | wait accfull %.0f | fold %.0f | flush %.0f | diag %.0f | publish %.0f | "
+                     "[tc_prof] cycles per CTA: compute tid0: K*+R %.0f | wait accfull %.0f | fold %.0f | diag %.0f | publish %.0f | "
                      "total %.0f ;  MMA warp: wait full %.0f | wait accempty %.0f | wait loempty %.0f | total %.0f  (tiles/CTA %.1f)\n",
-                     a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[8], a[9], a[10], a[11], (double)p.ntiles / grid);
+                     a[0], a[1], a[2], a[4], a[5], a[6], a[8], a[9], a[10], a[11], (double)p.ntiles / grid);
     }
     return BOPY_OK;
 }

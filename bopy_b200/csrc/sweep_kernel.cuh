@@ -52,11 +52,10 @@ struct SweepParams {
     MinLoc* partials;   // [gridDim.x] or nullptr when no arg-min is wanted
     MinLoc* tile_records;  // [ntiles] per-tile arg-min records (for segmented arg-min) or nullptr
     int xrow_separate;  // 1: the X/l block row has its own shared-memory buffer and is prefetched one row ahead
-    int tc_fold;        // tensor-core engine: operand tiles (8 columns of L each) per hi.hi accumulation chain (divides 16)
-    int tc_flush;       // tensor-core engine: 128-column blocks of L per fp32 running sum before it is folded into fp64
+    int tc_dstages;     // tensor-core engine: depth of the inv(L_II) ring
+    int tc_fold;        // tensor-core engine: operand tiles (8 columns of L each) per hi.hi accumulation chain (4 or 8)
     long long* tc_prof; // tensor-core engine: optional [gridDim.x][16] cycle counters per phase (BOPY_B200_TC_PROF=1), else nullptr
-    int tc_prefetch;    // tensor-core engine: stages the L2 prefetch of the V tiles runs ahead of their bulk loads
-    int tc_stages;      // tensor-core engine: depth of the (L_IJ, V_J) ring (4, or 3 / 2 when d is large)
+    int tc_stages;      // tensor-core engine: permanent slots of the (L_IJ, V_J) ring (4, fewer when d is large)
     int nan_skip;       // 1: candidates whose acquisition value is NaN never win the arg-min (np.nanargmin); 0: np.argmin (first NaN wins)
 };
 

@@ -7,13 +7,17 @@ fp64 path (north star: posterior mean/var within 1e-9 relative):
   cancelling sum of n terms alpha_i k_i of size up to |alpha|_max, and var = prior - sum v^2 cancels to
   ~alpha_reg * prior at training points, where the reference's own two formulations (full-cov gemm vs
   diag einsum) already differ by ~1e-12 * prior.
-fp32 mode (north star: 1e-4).  Only L_IJ and V are stored/multiplied in fp32; K*, the mean, the residual
-accumulation across 128-column blocks, the diagonal solve and sum v^2 are fp64.  What remains is the first-order
-sensitivity of sum v^2 to rounding L and V to fp32, S = 2 eps32 |w|^T |L| |v| with w = K^-1 k* (1e-6..4e-6 of the
-prior on the BASELINE configs):
+fp32 mode (north star: 1e-4).  Only L_IJ and V are stored (as TF32 pairs, 22 bits) and multiplied at fp32 grade on the
+tensor cores; K*, the mean, the diagonal solve and sum v^2 are fp64.  What remains is the first-order sensitivity of
+sum v^2 to rounding L and V and to the tensor core's truncating fp32 accumulation (measured 9e-7..1e-6 of the prior on
+the BASELINE configs C4 / C5, profiles/r02/f32_error_histogram.txt):
     |mean - mean_ref| : as fp64
-    |var  - var_ref | <= 1e-4 * max(|var_ref|, 1e-1 * prior_var)
-  i.e. 1e-4 relative wherever the posterior variance is at least a tenth of the prior, 1e-5 * prior below that.
+    |var  - var_ref | <= 1e-4 * max(|var_ref|, 1e-2 * prior_var)
+  i.e. 1e-4 relative wherever the posterior variance is at least a hundredth of the prior (SURVEY.md section 7's own
+  estimate of where fp32 can deliver that), 1e-6 * prior below.  Two fixtures are too ill-conditioned for that floor in
+  ANY fp32-grade arithmetic and keep 1e-1 (they are listed, not hidden): c3_branin_n256 (length scale 3 on 256 points in a
+  15 x 15 box, alpha 1e-6: posterior variances down to 1e-6 of the prior, cond(K) ~ 1e9) and ragged_n333_d4_opt
+  (optimised hyper-parameters, cond(K) ~ 1e8).  DESIGN.md section 5.
 Arg-min: index identical, or a *stated tie*: the reference's own acquisition values at the two indices
 differ by no more than the acquisition's error bound implied by the var/mean tolerances above
 (tie_tol, relative to the spread of the reference acquisition values).
@@ -22,8 +26,10 @@ import numpy as np
 
 TOL = {
     "f64": dict(mean_rtol=1e-9, mean_atol=1e-9, var_rtol=1e-9, var_atol=1e-11, var_floor=0.0, tie=1e-9),
-    "f32": dict(mean_rtol=1e-9, mean_atol=1e-9, var_rtol=1e-4, var_atol=0.0, var_floor=1e-1, tie=1e-4),
+    "f32": dict(mean_rtol=1e-9, mean_atol=1e-9, var_rtol=1e-4, var_atol=0.0, var_floor=1e-2, tie=1e-4),
 }
+# fixtures whose Gram matrix is too ill-conditioned for the 1e-2 floor in fp32-grade arithmetic (see the docstring)
+F32_VAR_FLOOR_OVERRIDE = {"c3_branin_n256": 1e-1, "ragged_n333_d4_opt": 1e-1}
 
 
 def prior_var(state):
@@ -37,11 +43,12 @@ def check_mean(mean, ref, state, dtype):
     return err, bound
 
 
-def check_var(var, ref, state, dtype):
+def check_var(var, ref, state, dtype, name=None):
     t = TOL[dtype]
     pv = prior_var(state)
     err = np.abs(var - ref)
-    bound = t["var_rtol"] * np.maximum(np.abs(ref), t["var_floor"] * pv) + t["var_atol"] * pv
+    floor = F32_VAR_FLOOR_OVERRIDE.get(name, t["var_floor"]) if dtype == "f32" else t["var_floor"]
+    bound = t["var_rtol"] * np.maximum(np.abs(ref), floor * pv) + t["var_atol"] * pv
     return err, bound
 
 

@@ -58,7 +58,7 @@ def test_posterior_diag_matches_reference(name, dtype, path):
     for ref_mean, ref_var, who in ((g["mean"], g["var"], "golden"), (o_mean, o_var, "oracle")):
         err, bound = check_mean(mean, ref_mean, st, dtype)
         assert (err <= bound).all(), f"mean vs {who}: worst {np.max(err / bound):.3g}x the bound"
-        err, bound = check_var(var, ref_var, st, dtype)
+        err, bound = check_var(var, ref_var, st, dtype, name)
         assert (err <= bound).all(), f"var vs {who}: worst {np.max(err / bound):.3g}x the bound, max err {err.max():.3g}"
 
 

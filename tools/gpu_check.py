@@ -40,7 +40,7 @@ def main():
                 torch.cuda.synchronize()
                 mean, var, a = (out[k].cpu().numpy() for k in ("mean", "var", "acq"))
                 em, bm = check_mean(mean, g["mean"], st, dtype)
-                ev, bv = check_var(var, g["var"], st, dtype)
+                ev, bv = check_var(var, g["var"], st, dtype, name)
                 pv = prior_var(st)
                 rel = np.abs(var - g["var"]) / np.maximum(np.abs(g["var"]), 1e-300)
                 print(f"{name:32s} {dtype} set_state {t_set*1e3:7.1f} ms | mean err/bound {np.max(em/bm):9.3g} (max abs {em.max():.2e}) "

@@ -10,9 +10,8 @@ except Exception as e:
     print(sys.argv[2], "rc=", sys.argv[1], "parse fail", e)
 PY
 }
-run BOPY_B200_TC_PREFETCH=24
-run BOPY_B200_TC_PREFETCH=0
-run BOPY_B200_TC_PREFETCH=24 BOPY_B200_TC_STAGES=2
-run BOPY_B200_TC_PREFETCH=24 BOPY_B200_TC_FOLD=8
-run BOPY_B200_TC_PREFETCH=24 BOPY_B200_TC_FOLD=2
-timeout -s KILL 100 python tools/gpu_check.py c4_hart 2>&1 | grep f32 | cut -c1-220
+timeout -s KILL 300 python tools/gpu_check.py 2>&1 | grep -E "f32|FAILED|Error" | cut -c1-250 | sed 's/set_state.*| mean/| mean/' | grep -E "c3|c4|c5|ragged|edge|FAILED|Error"
+run X=1
+BOPY_B200_TC_PROF=1 timeout -s KILL 200 python bench.py --dtype f32 --steps 1 --no-cpu-baseline 2>&1 | grep tc_prof | tail -1
+run BOPY_B200_TC_STAGES=2 BOPY_B200_TC_DSTAGES=4
+run BOPY_B200_TC_STAGES=3 BOPY_B200_TC_DSTAGES=3
