@@ -54,7 +54,8 @@ def test_smoke_entry_point():
 def test_bench_default_line_small():
     """bench.py end to end on a reduced candidate count: every key of the contract is present."""
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3",
-                          "--candidates", "65536", "--cpu-budget", "1"], capture_output=True, text=True, timeout=900)
+                          "--candidates", "65536", "--c5-candidates", "32768", "--cpu-budget", "1"], capture_output=True,
+                         text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -63,3 +64,10 @@ def test_bench_default_line_small():
     assert line["cpu_baseline"] is not None and line["cpu_baseline"]["value"] > 0
     assert line["roofline"]["frac"] > 0 and line["gpu_launches"] > 0
     assert line["argmin"]["index"] == line["argmin"]["e2e_index"]
+    # every BASELINE config is in the line, on its own inputs, with a green parity spot-check against the golden vectors
+    for key in ("C1", "C3", "C4_f32", "C5"):
+        cfg = line["configs"][key]
+        assert "error" not in cfg, cfg
+        assert cfg["value"] > 0 and cfg["roofline"]["frac"] > 0 and cfg["parity"]["ok"], (key, cfg.get("parity"))
+    assert line["configs"]["C5"]["multistart_1024"]["f_min"] < 0
+    assert set(line["strong_scaling"]) == {"C4", "C3"} and all("error" not in v for v in line["strong_scaling"].values())
