@@ -19,6 +19,7 @@
 #include "minloc_comm.cuh"
 #include "probe_kernel.cuh"
 #include "prune_kernels.cuh"
+#include "small_kernel.cuh"
 #include "sweep_kernel.cuh"
 #include "sweep_tc_kernel.cuh"
 
@@ -66,6 +67,7 @@ struct bopy_gp {
     bool fma64 = false;        // fp64 solve with the register-tiled FMA engine instead of DMMA (BOPY_B200_F64_ENGINE=fma)
     int f32_engine = 0;        // fp32 solve: 0 = tcgen05.mma kind::tf32 + TMEM (default), 1 = warp-level mma.sync 3xTF32
                                // (BOPY_B200_F32_ENGINE=mma_sync), 2 = register-tiled FFMA (BOPY_B200_F32_ENGINE=fma)
+    bool small_n = true;       // n <= 32 on fp64 handles: thread-per-candidate kernel (BOPY_B200_SMALL_N=0 switches it off)
     int nan_skip = 0;          // arg-min policy for NaN acquisition values: 0 = np.argmin (first NaN wins), 1 = np.nanargmin
     // latency path (probe_kernel): used for m <= probe_max_m on fp64 handles whose block rows fit one wave of CTAs
     bool probe_capable = false;
@@ -252,6 +254,27 @@ int check_ready(const bopy_gp* gp) {
     if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
     if (!gp->ready) return fail(BOPY_ERR_NOT_READY, "bopy_gp_set_state has not been called on this handle");
     return BOPY_OK;
+}
+
+// n <= 32 on an fp64 handle (and no V export): the thread-per-candidate kernel serves every m
+bool small_applies(const bopy_gp* gp, int slot_per_tile) {
+    return gp->small_n && gp->dtype == BOPY_F64 && !gp->fma64 && gp->n <= SMALL_N_MAX && slot_per_tile == 0;
+}
+
+template <int NP> int launch_small_k(int kernel, const SmallParams& q, int grid, cudaStream_t st) {
+    switch (kernel) {
+        case BOPY_KERNEL_RBF: small_n_kernel<NP, K_RBF><<<grid, SMALL_NT, 0, st>>>(q); break;
+        case BOPY_KERNEL_MATERN12: small_n_kernel<NP, K_M12><<<grid, SMALL_NT, 0, st>>>(q); break;
+        case BOPY_KERNEL_MATERN32: small_n_kernel<NP, K_M32><<<grid, SMALL_NT, 0, st>>>(q); break;
+        case BOPY_KERNEL_MATERN52: small_n_kernel<NP, K_M52><<<grid, SMALL_NT, 0, st>>>(q); break;
+        default: return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
+int small_grid(const bopy_gp* gp, long long m) {
+    return (int)std::min<long long>((m + SMALL_NT - 1) / SMALL_NT, (long long)gp->sm_count * SMALL_CTAS_PER_SM);
 }
 
 // one launch of the latency path (probe_kernel) over m candidates laid out by `pl`
@@ -452,6 +475,42 @@ int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, d
     p.index_base = index_base;
     p.nan_skip = gp->nan_skip;
     const bool want_min = (min_val != nullptr || min_idx != nullptr);
+    if (small_applies(gp, slot_per_tile)) {
+        SmallParams q;
+        std::memset(&q, 0, sizeof(q));
+        q.Xt = gp->Xt;
+        q.Dinv = gp->Dinv;
+        q.Xs = Xs;
+        q.m = m;
+        q.ntiles = (m + SMALL_NT - 1) / SMALL_NT;
+        q.n = (int)gp->n;
+        q.d = gp->d;
+        for (int k = 0; k < gp->d; ++k) q.ls[k] = gp->ls[k];
+        q.amp = gp->amp;
+        q.kss = p.kss;
+        q.y_mean = gp->y_mean;
+        q.y_std = gp->y_std;
+        q.y_var = p.y_var;
+        q.acq = acq;
+        q.eta = eta;
+        q.kappa = kappa;
+        q.mean_out = mean_out;
+        q.var_out = var_out;
+        q.acq_out = acq_out;
+        q.index_base = index_base;
+        q.partials = want_min ? gp->partials : nullptr;
+        q.tile_records = tile_records;
+        q.nan_skip = gp->nan_skip;
+        const int grid = small_grid(gp, m);
+        int rc = gp->n <= 8 ? launch_small_k<8>(gp->kernel, q, grid, st)
+                            : (gp->n <= 16 ? launch_small_k<16>(gp->kernel, q, grid, st) : launch_small_k<32>(gp->kernel, q, grid, st));
+        if (rc != BOPY_OK) return rc;
+        if (want_min) {
+            minloc_finalize_kernel<<<1, 256, 0, st>>>(gp->partials, grid, min_val, min_idx);
+            CUDA_TRY(cudaGetLastError());
+        }
+        return BOPY_OK;
+    }
     if (allow_probe && probe_applies(gp, m, slot_per_tile, tile_records)) {
         // small m: latency path, the forward substitution spread over the block rows of L (probe_kernel.cuh)
         const ProbePlan pl = probe_plan(gp, m);
@@ -529,7 +588,11 @@ int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, 
     if (e == cudaSuccess) e = cudaMalloc(&gp->Xt, (size_t)gp->n_blocks * (d + 1) * BM * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&gp->Dinv, (size_t)gp->n_blocks * BM * BM * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&gp->Vws, (size_t)gp->sm_count * gp->n_pad * BN * es);
-    if (e == cudaSuccess) e = cudaMalloc(&gp->partials, (size_t)gp->sm_count * sizeof(MinLoc));
+    if (e == cudaSuccess) e = cudaMalloc(&gp->partials, (size_t)gp->sm_count * SMALL_CTAS_PER_SM * sizeof(MinLoc));
+    {
+        const char* sn = std::getenv("BOPY_B200_SMALL_N");
+        gp->small_n = !(sn != nullptr && std::strcmp(sn, "0") == 0);
+    }
     // latency path: fp64 DMMA handles whose block rows fit one wave of CTAs (the V chain needs them all in flight)
     gp->probe_capable = dtype == BOPY_F64 && !gp->fma64 && gp->n_blocks <= gp->sm_count;
     if (gp->probe_capable) {
@@ -1635,7 +1698,9 @@ int bopy_minloc_allreduce(bopy_comm* comm, double* val_dev, int64_t* idx_dev, in
 int bopy_gp_launch_info(const bopy_gp* gp, int64_t m, int* grid_out, int* launches_out, int64_t* workspace_bytes_out) {
     if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
     const long long ntiles = (m + BN - 1) / BN;
-    if (probe_applies(gp, m, 0, nullptr)) {
+    if (small_applies(gp, 0)) {
+        if (grid_out) *grid_out = small_grid(gp, m);
+    } else if (probe_applies(gp, m, 0, nullptr)) {
         if (grid_out) *grid_out = probe_plan(gp, m).grid;
     } else if (grid_out) {
         *grid_out = (int)std::min<long long>(ntiles, gp->sm_count);
