@@ -1,5 +1,7 @@
+"""C1 / C3 through bench.run_config (development aid, also the command the round-2 ncu captures of the small-n kernels profile)."""
 import sys, time, json
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, torch
 ctx = bench.Ctx()
 from bopy_b200 import _native
