@@ -1,6 +1,6 @@
 """Summarise `.ncu-rep` captures (read here with `ncu -i ... --page raw --csv`) into the JSON files under profiles/r02/.
 
-    python tools/ncu_summary.py gpurun_out/ncu_c4_f64.ncu-rep  profiles/r02/ncu_sweep_f64_c4_summary.json  [traffic-key]
+    python tools/ncu_summary.py gpurun_out/ncu_c4_f64_raw.csv  profiles/r02/ncu_sweep_f64_c4_summary.json  [traffic-key]
 
 Writes the metrics the roofline discussion uses (duration, DRAM bytes, L2 hit rate, pipe utilisation, registers, shared
 memory, stall reasons) for every kernel in the report and, with a traffic key ("C4_f64", "C4_f32", ...), records
@@ -30,7 +30,11 @@ KEEP = [
 
 
 def rows_of(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    """`rep`: a .ncu-rep (read through ncu) or the `ncu -i ... --page raw --csv` dump made on the GPU box."""
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     return hdr, units, rows[2:]
