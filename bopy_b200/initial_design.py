@@ -30,6 +30,9 @@ class UniformRandomInitialDesign(InitialDesign):
 
 
 class SobolSequenceInitialDesign(InitialDesign):
+    """Sobol points without the origin (bopy/initial_design.py:41-51 uses sobol_seq.i4_sobol_generate; this uses scipy's
+    generator, whose Joe-Kuo direction numbers can differ from sobol_seq's tables in higher dimensions)."""
+
     def _generate(self, n_dimensions, n_points):
         from scipy.stats import qmc
         sampler = qmc.Sobol(d=n_dimensions, scramble=False)
@@ -41,6 +44,10 @@ class SobolSequenceInitialDesign(InitialDesign):
 
 
 class LatinHypercubeInitialDesign(InitialDesign):
+    """Latin hypercube (bopy/initial_design.py:54-63 uses pyDOE.lhs, which draws from numpy's GLOBAL random state): the
+    sampler is seeded from that state, so `np.random.seed(...)` makes a BO run reproducible here too."""
+
     def _generate(self, n_dimensions, n_points):
+        import numpy as np
         from scipy.stats import qmc
-        return qmc.LatinHypercube(d=n_dimensions).random(n_points)
+        return qmc.LatinHypercube(d=n_dimensions, seed=int(np.random.randint(2 ** 31 - 1))).random(n_points)

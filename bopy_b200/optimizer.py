@@ -260,11 +260,17 @@ class DirectOptimizer(Optimizer):
     """DIRECT global optimiser, one acquisition probe per call (bopy/optimizer.py:70-107).
 
     The reference binds the Fortran `scipydirect.minimize`; this uses `scipy.optimize.direct`
-    (the same algorithm).  `direct_kwargs` accepts scipydirect's names (`maxf`, `maxT`, `eps`,
-    `algmethod`) and maps them onto scipy's (`maxfun`, `maxiter`, `eps`, `locally_biased`).
+    (the same algorithm).  `direct_kwargs` accepts scipydirect's names and maps them onto scipy's:
+    `maxf` -> `maxfun`, `maxT` -> `maxiter`, `algmethod` -> `locally_biased`, `fglobal` -> `f_min`,
+    `fglper` (per cent) -> `f_min_rtol`, `volper` -> `vol_tol`, `sigmaper` -> `len_tol`; `disp` / `logfilename` have no
+    counterpart and are ignored.  Keys that are absent take scipydirect's defaults (original DIRECT, maxf = 20000,
+    maxT = 6000), not scipy's (DIRECT_L, 1000 d evaluations, 1000 iterations).
     """
 
-    _RENAMED = {"maxf": "maxfun", "maxT": "maxiter", "algmethod": "locally_biased"}
+    _RENAMED = {"maxf": "maxfun", "maxT": "maxiter", "algmethod": "locally_biased", "fglobal": "f_min",
+                "fglper": "f_min_rtol", "volper": "vol_tol", "sigmaper": "len_tol"}
+    _IGNORED = ("disp", "logfilename")
+    _DEFAULTS = {"locally_biased": False, "maxfun": 20000, "maxiter": 6000}
 
     def __init__(self, acquisition_function: AcquisitionFunction, bounds: Bounds, **direct_kwargs: Dict[str, Any]):
         super().__init__(acquisition_function, bounds)
@@ -273,10 +279,18 @@ class DirectOptimizer(Optimizer):
     def _optimize(self) -> Tuple[np.ndarray, np.ndarray]:
         from scipy.optimize import direct
 
-        kwargs = {}
+        kwargs = dict(self._DEFAULTS)
         for key, value in self.direct_kwargs.items():
+            if key in self._IGNORED:
+                continue
             name = self._RENAMED.get(key, key)
-            kwargs[name] = bool(value) if name == "locally_biased" else value
+            if name == "locally_biased":
+                value = bool(value)
+            elif name == "f_min_rtol":
+                value = float(value) / 100.0          # scipydirect: per cent
+            elif name in ("vol_tol", "len_tol") and float(value) < 0:
+                continue                              # scipydirect's "-1 = off": scipy's own (tiny) default
+            kwargs[name] = value
 
         def objective(point):
             return float(self.acquisition_function(np.asarray(point, dtype=np.float64).reshape(1, -1))[0])
@@ -373,14 +387,19 @@ class OneShotBatchOptimizerTopKStrategy(OneShotBatchOptimizerStrategy):
 
 
 class OneShotBatchOptimizerKDPPSamplingStrategy(OneShotBatchOptimizerStrategy):
-    """k-DPP sample with likelihood kernel(x) + alpha I (bopy/optimizer.py:200-232); needs `dppy`."""
+    """k-DPP sample with likelihood kernel(x) + alpha I (bopy/optimizer.py:200-232); needs `dppy`.  The likelihood matrix is
+    N x N: with a device sweep's log of a million evaluations the `max_points` best ones are kept first."""
 
-    def __init__(self, kernel: Callable[[np.ndarray], np.ndarray], alpha: float = 1e-5):
+    def __init__(self, kernel: Callable[[np.ndarray], np.ndarray], alpha: float = 1e-5, max_points: int = 4096):
         super().__init__()
         self.kernel = kernel
         self.alpha = alpha
+        self.max_points = int(max_points)
 
     def select(self, x, a_x, batch_size):
+        if len(x) > self.max_points:
+            keep = np.argsort(np.where(np.isnan(a_x), np.inf, a_x), kind="stable")[: self.max_points]
+            x, a_x = x[keep], a_x[keep]
         try:
             from dppy.finite_dpps import FiniteDPP
         except ImportError as exc:  # the dependency is optional and absent from this image
@@ -403,6 +422,11 @@ class OneShotBatchOptimizer(Optimizer):
         self.strategy = strategy
 
     def _optimize(self) -> Tuple[np.ndarray, np.ndarray]:
+        if getattr(self.base_optimizer, "distributed", False):
+            # a sharded sweep logs only the rank's own slice: every rank would pick a different batch and the replicated
+            # surrogates would drift apart silently
+            raise ValueError("OneShotBatchOptimizer needs the whole evaluation log on every rank: use a base optimizer "
+                             "without `distributed=True` / `process_group`")
         self.acquisition_function.start_optimization()
         self.base_optimizer.optimize()
         if hasattr(self.strategy, "select_on_device") and hasattr(self.acquisition_function, "get_evaluations_on_device") \

@@ -261,3 +261,61 @@ def test_top_k_strategy_host_rule():
     assert fs.tolist() == [-5.0, -4.9]
     xs, fs = OneShotBatchOptimizerTopKStrategy(min_distance=10.0).select(x, a, 4)
     assert fs.tolist() == [-5.0]                        # fewer than asked for when the distance rule leaves no more
+
+
+def test_direct_optimizer_maps_scipydirect_arguments_and_defaults():
+    """scipydirect's defaults (original DIRECT, maxf 20000, maxT 6000) and its keyword names."""
+    import scipy.optimize
+    from bopy_b200.optimizer import DirectOptimizer
+
+    class Quadratic:
+        def __call__(self, x):
+            return np.array([float(((x - 0.3) ** 2).sum())])
+
+    seen = {}
+    real = scipy.optimize.direct
+
+    def spy(func, bounds, **kwargs):
+        seen.update(kwargs)
+        return real(func, bounds, **kwargs)
+
+    scipy.optimize.direct = spy
+    try:
+        res = DirectOptimizer(Quadratic(), Bounds([Bound(0.0, 1.0)]), maxf=80, fglobal=0.0, fglper=1.0, volper=-1.0,
+                              disp=True, logfilename="x.log").optimize()
+    finally:
+        scipy.optimize.direct = real
+    assert seen["maxfun"] == 80 and seen["maxiter"] == 6000 and seen["locally_biased"] is False
+    assert seen["f_min"] == 0.0 and seen["f_min_rtol"] == pytest.approx(0.01) and "vol_tol" not in seen
+    assert "disp" not in seen and "logfilename" not in seen
+    assert res.x_min.shape == (1, 1) and res.f_min.shape == (1,) and abs(res.x_min[0, 0] - 0.3) < 0.05
+
+
+def test_latin_hypercube_follows_numpy_global_seed_and_one_shot_rejects_sharded_base():
+    from bopy_b200.initial_design import LatinHypercubeInitialDesign
+    from bopy_b200.optimizer import CandidateSweepOptimizer, OneShotBatchOptimizer, OneShotBatchOptimizerRandomSamplingStrategy
+    b = Bounds([Bound(0.0, 1.0), Bound(-2.0, 2.0)])
+    np.random.seed(5)
+    first = LatinHypercubeInitialDesign().generate(b, 7)
+    np.random.seed(5)
+    assert np.array_equal(first, LatinHypercubeInitialDesign().generate(b, 7))
+
+    class Acq:
+        surrogate = None
+
+        def start_optimization(self):
+            pass
+
+    base = CandidateSweepOptimizer(Acq(), b, n_candidates=128, distributed=True)
+    with pytest.raises(ValueError, match="whole evaluation log"):
+        OneShotBatchOptimizer(Acq(), b, base_optimizer=base, batch_size=2,
+                              strategy=OneShotBatchOptimizerRandomSamplingStrategy()).optimize()
+
+
+def test_matern_inf_is_flattened_to_rbf_and_unsupported_kernels_say_so():
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern, RationalQuadratic
+    from bopy_b200.kernel_spec import UnsupportedKernelError, flatten_sklearn_kernel
+    flat = flatten_sklearn_kernel(ConstantKernel(2.0) * Matern([0.5, 0.25], nu=np.inf))
+    assert flat.kernel == "rbf" and flat.amplitude == 2.0 and np.array_equal(flat.length_scale, [0.5, 0.25])
+    with pytest.raises(UnsupportedKernelError, match="no CPU fallback"):
+        flatten_sklearn_kernel(RationalQuadratic())

@@ -47,6 +47,19 @@ def main():
                       f"| var err/bound {np.max(ev/bv):9.3g} (max abs/prior {ev.max()/pv:.2e}, max rel {rel.max():.2e}) "
                       f"| argmin {int(out['min_idx'].item())} ref {int(g['argmin_ei'])} np {int(np.argmin(a))} "
                       f"| nan {int(np.isnan(a).sum())}/{int(np.isnan(g['ei']).sum())}")
+                if dtype == "f32":
+                    # the pure-relative error of the variance (north star: 1e-4 in fp32) as a histogram, and where it sits
+                    # against the posterior variance itself: relative error is only large where var << prior
+                    ok = np.isfinite(var) & np.isfinite(g["var"]) & (np.abs(g["var"]) > 0)
+                    edges = [0, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, np.inf]
+                    hist = np.histogram(rel[ok], bins=edges)[0]
+                    labels = ["<1e-7", "<1e-6", "<1e-5", "<1e-4", "<1e-3", "<1e-2", "<1e-1", ">=1e-1"]
+                    print("    relative |dvar|/|var| histogram: " + "  ".join(f"{lb}:{int(c)}" for lb, c in zip(labels, hist)))
+                    over = ok & (rel > 1e-4)
+                    q = np.quantile(np.abs(var - g["var"])[ok] / pv, [0.5, 0.9, 0.99, 1.0])
+                    print(f"    |dvar|/prior quantiles 50/90/99/100 %: {q[0]:.2e} {q[1]:.2e} {q[2]:.2e} {q[3]:.2e}; "
+                          f"candidates with relative error > 1e-4: {int(over.sum())} of {int(ok.sum())}"
+                          + (f", all with var/prior <= {float(np.max(np.abs(g['var'])[over]) / pv):.2e}" if over.any() else ""))
                 gp.close()
             except Exception:
                 print(name, dtype, "FAILED")
