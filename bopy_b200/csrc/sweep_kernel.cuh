@@ -226,23 +226,43 @@ struct DmmaPolicy {
         v += __shfl_xor_sync(0xffffffffu, v, 16);
         return v;
     }
-    // DIAG: inv(L_II) is lower triangular, so row atom a only needs the k tiles kc <= a
-    template <bool DIAG>
-    __device__ __forceinline__ void mma_tile(double (&acc)[RI][CJ], const double* __restrict__ As,
-                                             const double* __restrict__ Bs, int kc) const {
+    // rows (atoms) I0 .. RI-1 of the warp tile times one operand tile
+    template <int I0>
+    __device__ __forceinline__ void mma_rows(double (&acc)[RI][CJ], const double* __restrict__ As,
+                                             const double* __restrict__ Bs) const {
 #pragma unroll
         for (int s = 0; s < KC / 4; ++s) {
             double a[RI], b[CJ / 2];
 #pragma unroll
             for (int jj = 0; jj < CJ / 2; ++jj) b[jj] = Bs[boff[jj] + s * 4 * BN];
 #pragma unroll
-            for (int i = 0; i < RI; ++i) a[i] = As[aoff[i] + s * 4 * BM];
+            for (int i = I0; i < RI; ++i) a[i] = As[aoff[i] + s * 4 * BM];
 #pragma unroll
-            for (int i = 0; i < RI; ++i) {
-                if (DIAG && atom(i) < kc) continue;   // warp-uniform
+            for (int i = I0; i < RI; ++i) {
 #pragma unroll
                 for (int jj = 0; jj < CJ / 2; ++jj) dmma_m8n8k4(acc[i][2 * jj], acc[i][2 * jj + 1], a[i], b[jj]);
             }
+        }
+    }
+    // DIAG: inv(L_II) is lower triangular, so row atom a only needs the k tiles kc <= a.  The warp's atoms ascend with i, so
+    // the atoms that still need tile kc are a suffix i0 .. RI-1; i0 is warp-uniform and selects one of RI fully unrolled
+    // bodies by a real branch.  (Written as `if (atom(i) < kc) continue;` ptxas predicates the DMMAs and pads every
+    // predicated-off one with NOPs: the skipped half of the triangle then still costs ~60 % of its time --
+    // profiles/r02/ncu_sweep_tc_f32_c4_source.csv.gz.)
+    template <bool DIAG>
+    __device__ __forceinline__ void mma_tile(double (&acc)[RI][CJ], const double* __restrict__ As,
+                                             const double* __restrict__ Bs, int kc) const {
+        if (!DIAG) {
+            mma_rows<0>(acc, As, Bs);
+            return;
+        }
+        const int i0 = (atom(0) < kc) + (atom(1) < kc) + (atom(2) < kc) + (atom(3) < kc);
+        switch (i0) {
+            case 0: mma_rows<0>(acc, As, Bs); break;
+            case 1: mma_rows<1>(acc, As, Bs); break;
+            case 2: mma_rows<2>(acc, As, Bs); break;
+            case 3: mma_rows<3>(acc, As, Bs); break;
+            default: break;
         }
     }
 };

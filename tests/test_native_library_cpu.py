@@ -52,3 +52,6 @@ def test_built_for_sm_100a_with_tma_bulk_copies(lib_path):
     assert "sm_100a" in elf
     sass = subprocess.run([cuobjdump, "-sass", lib_path], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "DFMA" in sass and "SYNCS" in sass   # bulk async copies + mbarriers + fp64 FMA
+    assert "DMMA" in sass                                            # fp64 engine: mma.sync.m8n8k4.f64
+    # fp32 engine: tcgen05.mma kind::tf32 (UTCHMMA), its commits (UTCBAR) and the TMEM read-back (LDTM)
+    assert "UTCHMMA" in sass and "UTCBAR" in sass and "LDTM" in sass
