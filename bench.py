@@ -504,6 +504,7 @@ def run_b200(args):
     else:
         peak = peaks_all["tf32_tcgen05"] / 3.0
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    group = native.set_group_mode(-2)      # (thread blocks per candidate tile, slots, lead) in force; 0 = one tile per block
     nominal = sm_count * (64 if args.dtype == "f64" else 128) * 2 * 1.965e9 / 1e12
     F = flops_per_candidate(n, d)
     achieved = F * m / (kernel_ms * 1e-3) / 1e12
@@ -521,7 +522,7 @@ def run_b200(args):
         "pipe": ("FP64 tensor sub-pipe (mma.sync.m8n8k4.f64 = SASS DMMA; tcgen05 has no f64 kind)" if args.dtype == "f64"
                  else "tcgen05.mma kind::tf32 (SASS UTCHMMA), accumulators in TMEM, 3xTF32 split: peak = measured rate / 3; "
                       "K*, diagonal solve and sum v^2 on the FP64 pipe"),
-        "kernel": "sweep_kernel" if args.dtype == "f64" else "sweep_tc_kernel",
+        "kernel": ("sweep_group_kernel" if group[0] >= 2 else "sweep_kernel") if args.dtype == "f64" else "sweep_tc_kernel",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "peak_source": "bopy_measure_peak: register-resident DFMA / DMMA loops and a shared-memory-operand tcgen05 loop measured "
                        "live on this GPU (MEASURED_PEAKS.json holds only HBM and bf16 peaks; the path is FP-pipe bound, SURVEY.md 8d)",
@@ -593,8 +594,11 @@ def run_b200(args):
                                f"alpha={ALPHA_REG}, normalize_y, EI + argmin, {m} candidates per GPU per step "
                                f"({world * m} per step in total), candidates U[0,1]^d from (seed, global index)",
                    "n": n, "d": d, "candidates_per_gpu": m, "acquisition": "EI",
-                   "l2": f"{nbuf} candidate buffers rotated between steps ({nbuf * m * d * 8 / 1e6:.0f} MB) and a "
-                         f"{info['workspace_bytes'] / 1e6:.0f} MB solve workspace: larger than the 126 MB L2",
+                   "l2": f"{nbuf} candidate buffers rotated between steps ({nbuf * m * d * 8 / 1e6:.0f} MB: larger than the 126 MB "
+                         f"L2) and {info['workspace_bytes'] / 1e6:.0f} MB of solve workspace in flight"
+                         + (f" (group mode: {group[0]} thread blocks per candidate tile, {group[1]} slots per group, so that "
+                            f"the workspace stays L2-resident)" if group[0] >= 2 else ""),
+                   "group_mode": {"group_size": group[0], "slots": group[1], "lead": group[2]},
                    "parallelism": f"candidates sharded over {world} GPU(s), state replicated, one min-loc exchange "
                                   f"(ncclAllGather of 16-byte records + one-warp kernel, on the sweep's stream)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m * d * 8, "d2h_bytes_per_step": 16,

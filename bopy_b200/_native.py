@@ -39,6 +39,8 @@ _SIGNATURES = {
                                       c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "bopy_gp_probe_trace": (c_int, [c_void_p, POINTER(c_int64)]),
     "bopy_gp_set_latency_path": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
+    "bopy_gp_set_group_mode": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int)]),
+    "bopy_group_schedule": (c_int, [c_int64, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "bopy_acq_value_and_grad": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p]),
     "bopy_acq_eval_host": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
@@ -79,6 +81,13 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None
+
+
+def group_schedule(job, n_blocks, lead):
+    """(tile sequence number, block row) of a group's job-th unit of work in group mode (host-only helper, for tests)."""
+    k, i = c_int(), c_int()
+    check(load().bopy_group_schedule(int(job), int(n_blocks), int(lead), byref(k), byref(i)), "bopy_group_schedule")
+    return k.value, i.value
 
 
 def load():
@@ -292,6 +301,13 @@ class NativeGP:
         eff = c_int64()
         check(self.lib.bopy_gp_set_latency_path(self._handle, int(max_m), byref(eff)), "bopy_gp_set_latency_path")
         return eff.value
+
+    def set_group_mode(self, group_size=-1, slots=-1, lead=-1):
+        """Thread blocks per candidate tile of the fp64 throughput sweep (bopy_gp_set_group_mode): -1 = the default chosen
+        from n, 0 = one tile per block, >= 2 = group mode, -2 = report only.  Returns (group_size, slots, lead) in force."""
+        eff = (c_int * 3)()
+        check(self.lib.bopy_gp_set_group_mode(self._handle, int(group_size), int(slots), int(lead), eff), "bopy_gp_set_group_mode")
+        return tuple(eff[:])
 
     def gradient_capable(self):
         """True if bopy_acq_value_and_grad serves this handle (fp64 solve, block rows fit one wave of thread blocks)."""

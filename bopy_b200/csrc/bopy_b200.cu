@@ -20,6 +20,7 @@
 #include "probe_kernel.cuh"
 #include "prune_kernels.cuh"
 #include "small_kernel.cuh"
+#include "sweep_group_kernel.cuh"
 #include "sweep_kernel.cuh"
 #include "sweep_tc_kernel.cuh"
 
@@ -91,6 +92,11 @@ struct bopy_gp {
     // staging of the host-buffer entry point (small calls: one point per DIRECT probe)
     double* host_x = nullptr;          // [HOST_CALL_MAX_M][d]
     double* host_out = nullptr;        // [3][HOST_CALL_MAX_M]: acq / mean / var
+    // group mode of the fp64 sweep (sweep_group_kernel.cuh): group_size CTAs share a candidate tile, so that the V
+    // workspace in flight fits the L2; 1 = off.  Buffers are allocated on first use.
+    int group_size = 1, group_slots = 2, group_lead = 0;
+    unsigned* gctl = nullptr;
+    double* gpart = nullptr;
 };
 
 namespace {
@@ -103,6 +109,30 @@ template <class E, int KIND> int launch_sweep_t(SweepParams p, int grid, cudaStr
     sweep_kernel<E, KIND><<<grid, NT_ALL, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     return BOPY_OK;
+}
+
+template <int KIND> int launch_sweep_group_t(SweepParams p, int grid, cudaStream_t st) {
+    using E = EngineF64;
+    size_t smem = sweep_smem_bytes<E>(p.d);
+    p.xrow_separate = sweep_xrow_separate<E>(p.d) ? 1 : 0;
+    // staging buffer for a tile's raw candidate rows behind the X/l row buffer, when it fits and the rows are 16-byte aligned
+    const size_t stage_bytes = (size_t)BN * p.d * sizeof(double);
+    p.xs_stage = (p.xrow_separate && smem + stage_bytes <= SMEM_LIMIT && reinterpret_cast<uintptr_t>(p.Xs) % 16 == 0) ? 1 : 0;
+    if (p.xs_stage) smem += stage_bytes;
+    CUDA_TRY(cudaFuncSetAttribute(sweep_group_kernel<E, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sweep_group_kernel<E, KIND><<<grid, NT_ALL, smem, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
+int launch_sweep_group(int kernel, const SweepParams& p, int grid, cudaStream_t st) {
+    switch (kernel) {
+        case BOPY_KERNEL_RBF: return launch_sweep_group_t<K_RBF>(p, grid, st);
+        case BOPY_KERNEL_MATERN12: return launch_sweep_group_t<K_M12>(p, grid, st);
+        case BOPY_KERNEL_MATERN32: return launch_sweep_group_t<K_M32>(p, grid, st);
+        case BOPY_KERNEL_MATERN52: return launch_sweep_group_t<K_M52>(p, grid, st);
+    }
+    return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
 }
 
 template <int KIND, int FOLD> int launch_sweep_tc_f(SweepParams p, int grid, cudaStream_t st);
@@ -248,6 +278,48 @@ long long packed_tiles(const bopy_gp* gp) {
     long long n = 0;
     dispatch_engine(gp, [&](auto e) { n = decltype(e)::total_tiles(gp->n_blocks); return 0; });
     return n;
+}
+
+// Group mode of the fp64 sweep (sweep_group_kernel.cuh): CTAs per candidate tile, workspace slots per group, rows of the next
+// tile interleaved with the current one.  Requests < 0 mean "choose":
+//   group size: 0 (one tile per CTA) when that kernel's workspace, sm_count x n_pad x 128 x 8 B, fits GROUP_L2_BUDGET anyway
+//               or the handle has fewer than 4 block rows; else the smallest size whose tiles in flight (groups x slots x
+//               n_pad x 128 x 8 B) fit the budget, at most 5/8 of the block rows (a tile's rows form a dependency chain);
+//   slots 3, lead = half the block rows: two tiles of a group run half a tile apart, the third slot decouples them
+//   (measured at C4: 8 CTAs x 3 slots x lead 8 = the speed of the one-tile-per-CTA kernel, 2 slots x lead 2 = -0.8 %).
+// group size 1 = the one-tile-per-CTA kernel with the zig-zag V order of round 1 (A/B runs), 0 = the same kernel with
+// group mode's ascending order (bit-identical to group mode).  BOPY_B200_SWEEP_GROUP / _SLOTS / _LEAD preset the requests.
+constexpr size_t GROUP_L2_BUDGET = (size_t)96 << 20;   // of the 126 MB L2; the packed factor and the candidate stream live there too
+void configure_group_mode(bopy_gp* gp, int G, int S, int lead) {
+    const int R = gp->n_blocks, sm = gp->sm_count;
+    const size_t slot_bytes = (size_t)gp->n_pad * BN * sizeof(double);
+    const bool capable = R >= 4 && gp->dtype == BOPY_F64 && !gp->fma64;
+    if (S < 0) S = 3;
+    S = std::max(2, std::min(S, 4));
+    if (G < 0) {
+        if (!capable || (size_t)sm * slot_bytes <= GROUP_L2_BUDGET) {
+            G = 0;
+        } else {
+            const int cap = std::max(2, 5 * R / 8);
+            G = 2;
+            while (G < cap && (size_t)((sm + G - 1) / G) * S * slot_bytes > GROUP_L2_BUDGET) ++G;
+        }
+    }
+    G = std::max(0, std::min(G, sm));
+    if (!capable && G > 1) G = 0;
+    while (S > 2 && G > 1 && ((sm + G - 1) / G) * S > sm) --S;       // the slots live in the handle's [sm_count] workspace
+    if (G > 1 && ((sm + G - 1) / G) * S > sm) G = 0;
+    if (lead < 0) lead = S >= 3 ? R / 2 : std::min(2, R / 2);
+    lead = std::max(0, std::min(lead, R / 2));
+    if (S < 3) lead = std::min(lead, std::max(0, R / 2 - 1));        // a full interleave needs the third slot (sweep_group_kernel.cuh)
+    gp->group_size = G;
+    gp->group_slots = S;
+    gp->group_lead = lead;
+}
+
+int env_int(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    return v != nullptr ? std::atoi(v) : fallback;
 }
 
 int check_ready(const bopy_gp* gp) {
@@ -444,6 +516,27 @@ int solve_alpha_chain(bopy_gp* gp, const double* yn_dev, double* alpha_dev, cuda
     return BOPY_OK;
 }
 
+// group mode serves the fp64 DMMA sweep on the handle's own workspace (never the V-exporting sweep of predict_cov)
+bool group_applies(const bopy_gp* gp, long long ntiles, int slot_per_tile, const void* Vws) {
+    return gp->group_size > 1 && gp->dtype == BOPY_F64 && !gp->fma64 && slot_per_tile == 0 && Vws == gp->Vws &&
+           ntiles < (1LL << 31);
+}
+
+// launch shape of group mode for a sweep of ntiles tiles.  Few tiles: larger groups, so that every SM works (a tile
+// cannot use more thread blocks than it has block rows)
+struct GroupPlan {
+    int G, grid, ngroups;
+};
+GroupPlan group_plan(const bopy_gp* gp, long long ntiles) {
+    GroupPlan pl;
+    pl.G = gp->group_size;
+    if (ntiles * pl.G < gp->sm_count)
+        pl.G = (int)std::max<long long>(pl.G, std::min<long long>(gp->n_blocks, gp->sm_count / ntiles));
+    pl.grid = (int)std::min<long long>(ntiles * pl.G, gp->sm_count);
+    pl.ngroups = (pl.grid + pl.G - 1) / pl.G;
+    return pl;
+}
+
 // the one place the sweep is launched from
 int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, double kappa, double* mean_out,
               double* var_out, double* acq_out, long long index_base, double* min_val, long long* min_idx,
@@ -525,8 +618,29 @@ int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, d
     }
     p.partials = want_min ? gp->partials : nullptr;
     p.tile_records = tile_records;
-    const int grid = (int)std::min<long long>(p.ntiles, gp->sm_count);
-    int rc = dispatch_engine(gp, [&](auto pol) { return launch_sweep_k<decltype(pol)>(gp->kernel, p, grid, st); });
+    p.zigzag = gp->group_size == 1 ? 1 : 0;
+    int grid = (int)std::min<long long>(p.ntiles, gp->sm_count);
+    int rc;
+    if (group_applies(gp, p.ntiles, slot_per_tile, Vws)) {
+        // group mode: G thread blocks per candidate tile, ceil(grid / G) x slots tiles of V in flight
+        const GroupPlan pl = group_plan(gp, p.ntiles);
+        const int S = gp->group_slots, ng_max = (gp->sm_count + gp->group_size - 1) / gp->group_size;
+        const size_t ctl_bytes = GroupCtl::words(ng_max, S, gp->n_blocks) * sizeof(unsigned);
+        if (gp->gctl == nullptr) {
+            CUDA_TRY(cudaMalloc(&gp->gctl, ctl_bytes));
+            CUDA_TRY(cudaMalloc(&gp->gpart, (size_t)ng_max * S * gp->n_blocks * 2 * BN * sizeof(double)));
+        }
+        grid = pl.grid;
+        p.group_size = pl.G;
+        p.group_slots = S;
+        p.group_lead = gp->group_lead;
+        p.gctl = gp->gctl;
+        p.gpart = gp->gpart;
+        CUDA_TRY(cudaMemsetAsync(gp->gctl, 0, ctl_bytes, st));
+        rc = launch_sweep_group(gp->kernel, p, grid, st);
+    } else {
+        rc = dispatch_engine(gp, [&](auto pol) { return launch_sweep_k<decltype(pol)>(gp->kernel, p, grid, st); });
+    }
     if (rc != BOPY_OK) return rc;
     if (want_min) {
         minloc_finalize_kernel<<<1, 256, 0, st>>>(gp->partials, grid, min_val, min_idx);
@@ -582,6 +696,8 @@ int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, 
     gp->fma64 = engine != nullptr && std::strcmp(engine, "fma") == 0;
     const char* engine32 = std::getenv("BOPY_B200_F32_ENGINE");
     gp->f32_engine = engine32 == nullptr ? 0 : (std::strcmp(engine32, "fma") == 0 ? 2 : (std::strcmp(engine32, "mma_sync") == 0 ? 1 : 0));
+    configure_group_mode(gp, env_int("BOPY_B200_SWEEP_GROUP", -1), env_int("BOPY_B200_SWEEP_SLOTS", -1),
+                         env_int("BOPY_B200_SWEEP_LEAD", -1));
     const size_t es = v_entry_bytes(gp);
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&gp->Lt, (size_t)packed_tiles(gp) * TILE_BYTES);
@@ -635,6 +751,8 @@ void bopy_gp_destroy(bopy_gp* gp) {
     cudaFree(gp->host_x);
     cudaFree(gp->host_out);
     cudaFree(gp->Lfull);
+    cudaFree(gp->gctl);
+    cudaFree(gp->gpart);
     delete gp;
 }
 
@@ -1074,6 +1192,32 @@ int bopy_gp_resize(bopy_gp* gp, int64_t n) {
                     (long long)n, gp->n_blocks, BM);
     gp->n = n;
     gp->ready = false;
+    return BOPY_OK;
+}
+
+int bopy_gp_set_group_mode(bopy_gp* gp, int group_size, int slots, int lead, int* effective_out) {
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    if (group_size != -2) {                // -2: report only
+        CUDA_TRY(cudaSetDevice(gp->device));
+        CUDA_TRY(cudaDeviceSynchronize()); // no sweep of this handle may be in flight while its control buffers change
+        configure_group_mode(gp, group_size, slots, lead);
+        cudaFree(gp->gctl);
+        cudaFree(gp->gpart);
+        gp->gctl = nullptr;
+        gp->gpart = nullptr;
+    }
+    if (effective_out) {
+        effective_out[0] = gp->group_size;
+        effective_out[1] = gp->group_slots;
+        effective_out[2] = gp->group_lead;
+    }
+    return BOPY_OK;
+}
+
+int bopy_group_schedule(int64_t job, int n_blocks, int lead, int* tile_seq_out, int* row_out) {
+    if (job < 0 || job > 0x7fffffffLL || n_blocks < 1 || lead < 0 || 2 * lead > n_blocks || tile_seq_out == nullptr || row_out == nullptr)
+        return fail(BOPY_ERR_BAD_ARG, "bopy_group_schedule: job >= 0, n_blocks >= 1, 0 <= 2 lead <= n_blocks, outputs non-NULL");
+    group_job((unsigned)job, n_blocks, lead, *tile_seq_out, *row_out);
     return BOPY_OK;
 }
 
@@ -1702,11 +1846,17 @@ int bopy_gp_launch_info(const bopy_gp* gp, int64_t m, int* grid_out, int* launch
         if (grid_out) *grid_out = small_grid(gp, m);
     } else if (probe_applies(gp, m, 0, nullptr)) {
         if (grid_out) *grid_out = probe_plan(gp, m).grid;
+    } else if (group_applies(gp, ntiles, 0, gp->Vws)) {
+        const GroupPlan pl = group_plan(gp, ntiles);
+        if (grid_out) *grid_out = pl.grid;
+        if (launches_out) *launches_out = 2;  // sweep_group_kernel + minloc_finalize_kernel (the control block is reset by a memset node)
+        if (workspace_bytes_out) *workspace_bytes_out = (int64_t)pl.ngroups * gp->group_slots * gp->n_pad * BN * (int64_t)sizeof(double);
+        return BOPY_OK;
     } else if (grid_out) {
         *grid_out = (int)std::min<long long>(ntiles, gp->sm_count);
     }
     if (launches_out) *launches_out = 2;  // sweep_kernel + minloc_finalize_kernel (argmin); 1 without argmin
-    if (workspace_bytes_out) *workspace_bytes_out = (int64_t)gp->sm_count * gp->n_pad * BN * (int64_t)v_entry_bytes(gp);
+    if (workspace_bytes_out) *workspace_bytes_out = (int64_t)std::min<long long>(ntiles, gp->sm_count) * gp->n_pad * BN * (int64_t)v_entry_bytes(gp);
     return BOPY_OK;
 }
 

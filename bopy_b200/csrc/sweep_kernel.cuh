@@ -57,6 +57,15 @@ struct SweepParams {
     long long* tc_prof; // tensor-core engine: optional [gridDim.x][16] cycle counters per phase (BOPY_B200_TC_PROF=1), else nullptr
     int tc_stages;      // tensor-core engine: permanent slots of the (L_IJ, V_J) ring (4, fewer when d is large)
     int nan_skip;       // 1: candidates whose acquisition value is NaN never win the arg-min (np.nanargmin); 0: np.argmin (first NaN wins)
+    // group mode (sweep_group_kernel.cuh): group_size CTAs share one candidate tile
+    int group_size;     // CTAs per group (0 / 1: sweep_kernel, one tile per CTA)
+    int group_slots;    // workspace slots (tiles in flight) per group
+    int group_lead;     // rows of the next tile interleaved with the last rows of the current one in the job order
+    unsigned* gctl;     // control block (GroupCtl), zeroed before the launch
+    double* gpart;      // [groups][slots][n_blocks][2][BN] partial mean / sum v^2 of every block row
+    int xs_stage;       // group mode: candidate rows of a tile are staged in shared memory by a bulk copy (room + alignment allow it)
+    int zigzag;         // sweep_kernel: 1 = odd block rows read V_{I-2} .. V_0 then V_{I-1} (L2 reuse of the per-CTA workspace);
+                        // 0 = ascending J, the order of group mode (same summation order = bit-identical results)
 };
 
 // exp(x) for x <= 0, branch-free so that the 64 evaluations a thread makes per block row interleave instead of
@@ -466,7 +475,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_kernel(const SweepParams p) {
                         // J order: even rows 0..I-1, odd rows I-2..0 then I-1 (zig-zag: the V slices read last by one
                         // block row are read first by the next, so they are still in L2; V_{I-1} always comes last)
                         const int jpos = t / CHG, c = t - jpos * CHG;
-                        const int J = (I & 1) ? (jpos < I - 1 ? I - 2 - jpos : I - 1) : jpos;
+                        const int J = ((I & 1) && p.zigzag) ? (jpos < I - 1 ? I - 2 - jpos : I - 1) : jpos;
                         if (J == I - 1 && c == 0) {   // first touch of V_{I-1}: wait until the consumers published it
                             mbar_wait(vbar, vphase);
                             vphase ^= 1u;

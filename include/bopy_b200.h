@@ -171,6 +171,27 @@ int bopy_gp_posterior_acq(bopy_gp* gp, const double* Xs_dev, int64_t m, int acq,
 int bopy_gp_set_latency_path(bopy_gp* gp, int64_t max_m, int64_t* effective_out);
 
 /*
+ * Group mode of the fp64 throughput sweep.  By default every thread block owns one tile of 128 candidates and keeps that
+ * tile's V = L^-1 K*^T (n_pad x 128 fp64) in a workspace slot: 148 slots, 310 MB at n = 2048 against a 126 MB L2, so half
+ * of the re-reads of V go to DRAM.  In group mode `group_size` thread blocks share a tile -- the unit of work is one
+ * (tile, block row of L) -- and a group keeps `slots` tiles in flight, with the first `lead` block rows of its next tile
+ * interleaved with the last `lead` of the current one; tiles in flight: ceil(148 / group_size) x slots.  The arithmetic
+ * and its order are those of the one-tile-per-block kernel, the results bit-identical (group_size 0).
+ * group_size -2: change nothing, only report; -1: choose from n (the handle's default), 0: one tile per block, 1: one tile per block with
+ * the round-1 zig-zag order of the V reads (differs from the others by rounding), >= 2: that many blocks per tile.
+ * slots (2..4) / lead (0 .. n_blocks/2) < 0: choose.  effective_out (nullable) receives {group_size, slots, lead} in force.
+ * fp64 DMMA handles with at least 4 block rows only; others stay at 0.  Synchronises the device.
+ */
+int bopy_gp_set_group_mode(bopy_gp* gp, int group_size, int slots, int lead, int* effective_out);
+
+/*
+ * The job order of group mode, for tests (host only, no device needed): the group's job-th unit of work is block row
+ * *row_out of the group's *tile_seq_out-th tile.  Every (tile, row) appears exactly once, after (tile, row - 1) and
+ * after (tile - 2, n_blocks - 1).
+ */
+int bopy_group_schedule(int64_t job, int n_blocks, int lead, int* tile_seq_out, int* row_out);
+
+/*
  * Acquisition value AND its gradient with respect to the candidate, for the multi-start refinement behind
  * Optimizer._optimize (bopy/optimizer.py:65-67; SURVEY.md section 8f rank 3 -- the reference has no gradient code):
  *   d mean/dx = y_std sum_i alpha_i dk_i/dx,  d var/dx = -2 y_std^2 sum_i w_i dk_i/dx,  w = L^-T (L^-1 k*),
