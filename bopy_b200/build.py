@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libbopy_b200.so")
 SOURCES = [os.path.join(CSRC, "bopy_b200.cu")]
 HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "sweep_kernel.cuh", "aux_kernels.cuh", "fit_kernels.cuh", "probe_kernel.cuh",
-                                             "grad_kernel.cuh", "prune_kernels.cuh", "sweep_tc_kernel.cuh", "tc_common.cuh", "minloc_comm.cuh", "small_kernel.cuh", "sweep_group_kernel.cuh")] + [
+                                             "grad_kernel.cuh", "prune_kernels.cuh", "sweep_tc_kernel.cuh", "tc_common.cuh", "minloc_comm.cuh", "small_kernel.cuh", "sweep_group_kernel.cuh", "sweep_warp_kernel.cuh")] + [
     os.path.join(ROOT, "include", "bopy_b200.h")]
 
 NVCC_FLAGS = [

@@ -23,6 +23,7 @@
 #include "sweep_group_kernel.cuh"
 #include "sweep_kernel.cuh"
 #include "sweep_tc_kernel.cuh"
+#include "sweep_warp_kernel.cuh"
 
 using namespace bopy;
 
@@ -94,6 +95,7 @@ struct bopy_gp {
     double* host_out = nullptr;        // [3][HOST_CALL_MAX_M]: acq / mean / var
     // group mode of the fp64 sweep (sweep_group_kernel.cuh): group_size CTAs share a candidate tile, so that the V
     // workspace in flight fits the L2; 1 = off.  Buffers are allocated on first use.
+    int warp_stages = 0;               // n <= 256 on fp64 handles: ring depth of the warp-autonomous kernel (sweep_warp_kernel.cuh), 0 = off
     int group_size = 1, group_slots = 2, group_lead = 0;
     unsigned* gctl = nullptr;
     double* gpart = nullptr;
@@ -123,6 +125,24 @@ template <int KIND> int launch_sweep_group_t(SweepParams p, int grid, cudaStream
     sweep_group_kernel<E, KIND><<<grid, NT_ALL, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     return BOPY_OK;
+}
+
+template <int KIND> int launch_sweep_warp_t(const SweepParams& p, int grid, int stages, cudaStream_t st) {
+    const size_t smem = wk_smem_bytes(p.d, p.n_blocks, stages);
+    CUDA_TRY(cudaFuncSetAttribute(sweep_warp_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sweep_warp_kernel<KIND><<<grid, WK_NT, smem, st>>>(p, stages);
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
+int launch_sweep_warp(int kernel, const SweepParams& p, int grid, int stages, cudaStream_t st) {
+    switch (kernel) {
+        case BOPY_KERNEL_RBF: return launch_sweep_warp_t<K_RBF>(p, grid, stages, st);
+        case BOPY_KERNEL_MATERN12: return launch_sweep_warp_t<K_M12>(p, grid, stages, st);
+        case BOPY_KERNEL_MATERN32: return launch_sweep_warp_t<K_M32>(p, grid, stages, st);
+        case BOPY_KERNEL_MATERN52: return launch_sweep_warp_t<K_M52>(p, grid, stages, st);
+    }
+    return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
 }
 
 int launch_sweep_group(int kernel, const SweepParams& p, int grid, cudaStream_t st) {
@@ -522,6 +542,11 @@ bool group_applies(const bopy_gp* gp, long long ntiles, int slot_per_tile, const
            ntiles < (1LL << 31);
 }
 
+// n <= 256 (one or two block rows) on an fp64 DMMA handle, no V export: the warp-autonomous kernel (sweep_warp_kernel.cuh)
+bool warp_applies(const bopy_gp* gp, int slot_per_tile) {
+    return gp->warp_stages > 0 && slot_per_tile == 0;
+}
+
 // launch shape of group mode for a sweep of ntiles tiles.  Few tiles: larger groups, so that every SM works (a tile
 // cannot use more thread blocks than it has block rows)
 struct GroupPlan {
@@ -621,7 +646,11 @@ int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, d
     p.zigzag = gp->group_size == 1 ? 1 : 0;
     int grid = (int)std::min<long long>(p.ntiles, gp->sm_count);
     int rc;
-    if (group_applies(gp, p.ntiles, slot_per_tile, Vws)) {
+    if (warp_applies(gp, slot_per_tile)) {
+        // n <= 256: warp-autonomous kernel, two thread blocks per SM, no workspace
+        grid = (int)std::min<long long>(p.ntiles, 2LL * gp->sm_count);
+        rc = launch_sweep_warp(gp->kernel, p, grid, gp->warp_stages, st);
+    } else if (group_applies(gp, p.ntiles, slot_per_tile, Vws)) {
         // group mode: G thread blocks per candidate tile, ceil(grid / G) x slots tiles of V in flight
         const GroupPlan pl = group_plan(gp, p.ntiles);
         const int S = gp->group_slots, ng_max = (gp->sm_count + gp->group_size - 1) / gp->group_size;
@@ -698,6 +727,9 @@ int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, 
     gp->f32_engine = engine32 == nullptr ? 0 : (std::strcmp(engine32, "fma") == 0 ? 2 : (std::strcmp(engine32, "mma_sync") == 0 ? 1 : 0));
     configure_group_mode(gp, env_int("BOPY_B200_SWEEP_GROUP", -1), env_int("BOPY_B200_SWEEP_SLOTS", -1),
                          env_int("BOPY_B200_SWEEP_LEAD", -1));
+    // opt-in experiment (BOPY_B200_WARP_KERNEL=1): measured slower than the blocked kernel at C3 (4.30 vs 3.33 ms), DESIGN.md section 4
+    if (dtype == BOPY_F64 && !gp->fma64 && gp->n_blocks <= WK_MAX_BLOCKS && env_int("BOPY_B200_WARP_KERNEL", 0) != 0)
+        gp->warp_stages = wk_stages(d, gp->n_blocks);
     const size_t es = v_entry_bytes(gp);
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&gp->Lt, (size_t)packed_tiles(gp) * TILE_BYTES);
@@ -1846,6 +1878,11 @@ int bopy_gp_launch_info(const bopy_gp* gp, int64_t m, int* grid_out, int* launch
         if (grid_out) *grid_out = small_grid(gp, m);
     } else if (probe_applies(gp, m, 0, nullptr)) {
         if (grid_out) *grid_out = probe_plan(gp, m).grid;
+    } else if (warp_applies(gp, 0)) {
+        if (grid_out) *grid_out = (int)std::min<long long>(ntiles, 2LL * gp->sm_count);
+        if (launches_out) *launches_out = 2;  // sweep_warp_kernel + minloc_finalize_kernel
+        if (workspace_bytes_out) *workspace_bytes_out = 0;
+        return BOPY_OK;
     } else if (group_applies(gp, ntiles, 0, gp->Vws)) {
         const GroupPlan pl = group_plan(gp, ntiles);
         if (grid_out) *grid_out = pl.grid;

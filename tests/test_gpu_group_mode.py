@@ -155,3 +155,42 @@ def test_group_mode_nan_policies():
     if True:
         assert res[(2, "first")]["min_idx"] == int(np.argmin(a)) and res[(2, "skip")]["min_idx"] == int(np.nanargmin(a))
     gp.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c3_branin_n256", "matern25_d2", "ard_amp_white", "edge_on_training_points"])
+def test_warp_autonomous_kernel_parity(name, monkeypatch):
+    """The opt-in warp-autonomous kernel for n <= 256 (csrc/sweep_warp_kernel.cuh, BOPY_B200_WARP_KERNEL=1): same results as
+    the golden vectors of the unmodified reference and, to rounding, as the default kernel."""
+    g, st = golden_state(name)
+    if st.X_train.shape[0] > 256:
+        pytest.skip("more than two block rows")
+    monkeypatch.setenv("BOPY_B200_WARP_KERNEL", "1")
+    monkeypatch.setenv("BOPY_B200_SMALL_N", "0")
+    wk = native_for(st, "f64")
+    monkeypatch.delenv("BOPY_B200_WARP_KERNEL")
+    ref = native_for(st, "f64")
+    for gp in (wk, ref):
+        gp.set_latency_path(0)
+    assert wk.launch_info(1 << 20)["grid"] == 296 and ref.launch_info(1 << 20)["grid"] == 148
+    d = g["Xs"].shape[1]
+    rng = np.random.default_rng(2)
+    lo, hi = g["Xs"].min(0), g["Xs"].max(0)
+    Xs = np.concatenate([g["Xs"], lo + rng.random((300 * 128 + 37, d)) * (hi - lo)])
+    eta = float(g["eta"])
+    a = _outputs(wk, wk.candidates(Xs), "ei", eta, index_base=3)
+    b = _outputs(ref, ref.candidates(Xs), "ei", eta, index_base=3)
+    pv = (st.kernel.amplitude + st.kernel.noise_level) * st.y_std ** 2
+    assert np.max(np.abs(a["mean"] - b["mean"])) <= 1e-12 * (np.max(np.abs(b["mean"])) + st.y_std)
+    assert np.max(np.abs(a["var"] - b["var"])) <= 1e-12 * pv
+    assert a["min_idx"] - 3 == int(np.argmin(a["acq"]))
+    m = len(g["Xs"])
+    err, bound = check_mean(a["mean"][:m], g["mean"], st, "f64")
+    assert (err <= bound).all()
+    err, bound = check_var(a["var"][:m], g["var"], st, "f64")
+    assert (err <= bound).all()
+    vals, idx = (t.cpu().numpy() for t in wk.segment_argmin(wk.candidates(Xs[:1024]), 256, "lcb", kappa=2.0))
+    own = _outputs(wk, wk.candidates(Xs[:1024]), "lcb", eta)["acq"]
+    assert np.array_equal(idx, np.array([s * 256 + int(np.argmin(own[s * 256:(s + 1) * 256])) for s in range(4)]))
+    wk.close()
+    ref.close()
