@@ -895,7 +895,7 @@ CholStreams& chol_streams() {
 }
 
 void launch_cholesky(double* A, int n, int ld, int nb, double* Dinv, int* status, cudaStream_t st) {
-    const size_t chol_smem = ((size_t)BM * (BM + 1) + BM + 2) * sizeof(double);
+    const size_t chol_smem = chol_smem_bytes();
     cudaFuncSetAttribute(chol_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem);
     CholStreams& cs = chol_streams();
     if (!(cs.ok && nb >= 4)) {   // plain right-looking order on one stream
@@ -913,8 +913,21 @@ void launch_cholesky(double* A, int n, int ld, int nb, double* Dinv, int* status
     cudaEventRecord(cs.start, st);            // everything queued on st so far (the Gram matrix) comes first
     cudaStreamWaitEvent(hi, cs.start, 0);
     bool rest_pending = false;
+    long long* prof = nullptr;                // development aid: phase time stamps of the first diagonal block to stderr
+    if (std::getenv("BOPY_B200_CHOL_PROF") != nullptr && cudaMalloc(&prof, 40 * sizeof(long long)) == cudaSuccess)
+        cudaMemset(prof, 0, 40 * sizeof(long long));
     for (int J = 0; J < nb; ++J) {
-        chol_block_kernel<<<1, CHOL_NT, chol_smem, hi>>>(A, n, ld, J, Dinv, status);
+        chol_block_kernel<<<1, CHOL_NT, chol_smem, hi>>>(A, n, ld, J, Dinv, status, J == 0 ? prof : nullptr);
+        if (J == 0 && prof != nullptr) {
+            long long h[40];
+            cudaStreamSynchronize(hi);
+            cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+            cudaFree(prof);
+            std::fprintf(stderr, "[chol_prof] cycles per panel (a | b | c):");
+            for (int pnl = 0; pnl < 8; ++pnl)
+                std::fprintf(stderr, " %lld|%lld|%lld", h[1 + 3 * pnl] - h[3 * pnl], h[2 + 3 * pnl] - h[1 + 3 * pnl], h[3 + 3 * pnl] - h[2 + 3 * pnl]);
+            std::fprintf(stderr, "  write-back %lld  inverse %lld  store %lld  total %lld\n", h[25] - h[24], h[26] - h[25], h[27] - h[26], h[27] - h[0]);
+        }
         const int below = nb - J - 1;
         if (below <= 0) break;
         gemm_nt_kernel<<<below, NT, 0, hi>>>(A, n, ld, J, Dinv, 0);
@@ -1058,7 +1071,7 @@ int bopy_gp_append(bopy_gp* gp, const double* X_dev, const double* yn_dev, doubl
     gp->n = n + 1;
     gp->y_mean = y_mean;
     gp->y_std = y_std;
-    const size_t chol_smem = ((size_t)BM * (BM + 1) + BM + 2) * sizeof(double);
+    const size_t chol_smem = chol_smem_bytes();
     cudaFuncSetAttribute(dinv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem);
     dinv_block_kernel<<<1, CHOL_NT, chol_smem, st>>>(gp->Lfull, n + 1, ld, n / BM, gp->Dinv);
     // 3. the packed factor, alpha for the (re-normalised) targets solved on it, then X / alpha
@@ -1106,7 +1119,7 @@ int bopy_gp_truncate(bopy_gp* gp, int64_t n_new, const double* X_dev, const doub
     gp->y_mean = y_mean;
     gp->y_std = y_std;
     const int ld = gp->n_pad;
-    const size_t chol_smem = ((size_t)BM * (BM + 1) + BM + 2) * sizeof(double);
+    const size_t chol_smem = chol_smem_bytes();
     cudaFuncSetAttribute(dinv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem);
     dinv_block_kernel<<<1, CHOL_NT, chol_smem, st>>>(gp->Lfull, (int)n_new, ld, gp->n_blocks - 1, gp->Dinv);
     cudaError_t e = cudaGetLastError();

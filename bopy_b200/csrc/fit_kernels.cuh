@@ -43,14 +43,21 @@ __global__ void gram_kernel(const double* __restrict__ X, int n, int d, LsParam 
 }
 
 // In-place inverse of the lower-triangular block held in sm[BM][BM+1] (rdg[k] = 1 / L[k][k] precomputed), for a CTA of
-// CHOL_NT = 256 threads; on return X[r][j] (r >= j) sits at sm[j][r].  Ends with a block-wide barrier.
+// CHOL_NT = 256 threads; on return X[r][j] (r >= j) sits at sm[j][r].  T: scratch of 64 x 65 doubles.  Ends with a
+// block-wide barrier.  Two levels: inv([[A, 0], [C, B]]) = [[inv A, 0], [-inv(B) C inv(A), inv B]] with 64 x 64 halves --
+// the two diagonal inverses run side by side (4 warps each) and the off-diagonal block is two dense 64^3 products; the
+// one-level column sweep had a dependent chain of 127 steps on warp 0 (41 % of chol_block_kernel).
 constexpr int CHOL_NT = 256;
-__device__ __forceinline__ void tri_inverse_in_place(double* sm, const double* rdg) {
-    constexpr int LD = BM + 1;
+constexpr int CHOL_PANEL = 16;
+constexpr size_t chol_smem_bytes() {
+    return ((size_t)BM * (BM + 1) + BM + 2 + CHOL_PANEL * (CHOL_PANEL + 1) + 64 * 65) * sizeof(double);
+}
+__device__ __forceinline__ void tri_inverse_in_place(double* sm, const double* rdg, double* T) {
+    constexpr int LD = BM + 1, H = BM / 2, TLD = H + 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // inverse: X = inv(L), one column j per lane PAIR (lane, lane ^ 16) of a warp -- warp w owns columns 16 w .. 16 w + 15,
-    // the two lanes of a pair take the even / odd k of  X[r][j] = -(sum_{k=j..r-1} L[r][k] X[k][j]) / L[r][r]  and join
-    // by one shuffle.  X[r][j] (r >= j) is parked at sm[j][r] (diagonal and strict upper triangle of row j, which
+    // diagonal halves: X = inv(L_hh), one column j per lane PAIR (lane, lane ^ 16) of a warp -- warp w owns columns
+    // 16 w .. 16 w + 15, the two lanes of a pair take the even / odd k of  X[r][j] = -(sum_{k=j..r-1} L[r][k] X[k][j]) / L[r][r]
+    // and join by one shuffle.  X[r][j] (r >= j) is parked at sm[j][r] (diagonal and strict upper triangle of row j, which
     // nobody else touches: L is only read strictly below its diagonal from here on).  The lanes of a warp walk r and k
     // in lock step, so the reads of L[r][k] are broadcasts and a warp-level barrier per r orders the pair's exchange.
     {
@@ -58,7 +65,8 @@ __device__ __forceinline__ void tri_inverse_in_place(double* sm, const double* r
         if (half == 0) sm[j * LD + j] = rdg[j];
         __syncwarp();
         const int jw = 16 * warp;   // no column of this warp has entries above row jw
-        for (int r = jw + 1; r < BM; ++r) {
+        const int rend = warp < 4 ? H : BM;
+        for (int r = jw + 1; r < rend; ++r) {
             double s0 = 0.0, s1 = 0.0;
             int k = jw + half;
             for (; k + 2 < r; k += 4) {
@@ -78,22 +86,173 @@ __device__ __forceinline__ void tri_inverse_in_place(double* sm, const double* r
         }
     }
     __syncthreads();
+    // off-diagonal block: thread (ty, tx) owns rows ty + 16 i and columns tx + 16 jj (i, jj < 4) of the 64 x 64 results
+    const int ty = tid >> 4, tx = tid & 15;
+    double acc[4][4];
+    // T = C inv(A):  T[r][j] = sum_{k >= j} L[64 + r][k] X[k][j],  X[k][j] parked at sm[j][k]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+    for (int k = 0; k < H; ++k) {
+        double lv[4], xv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lv[i] = sm[(H + ty + 16 * i) * LD + k];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) xv[jj] = k >= tx + 16 * jj ? sm[(tx + 16 * jj) * LD + k] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fma(lv[i], xv[jj], acc[i][jj]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) T[(ty + 16 * i) * TLD + tx + 16 * jj] = acc[i][jj];
+    __syncthreads();
+    // X21 = -inv(B) T:  X[64 + r][j] = -sum_{s <= r} Xb[r][s] T[s][j],  Xb[r][s] parked at sm[64 + s][64 + r]; the result goes
+    // to sm[j][64 + r] (rows < 64, columns >= 64: the untouched upper-right quarter)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+    for (int sidx = 0; sidx < H; ++sidx) {
+        double xv[4], tv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i] = sidx <= ty + 16 * i ? sm[(H + sidx) * LD + H + ty + 16 * i] : 0.0;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) tv[jj] = T[sidx * TLD + tx + 16 * jj];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fma(xv[i], tv[jj], acc[i][jj]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) sm[(tx + 16 * jj) * LD + H + ty + 16 * i] = -acc[i][jj];
+    __syncthreads();
+}
+
+// (a) of chol_block_kernel, one warp: Cholesky of the 16 x 16 block at (k0, k0) of sm in registers (lane r = row r; lanes
+// 16..31 mirror lanes 0..15 and do not store), rdg[k0 + r] = 1 / L_rr, and W = inv(L16) to w16 (row-major, leading dimension
+// 17).  A function of its own (not inlined): inside the big kernel the unroller gives up on the triangular loops and the
+// row array goes to local memory -- 17 k cycles per panel instead of 4 k.
+__device__ __noinline__ void chol16_factor_and_invert(double* sm, double* rdg, double* w16, int* fail, int k0, int lane) {
+    constexpr int LD = BM + 1, PW = CHOL_PANEL, WLD = PW + 1;
+    const int r = lane & (PW - 1);
+    double a[PW];
+#pragma unroll
+    for (int c = 0; c < PW; ++c) a[c] = c <= r ? sm[(k0 + r) * LD + k0 + c] : 0.0;
+    bool bad = false;
+    double rinv_own = 1.0;                  // 1 / L[r][r] of this lane's own row
+#pragma unroll
+    for (int k = 0; k < PW; ++k) {
+        const double akk = __shfl_sync(0xffffffffu, a[k], k);
+        bad = bad || !(akk > 0.0);
+        // L_kk = sqrt(a_kk) from the reciprocal square root + one correction step (<= 1 ulp), 1 / L_kk for free
+        const double ri = rsqrt(akk);
+        double lkk = akk * ri;
+        lkk = fma(fma(-lkk, lkk, akk), 0.5 * ri, lkk);
+        if (r == k) {
+            a[k] = lkk;
+            rinv_own = ri;
+        } else if (r > k) {
+            a[k] = a[k] * ri;
+        }
+#pragma unroll
+        for (int c = k + 1; c < PW; ++c) {
+            const double lck = __shfl_sync(0xffffffffu, a[k], c);   // L[c][k]
+            if (r >= c) a[c] = fma(-a[k], lck, a[c]);
+        }
+    }
+    if (bad) {
+        if (lane == 0) *fail = 1;
+        return;
+    }
+    if (lane < PW) {
+#pragma unroll
+        for (int c = 0; c < PW; ++c)
+            if (c <= r) sm[(k0 + r) * LD + k0 + c] = a[c];
+        rdg[k0 + r] = rinv_own;
+    }
+    // W = inv(L16), lane j = column j: W[i][j] = -(sum_{k=j..i-1} L[i][k] W[k][j]) / L[i][i], the entries L[i][k] by
+    // shuffle from lane i's row
+    const int j = r;
+    double x[PW];
+#pragma unroll
+    for (int i = 0; i < PW; ++i) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+            const double lik = __shfl_sync(0xffffffffu, a[k], i);
+            if (k & 1) s1 = fma(lik, x[k], s1);
+            else s0 = fma(lik, x[k], s0);
+        }
+        const double ri = __shfl_sync(0xffffffffu, rinv_own, i);
+        x[i] = i < j ? 0.0 : (i == j ? ri : -(s0 + s1) * ri);
+    }
+    if (lane < PW) {
+#pragma unroll
+        for (int i = 0; i < PW; ++i) w16[i * WLD + j] = x[i];
+    }
 }
 
 // In-place Cholesky of the diagonal block J (identity padded beyond n) + its inverse, all in shared memory.
 // One CTA of CHOL_NT threads.  status[0] is set to J+1 if a non-positive pivot is met (not positive definite).
-// Panel-blocked (16 columns at a time) so that the 128 columns cost 8 x 3 block-wide barriers instead of 256:
-//   (a) the 16 x 16 diagonal block of the panel is factorised by one warp (warp-level barriers only),
-//   (b) every row below it solves its 16 panel entries against that factor on its own (one thread per row),
-//   (c) the trailing lower triangle takes the rank-16 update with no barrier between the 16 rank-1 terms.
-// The inverse is column-parallel and barrier-free: thread j forward-substitutes column j of inv(L_JJ), parking it in
-// row j of the (unused) strict upper triangle of the working block.
-constexpr int CHOL_PANEL = 16;
-__global__ void __launch_bounds__(CHOL_NT) chol_block_kernel(double* A, int n, int ld, int J, double* Dinv, int* status) {
-    extern __shared__ double sm[];          // [BM][BM+1] working block, then rdg[BM] (1 / L_kk), fail flag
+// This kernel is the serial chain of the device fit (n/128 of them, nothing else can run beside a diagonal block's
+// factorisation), so it is organised around latency.  Panel-blocked, 16 columns at a time, 3 block-wide barriers per panel:
+//   (a) one warp factorises the 16 x 16 diagonal block of the panel in REGISTERS (lane r = row r, column entries by
+//       shuffles) with a reciprocal square root per pivot -- sqrt + divide were 2 x ~400 cycles on each of the 16 dependent
+//       steps, 40 % of the kernel (ncu source page) -- and then inverts it (W = inv(L16), lane j = column j);
+//   (b) the rows below become a small product, X = A_panel W^T: 2 threads per row, 8 independent dot products each (as a
+//       forward substitution it was one dependent chain of 136 FMAs per row);
+//   (c) the trailing lower triangle takes the rank-16 update, only the 16 x 16 blocks on or below the diagonal of what is
+//       left (the update used to cover the full 128 x 128 square for every panel).
+// The inverse of the whole block is column-parallel and barrier-free: thread j forward-substitutes column j of
+// inv(L_JJ), parking it in row j of the (unused) strict upper triangle of the working block.
+
+// (c) for NBK remaining 16-row blocks: thread (ty, tx) owns the elements (t0 + ty + 16 i, t0 + tx + 16 j), j <= i < NBK
+template <int NBK>
+__device__ __forceinline__ void chol_trailing_update(double* sm, int k0) {
     constexpr int LD = BM + 1, PW = CHOL_PANEL;
+    const int tid = threadIdx.x, t0 = k0 + PW, c0 = t0 + (tid & 15), r0 = t0 + (tid >> 4);
+    double upd[NBK][NBK];
+#pragma unroll
+    for (int i = 0; i < NBK; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) upd[i][j] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < PW; ++k) {
+        const int kk = k0 + k;
+        double lck[NBK], lrk[NBK];
+#pragma unroll
+        for (int j = 0; j < NBK; ++j) lck[j] = sm[(c0 + 16 * j) * LD + kk];
+#pragma unroll
+        for (int i = 0; i < NBK; ++i) lrk[i] = sm[(r0 + 16 * i) * LD + kk];
+#pragma unroll
+        for (int i = 0; i < NBK; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) upd[i][j] = fma(lrk[i], lck[j], upd[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < NBK; ++i) {
+        const int r = r0 + 16 * i;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const int c = c0 + 16 * j;
+            if (c <= r) sm[r * LD + c] -= upd[i][j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CHOL_NT) chol_block_kernel(double* A, int n, int ld, int J, double* Dinv, int* status,
+                                                             long long* prof = nullptr) {   // prof: optional [40] clock stamps (BOPY_B200_CHOL_PROF)
+    extern __shared__ double sm[];          // [BM][BM+1] working block, rdg[BM] (1 / L_kk), fail flag, w16[16][17], T[64][65]
+    constexpr int LD = BM + 1, PW = CHOL_PANEL, WLD = PW + 1;
     double* const rdg = sm + BM * LD;
     int* const fail = reinterpret_cast<int*>(rdg + BM);
+    double* const w16 = rdg + BM + 2;       // inverse of the panel's 16 x 16 diagonal block, row-major
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, base = J * BM;
     for (int e = tid; e < BM * BM; e += CHOL_NT) {
         const int r = e / BM, c = e - r * BM, gr = base + r, gc = base + c;
@@ -103,91 +262,59 @@ __global__ void __launch_bounds__(CHOL_NT) chol_block_kernel(double* A, int n, i
     }
     if (tid == 0) *fail = 0;
     __syncthreads();
+#define BOPY_CHOL_STAMP(slot)                                      \
+    do {                                                           \
+        if (prof != nullptr && tid == 0) prof[slot] = clock64();   \
+    } while (0)
+    BOPY_CHOL_STAMP(0);
     for (int k0 = 0; k0 < BM; k0 += PW) {
-        // (a) Cholesky of the PW x PW diagonal block in REGISTERS: lane r of warp 0 holds row r, column entries travel
-        //     by shuffles (no shared-memory round trip inside the 16 dependent steps)
-        if (warp == 0) {
-            const int r = lane & (PW - 1);          // lanes 16..31 mirror lanes 0..15 and do not store
-            double a[PW];
-#pragma unroll
-            for (int c = 0; c < PW; ++c) a[c] = c <= r ? sm[(k0 + r) * LD + k0 + c] : 0.0;
-            bool bad = false;
-            double pivot = 1.0;                     // this lane's own diagonal entry L[r][r]
-#pragma unroll
-            for (int k = 0; k < PW; ++k) {
-                const double akk = __shfl_sync(0xffffffffu, a[k], k);
-                bad = bad || !(akk > 0.0);
-                const double lkk = sqrt(akk);
-                if (r == k) a[k] = pivot = lkk;
-                else if (r > k) a[k] = a[k] / lkk;
-#pragma unroll
-                for (int c = k + 1; c < PW; ++c) {
-                    const double lck = __shfl_sync(0xffffffffu, a[k], c);   // L[c][k]
-                    if (r >= c) a[c] = fma(-a[k], lck, a[c]);
-                }
-            }
-            if (bad) {
-                if (lane == 0) *fail = 1;
-            } else if (lane < PW) {
-#pragma unroll
-                for (int c = 0; c < PW; ++c)
-                    if (c <= r) sm[(k0 + r) * LD + k0 + c] = a[c];
-                rdg[k0 + r] = 1.0 / pivot;          // reciprocal of the pivot: the panel rows multiply by it
-            }
-        }
+        // (a) Cholesky of the PW x PW diagonal block in registers, then its inverse
+        if (warp == 0) chol16_factor_and_invert(sm, rdg, w16, fail, k0, lane);
         __syncthreads();
+        BOPY_CHOL_STAMP(1 + 3 * (k0 / PW));
         if (*fail) {
             if (tid == 0) status[0] = J + 1;
             return;
         }
-        // (b) panel rows below the diagonal block: x L16^T = a, one thread per row
-        if (tid < BM && tid >= k0 + PW) {
-            double x[PW];
-#pragma unroll
-            for (int c = 0; c < PW; ++c) {
-                double sacc = sm[tid * LD + k0 + c];
-#pragma unroll
-                for (int k = 0; k < c; ++k) sacc = fma(-x[k], sm[(k0 + c) * LD + k0 + k], sacc);
-                x[c] = sacc * rdg[k0 + c];
-            }
-#pragma unroll
-            for (int c = 0; c < PW; ++c) sm[tid * LD + k0 + c] = x[c];
-        }
-        __syncthreads();
-        // (c) trailing lower triangle -= panel panel^T; thread (ty, tx) owns the (r, c) with (r - t0) % 16 == ty and
-        // (c - t0) % 16 == tx; the 16 rank-1 terms are independent of one another
+        // (b) panel rows below the diagonal block: X = A_panel W^T, X[row][c] = sum_{k <= c} A[row][k] W[c][k];
+        //     thread = (row, 8 of the 16 columns)
         {
-            const int t0 = k0 + PW, c0 = t0 + (tid & 15), r0 = t0 + (tid >> 4);
-            if (t0 < BM) {
-                double upd[8][8];
+            const int row = k0 + PW + (tid >> 1), ch = tid & 1;
+            double x[8];
+            if (row < BM) {
+                double av[PW];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int k = 0; k < PW; ++k) av[k] = sm[row * LD + k0 + k];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) upd[i][j] = 0.0;
-                for (int k = 0; k < PW; ++k) {
-                    const int kk = k0 + k;
-                    double lck[8], lrk[8];
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int c = 8 * ch + cc;
+                    double sacc = 0.0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) lck[j] = (c0 + 16 * j < BM) ? sm[(c0 + 16 * j) * LD + kk] : 0.0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) lrk[i] = (r0 + 16 * i < BM) ? sm[(r0 + 16 * i) * LD + kk] : 0.0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) upd[i][j] = fma(lrk[i], lck[j], upd[i][j]);
+                    for (int k = 0; k < PW; ++k) sacc = fma(av[k], (k <= c) ? w16[c * WLD + k] : 0.0, sacc);
+                    x[cc] = sacc;
                 }
+            }
+            __syncwarp();   // the two threads of a row sit in one warp: both have read the row before either overwrites it
+            if (row < BM) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = r0 + 16 * i;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int c = c0 + 16 * j;
-                        if (r < BM && c <= r) sm[r * LD + c] -= upd[i][j];
-                    }
-                }
+                for (int cc = 0; cc < 8; ++cc) sm[row * LD + k0 + 8 * ch + cc] = x[cc];
             }
         }
         __syncthreads();
+        BOPY_CHOL_STAMP(2 + 3 * (k0 / PW));
+        // (c) trailing lower triangle -= panel panel^T
+        switch ((BM - k0 - PW) / 16) {
+            case 7: chol_trailing_update<7>(sm, k0); break;
+            case 6: chol_trailing_update<6>(sm, k0); break;
+            case 5: chol_trailing_update<5>(sm, k0); break;
+            case 4: chol_trailing_update<4>(sm, k0); break;
+            case 3: chol_trailing_update<3>(sm, k0); break;
+            case 2: chol_trailing_update<2>(sm, k0); break;
+            case 1: chol_trailing_update<1>(sm, k0); break;
+            default: break;
+        }
+        __syncthreads();
+        BOPY_CHOL_STAMP(3 + 3 * (k0 / PW));
     }
     for (int e = tid; e < BM * BM; e += CHOL_NT) {
         const int r = e / BM, c = e - r * BM, gr = base + r, gc = base + c;
@@ -195,17 +322,21 @@ __global__ void __launch_bounds__(CHOL_NT) chol_block_kernel(double* A, int n, i
     }
     if (tid < BM) rdg[tid] = 1.0 / sm[tid * LD + tid];
     __syncthreads();
-    tri_inverse_in_place(sm, rdg);
+    BOPY_CHOL_STAMP(25);
+    tri_inverse_in_place(sm, rdg, w16 + PW * WLD);
+    BOPY_CHOL_STAMP(26);
     double* D = Dinv + (size_t)J * BM * BM;
     for (int e = tid; e < BM * BM; e += CHOL_NT) {
         const int r = e / BM, c = e - r * BM;
         D[e] = c <= r ? sm[c * LD + r] : 0.0;
     }
+    BOPY_CHOL_STAMP(27);
+#undef BOPY_CHOL_STAMP
 }
 
 // Dinv[I] = inv(L_II) for ONE diagonal block of a factor that is already there (the appended row changed block I only)
 __global__ void __launch_bounds__(CHOL_NT) dinv_block_kernel(const double* __restrict__ L, int n, int ld, int I, double* Dinv) {
-    extern __shared__ double sm[];          // [BM][BM+1], then rdg[BM]
+    extern __shared__ double sm[];          // [BM][BM+1], then rdg[BM], ... (chol_smem_bytes(): the layout of chol_block_kernel)
     constexpr int LD = BM + 1;
     double* const rdg = sm + BM * LD;
     const int tid = threadIdx.x, base = I * BM;
@@ -216,7 +347,7 @@ __global__ void __launch_bounds__(CHOL_NT) dinv_block_kernel(const double* __res
     __syncthreads();
     if (tid < BM) rdg[tid] = 1.0 / sm[tid * LD + tid];
     __syncthreads();
-    tri_inverse_in_place(sm, rdg);
+    tri_inverse_in_place(sm, rdg, rdg + BM + 2 + CHOL_PANEL * (CHOL_PANEL + 1));
     double* D = Dinv + (size_t)I * BM * BM;
     for (int e = tid; e < BM * BM; e += CHOL_NT) {
         const int r = e / BM, c = e - r * BM;
