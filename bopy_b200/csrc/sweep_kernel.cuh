@@ -69,30 +69,46 @@ struct SweepParams {
 };
 
 // exp(x) for x <= 0, branch-free so that the 64 evaluations a thread makes per block row interleave instead of
-// serialising on libdevice's special-case branches (the kernel-tile step was latency bound on them).
-// 2^k * exp(r), k = rint(x log2 e) by the 1.5*2^52 trick, r = x - k ln2 (hi/lo), degree-13 Taylor polynomial on
-// |r| <= ln2/2 (truncation 4e-18): <= 2 ulp against np.exp over [-708, 0] (restated in tools/exp_study.py).
-// Below -708 the true value is a denormal < 2.5e-308: returned as 0.  NaN propagates.
+// serialising on libdevice's special-case branches (the kernel-tile step was latency bound on them), and short: the
+// exponentials run on the same FP64 pipe as the DMMAs of the solve (10 FP64 instructions here; the degree-13 Taylor
+// version of round 1 took 25: 13 % of the pipe at n = 256).
+//   x = (64 k + j) ln2/64 + r,  |r| <= ln2/128,  exp(x) = 2^k * T[j] * (1 + q(r)),  T[j] = 2^(j/64) (correctly rounded),
+//   n = 64 k + j = rint(x 64/ln2) by the 1.5*2^52 trick, r = x - n ln2/64 with ln2/64 split hi (32 bits: n hi is exact) + lo,
+//   q = r + r^2 (1/2 + r/6 + r^2 (1/24 + r/120))  (truncation r^6/720 < 3.5e-17),  result = fma(T, q, T) * 2^k.
+// <= 1 ulp against the true exponential on [-708, 0] (T and the final fma are the only roundings that matter), exact at 0
+// (restated in numpy in tools/exp_study.py).  Below -708 the true value is a denormal < 2.5e-308: returned as 0.  NaN propagates.
+static __device__ const double EXP_TABLE_64[64] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951,
+};
 __device__ __forceinline__ double exp_nonpos(double x) {
     const double xc = fmax(x, -708.0);
-    const double t = fma(xc, 1.4426950408889634, 6755399441055744.0);
-    const int k = __double2loint(t);
-    const double kd = t - 6755399441055744.0;
-    double r = fma(kd, -6.93147180369123816490e-01, xc);
-    r = fma(kd, -1.90821492927058770002e-10, r);
-    // degree-13 Taylor polynomial, Estrin's scheme: depth 4 instead of Horner's 14 dependent FMAs
-    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    const double a0 = 1.0 + r;                                                     // 1/0! + r/1!
-    const double a1 = fma(1.6666666666666666e-01, r, 0.5);                         // 1/2! + r/3!
-    const double a2 = fma(8.333333333333333e-03, r, 4.1666666666666664e-02);       // 1/4! + r/5!
-    const double a3 = fma(1.984126984126984e-04, r, 1.388888888888889e-03);        // 1/6! + r/7!
-    const double a4 = fma(2.7557319223985893e-06, r, 2.48015873015873e-05);        // 1/8! + r/9!
-    const double a5 = fma(2.505210838544172e-08, r, 2.755731922398589e-07);        // 1/10! + r/11!
-    const double a6 = fma(1.6059043836821613e-10, r, 2.08767569878681e-09);        // 1/12! + r/13!
-    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
-    const double c0 = fma(b1, r4, b0), c1 = fma(a6, r4, b2);
-    const double p = fma(c1, r8, c0);
-    double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));   // * 2^k, k in [-1022, 0]
+    const double t = fma(xc, 92.33248261689366, 6755399441055744.0);
+    const int n = __double2loint(t);                           // 64 k + j, in [-65372, 0]
+    const double nd = t - 6755399441055744.0;
+    double r = fma(nd, -0.01083042469326756, xc);              // ln2/64, leading 32 bits
+    r = fma(nd, -2.9815858269852933e-12, r);                   // ... and the rest
+    const double r2 = r * r;
+    const double a1 = fma(1.6666666666666666e-01, r, 0.5);
+    const double a2 = fma(8.333333333333333e-03, r, 4.1666666666666664e-02);
+    const double q = fma(fma(a2, r2, a1), r2, r);
+    const double T = __ldg(&EXP_TABLE_64[n & 63]);
+    const double p = fma(T, q, T);                              // in (0.99, 2)
+    double res = __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));   // * 2^k, k in [-1022, 0]
     res = x < -708.0 ? 0.0 : res;
     return x != x ? x : res;
 }
