@@ -752,7 +752,12 @@ int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, 
         if (e == cudaSuccess) e = cudaMemset(gp->probe_flags, 0, nflags * sizeof(unsigned));
         if (e == cudaSuccess)
             e = cudaMalloc(&gp->probe_part, (size_t)gp->probe_max_batch * gp->n_blocks * 2 * PROBE_MAX_NC * sizeof(double));
+        // default switch-over: 4096 = the measured crossover against the one-tile-per-block kernel at n = 2048.  In group mode
+        // the throughput kernel spreads a few tiles over all SMs (its time for small m is one dependency chain of n/128 hops,
+        // ~31 us each), while the latency path serves 32 candidates per 4.4 us hop and group of thread blocks: they meet at
+        // m ~ 225 x (148 / block rows): ~2000 at n = 2048, ~450 at n = 8192 (profiles/r02/latency_small_m.log)
         long long max_m = 4096;
+        if (gp->group_size >= 2) max_m = std::min<long long>(max_m, 225LL * std::max(1, gp->sm_count / gp->n_blocks));
         if (const char* v = std::getenv("BOPY_B200_PROBE_MAX_M")) max_m = std::atoll(v);
         gp->probe_max_m = std::max(0LL, std::min<long long>(max_m, probe_capacity(gp)));
     }

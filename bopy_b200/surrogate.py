@@ -74,7 +74,7 @@ class B200GPSurrogate(Surrogate):
     latency_max_m : int | None
         Calls with at most this many candidates take the latency path of the library (`bopy_gp_set_latency_path`:
         the solve of a small batch is spread over the block rows of L, ~n/128 hops of a few microseconds, instead
-        of one thread block walking all of L).  None keeps the library default (4096); 0 switches it off.
+        of one thread block walking all of L).  None keeps the library default (4096, less where the group-mode sweep overtakes it earlier); 0 switches it off.
     """
 
     def __init__(self, gp, dtype: str = "f64", device=None, device_fit="auto", latency_max_m=None):

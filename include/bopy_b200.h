@@ -164,7 +164,8 @@ int bopy_gp_posterior_acq(bopy_gp* gp, const double* Xs_dev, int64_t m, int acq,
  * Small candidate sets (the reference's own calling pattern: one point per DIRECT probe, bopy/optimizer.py:95-107;
  * a few hundred for plots and fantasies) take a latency path: the forward substitution of one batch of 8-32
  * candidates is spread over the block rows of L, one CTA per block row, instead of one CTA walking all of L.
- * It serves fp64 handles for m <= max_m (default 4096, at most 148*128; 0 switches it off).  Same arithmetic as the
+ * It serves fp64 handles for m <= max_m (default 4096, or the smaller m at which the group-mode sweep overtakes it:
+ * ~2000 at n = 2048, ~450 at n = 8192; at most 148*128; 0 switches it off).  Same arithmetic as the
  * throughput path; the order of a few partial sums differs, so the two agree to rounding (~1e-15), not bit for bit.
  * Writes the limit now in force to effective_out (nullable); fp32 handles always report 0.
  */
