@@ -555,14 +555,27 @@ def run_b200(args):
     probe = None
     if world == 1:
         x1 = np.ascontiguousarray(np.random.default_rng(7).random((1, d)))
-        for _ in range(20):
-            ei(x1)
-        t0 = time.perf_counter()
-        for _ in range(200):
-            ei(x1)
-        probe = {"ms_per_call": 1e3 * (time.perf_counter() - t0) / 200,
-                 "what": "EI(x) through the public API, x a (1, d) numpy array, numpy out ("
-                         + ("latency path: probe_kernel)" if args.dtype == "f64" else "fp32 handles have no latency path: sweep kernel)")}
+
+        def per_call_ms(warm):
+            for _ in range(warm):
+                ei(x1)
+            t0 = time.perf_counter()
+            for _ in range(200):
+                ei(x1)
+            return 1e3 * (time.perf_counter() - t0) / 200
+        if args.dtype == "f64":
+            native.set_inverse_path(0)
+            chained = per_call_ms(20)
+            served = native.set_inverse_path(-1)          # the library default: W = L^-1 from the 32nd probe of a state on
+            probe = {"ms_per_call": per_call_ms(40), "ms_per_call_chained": chained,
+                     "what": "EI(x) through the public API, x a (1, d) numpy array, numpy out, library defaults: after 32 "
+                             "probes of one state a call is ONE matrix-vector product with W = L^-1 (probe_inv_kernel"
+                             + (")" if served >= 1 else " -- not available on this handle)")
+                             + "; ms_per_call_chained: the same call on probe_kernel (n/128 dependent hops)"}
+        else:
+            probe = {"ms_per_call": per_call_ms(20),
+                     "what": "EI(x) through the public API, x a (1, d) numpy array, numpy out (fp32 handles have no "
+                             "latency path: sweep kernel)"}
 
     # opt-in branch and bound for the same arg-min (not part of `value`: most candidates skip the full posterior)
     pruned = None

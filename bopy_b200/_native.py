@@ -39,6 +39,7 @@ _SIGNATURES = {
                                       c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "bopy_gp_probe_trace": (c_int, [c_void_p, POINTER(c_int64)]),
     "bopy_gp_set_latency_path": (c_int, [c_void_p, c_int64, POINTER(c_int64)]),
+    "bopy_gp_set_inverse_path": (c_int, [c_void_p, c_int, POINTER(c_int64)]),
     "bopy_gp_set_group_mode": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int)]),
     "bopy_group_schedule": (c_int, [c_int64, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "bopy_acq_value_and_grad": (c_int, [c_void_p, c_int, c_double, c_double, c_void_p, c_int64, c_void_p, c_void_p,
@@ -300,6 +301,14 @@ class NativeGP:
         Returns the limit in force (0 for fp32 handles)."""
         eff = c_int64()
         check(self.lib.bopy_gp_set_latency_path(self._handle, int(max_m), byref(eff)), "bopy_gp_set_latency_path")
+        return eff.value
+
+    def set_inverse_path(self, mode=-1):
+        """Calls of a handful of candidates as one product with W = L^-1 (probe_inv_kernel): -1 = W is built at the
+        max(32, block rows^2 / 8)-th such call on one state (default), 1 = at the first, 0 = never.  Returns the number of candidates per call that
+        path serves on the current state (0 = none)."""
+        eff = c_int64()
+        check(self.lib.bopy_gp_set_inverse_path(self._handle, int(mode), byref(eff)), "bopy_gp_set_inverse_path")
         return eff.value
 
     def set_group_mode(self, group_size=-1, slots=-1, lead=-1):

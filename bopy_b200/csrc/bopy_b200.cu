@@ -17,6 +17,7 @@
 #include "fit_kernels.cuh"
 #include "grad_kernel.cuh"
 #include "minloc_comm.cuh"
+#include "probe_inv_kernel.cuh"
 #include "probe_kernel.cuh"
 #include "prune_kernels.cuh"
 #include "small_kernel.cuh"
@@ -90,6 +91,16 @@ struct bopy_gp {
     double* Lfull = nullptr;
     bool Lfull_valid = false;
     double alpha_reg = 0.0;            // the jitter the kept factor was built with
+    bool Lfull_factor = false;         // Lfull holds the CURRENT factor (kept by the fit, or copied by bopy_gp_set_state)
+    // inverse path (probe_inv_kernel.cuh): W = L^-1 for calls of <= inv_max_m candidates on a state that is probed often
+    int inv_mode = -1;                 // -1 auto (W is built at the inv_auto_calls()-th small call on a state), 0 off, 1 on
+    long long inv_max_m = 0;           // 0: this handle has no inverse path
+    double* Winv = nullptr;            // [n_pad][n_pad]
+    bool Winv_valid = false;
+    int inv_small_calls = 0;           // small calls since the state last changed
+    double* inv_part = nullptr;        // [sm_count][INV_MAX_NC]
+    unsigned* inv_ticket = nullptr;
+    unsigned inv_ticket_base = 0;
     // staging of the host-buffer entry point (small calls: one point per DIRECT probe)
     double* host_x = nullptr;          // [HOST_CALL_MAX_M][d]
     double* host_out = nullptr;        // [3][HOST_CALL_MAX_M]: acq / mean / var
@@ -421,6 +432,121 @@ int launch_probe(bopy_gp* gp, const ProbePlan& pl, const double* Xs, long long m
     return rc;
 }
 
+// ---- inverse path (probe_inv_kernel.cuh): calls of a handful of candidates on a state that is probed often -----------
+// auto mode: W = L^-1 is built at the k-th small call on one state, k = max(32, block rows^2 / 8) -- about where the chained
+// calls made so far have cost what the build costs (4.1 ms against 0.105 ms per call at n = 2048, 139 ms against 0.33 ms at
+// n = 8192: profiles/r02/latency_small_m.log), so that a state that is probed less often never pays more than twice
+int inv_auto_calls(const bopy_gp* gp) { return std::max(32, gp->n_blocks * gp->n_blocks / 8); }
+constexpr int INV_MAX_NPAD = 8192;                  // W and the kept factor are n_pad^2 doubles each (512 MB at 8192)
+constexpr size_t INV_SMEM_BUDGET = (size_t)200 << 10;
+
+// most candidates one inverse-path call can hold on this handle: K* of the call lives in shared memory ([nc][n_pad])
+long long inv_capacity(const bopy_gp* gp) {
+    if (!gp->probe_capable || gp->n_pad > INV_MAX_NPAD) return 0;
+    if (gp->small_n && gp->n_pad == BM && gp->n <= SMALL_N_MAX) return 0;   // served by small_n_kernel
+    for (int nc = INV_MAX_NC; nc >= 1; nc >>= 1)
+        if (inv_smem_bytes(nc, gp->n_pad, gp->d) <= INV_SMEM_BUDGET) return nc;
+    return 0;
+}
+
+bool inv_applies(const bopy_gp* gp, long long m, int slot_per_tile, const MinLoc* tile_records) {
+    return gp->inv_mode != 0 && m <= gp->inv_max_m && gp->Lfull_factor && probe_applies(gp, m, slot_per_tile, tile_records);
+}
+
+// every change of the fitted state: W no longer matches, the count of small calls starts again
+void state_changed(bopy_gp* gp) {
+    gp->Winv_valid = false;
+    gp->inv_small_calls = 0;
+}
+
+// W = L^-1 by blocked TRTRI on the kept factor: diagonal blocks = Dinv, then one block diagonal at a time
+// (W_IJ = -Dinv_I sum_{K=J}^{I-1} L_IK W_KJ), on the fit's DMMA tile kernel
+int build_linv(bopy_gp* gp, cudaStream_t st) {
+    const int nb = gp->n_blocks, np = gp->n_pad;
+    if (gp->inv_ticket == nullptr) {
+        if (gp->Winv == nullptr) {
+            CUDA_TRY(cudaMalloc(&gp->Winv, (size_t)np * np * sizeof(double)));
+            CUDA_TRY(cudaMemsetAsync(gp->Winv, 0, (size_t)np * np * sizeof(double), st));   // the upper blocks stay 0
+        }
+        if (gp->inv_part == nullptr) CUDA_TRY(cudaMalloc(&gp->inv_part, (size_t)gp->sm_count * INV_MAX_NC * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&gp->inv_ticket, sizeof(unsigned)));
+        CUDA_TRY(cudaMemsetAsync(gp->inv_ticket, 0, sizeof(unsigned), st));
+        gp->inv_ticket_base = 0;
+    }
+    copy_diag_blocks_kernel<<<nb, 256, 0, st>>>(gp->Dinv, gp->Winv, np);
+    for (int delta = 1; delta < nb; ++delta) {
+        tile_gemm_kernel<<<nb - delta, NT, 0, st>>>(0, nb, delta, gp->Lfull, gp->Winv, gp->Dinv, nullptr, np);
+        tile_gemm_kernel<<<nb - delta, NT, 0, st>>>(1, nb, delta, gp->Lfull, gp->Winv, gp->Dinv, nullptr, np);
+    }
+    CUDA_TRY(cudaGetLastError());
+    gp->Winv_valid = true;
+    return BOPY_OK;
+}
+
+template <int NC, int KIND> int launch_inv_t(const InvParams& q, int grid, size_t smem, cudaStream_t st) {
+    CUDA_TRY(cudaFuncSetAttribute(probe_inv_kernel<NC, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    probe_inv_kernel<NC, KIND><<<grid, INV_NT, smem, st>>>(q);
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
+template <int NC> int launch_inv_k(int kernel, const InvParams& q, int grid, size_t smem, cudaStream_t st) {
+    switch (kernel) {
+        case BOPY_KERNEL_RBF: return launch_inv_t<NC, K_RBF>(q, grid, smem, st);
+        case BOPY_KERNEL_MATERN12: return launch_inv_t<NC, K_M12>(q, grid, smem, st);
+        case BOPY_KERNEL_MATERN32: return launch_inv_t<NC, K_M32>(q, grid, smem, st);
+        case BOPY_KERNEL_MATERN52: return launch_inv_t<NC, K_M52>(q, grid, smem, st);
+    }
+    return fail(BOPY_ERR_BAD_ARG, "unknown kernel id %d", kernel);
+}
+
+int inv_grid(const bopy_gp* gp) {
+    return (int)std::min<long long>(gp->sm_count, (gp->n + INV_WARPS - 1) / INV_WARPS);
+}
+
+// one launch of the inverse path over m <= inv_max_m candidates (W must be valid)
+int launch_inv(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, double kappa, double* mean_out,
+               double* var_out, double* acq_out, long long index_base, double* min_val, long long* min_idx,
+               cudaStream_t st) {
+    InvParams q;
+    std::memset(&q, 0, sizeof(q));
+    q.W = gp->Winv;
+    q.Xt = gp->Xt;
+    q.Xs = Xs;
+    q.m = (int)m;
+    q.n = (int)gp->n;
+    q.n_blocks = gp->n_blocks;
+    q.d = gp->d;
+    for (int k = 0; k < gp->d; ++k) q.ls[k] = gp->ls[k];
+    q.amp = gp->amp;
+    q.kss = gp->amp + gp->noise;
+    q.y_mean = gp->y_mean;
+    q.y_std = gp->y_std;
+    q.y_var = gp->y_std * gp->y_std;
+    q.acq = acq;
+    q.eta = eta;
+    q.kappa = kappa;
+    q.mean_out = mean_out;
+    q.var_out = var_out;
+    q.acq_out = acq_out;
+    q.index_base = index_base;
+    q.nan_skip = gp->nan_skip;
+    q.min_val = min_val;
+    q.min_idx = min_idx;
+    q.part = gp->inv_part;
+    q.ticket = gp->inv_ticket;
+    q.ticket_base = gp->inv_ticket_base;
+    const int grid = inv_grid(gp);
+    const int nc = m <= 1 ? 1 : (m <= 2 ? 2 : (m <= 4 ? 4 : 8));
+    const size_t smem = inv_smem_bytes(nc, gp->n_pad, gp->d);
+    const int rc = nc == 1 ? launch_inv_k<1>(gp->kernel, q, grid, smem, st)
+                           : (nc == 2 ? launch_inv_k<2>(gp->kernel, q, grid, smem, st)
+                                      : (nc == 4 ? launch_inv_k<4>(gp->kernel, q, grid, smem, st)
+                                                 : launch_inv_k<8>(gp->kernel, q, grid, smem, st)));
+    if (rc == BOPY_OK) gp->inv_ticket_base += (unsigned)grid;
+    return rc;
+}
+
 template <int NA, int KIND> int launch_grad_t(const GradParams& p, int grid, cudaStream_t st) {
     const size_t smem = grad_smem_bytes<NA>(p.d);
     CUDA_TRY(cudaFuncSetAttribute(grad_kernel<NA, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -629,6 +755,17 @@ int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, d
         }
         return BOPY_OK;
     }
+    if (allow_probe && inv_applies(gp, m, slot_per_tile, tile_records)) {
+        // a handful of candidates on a state that is probed often: one matrix-vector product with W = L^-1
+        bool use = gp->Winv_valid;
+        if (!use && (gp->inv_mode == 1 || ++gp->inv_small_calls >= inv_auto_calls(gp))) {
+            const int rc = build_linv(gp, st);
+            if (rc != BOPY_OK) return rc;
+            use = true;
+        }
+        if (use)
+            return launch_inv(gp, Xs, m, acq, eta, kappa, mean_out, var_out, acq_out, index_base, min_val, min_idx, st);
+    }
     if (allow_probe && probe_applies(gp, m, slot_per_tile, tile_records)) {
         // small m: latency path, the forward substitution spread over the block rows of L (probe_kernel.cuh)
         const ProbePlan pl = probe_plan(gp, m);
@@ -760,6 +897,8 @@ int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, 
         if (gp->group_size >= 2) max_m = std::min<long long>(max_m, 225LL * std::max(1, gp->sm_count / gp->n_blocks));
         if (const char* v = std::getenv("BOPY_B200_PROBE_MAX_M")) max_m = std::atoll(v);
         gp->probe_max_m = std::max(0LL, std::min<long long>(max_m, probe_capacity(gp)));
+        gp->inv_max_m = inv_capacity(gp);
+        gp->inv_mode = std::max(-1, std::min(1, env_int("BOPY_B200_INVERSE_PATH", -1)));
     }
     if (e != cudaSuccess) {
         bopy_gp_destroy(gp);
@@ -788,6 +927,9 @@ void bopy_gp_destroy(bopy_gp* gp) {
     cudaFree(gp->host_x);
     cudaFree(gp->host_out);
     cudaFree(gp->Lfull);
+    cudaFree(gp->Winv);
+    cudaFree(gp->inv_part);
+    cudaFree(gp->inv_ticket);
     cudaFree(gp->gctl);
     cudaFree(gp->gpart);
     delete gp;
@@ -966,13 +1108,26 @@ int bopy_gp_set_state(bopy_gp* gp, const double* X_dev, const double* L_dev, con
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaSetDevice(gp->device));
     gp->ready = false;
+    state_changed(gp);
+    gp->Lfull_valid = false;   // bopy_gp_append needs a factor of the library's own fit (its jitter is known)
+    gp->Lfull_factor = false;
     const LsParam ls = store_hyper(gp, length_scale_host, n_ls, amplitude, noise_level, y_mean, y_std);
     dinv_kernel<<<gp->n_blocks, BM, 0, st>>>(L_dev, (int)gp->n, (int)gp->n, gp->Dinv);
     CUDA_TRY(cudaGetLastError());
     rc = pack_state(gp, X_dev, L_dev, (int)gp->n, alpha_dev, ls, st);
     if (rc != BOPY_OK) return rc;
+    if (gp->inv_max_m > 0 && gp->inv_mode != 0) {
+        // the inverse path builds W = L^-1 from the row-major factor: keep a copy (rows beyond n are never read)
+        const size_t ld = (size_t)gp->n_pad, n = (size_t)gp->n;
+        if (gp->Lfull == nullptr) {
+            CUDA_TRY(cudaMalloc(&gp->Lfull, ld * ld * sizeof(double)));
+            CUDA_TRY(cudaMemsetAsync(gp->Lfull, 0, ld * ld * sizeof(double), st));
+        }
+        CUDA_TRY(cudaMemcpy2DAsync(gp->Lfull, ld * sizeof(double), L_dev, n * sizeof(double), n * sizeof(double), n,
+                                   cudaMemcpyDeviceToDevice, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
-    gp->Lfull_valid = false;   // the caller's factor was packed, not kept
+    gp->Lfull_factor = gp->inv_max_m > 0 && gp->inv_mode != 0;
     gp->ready = true;
     return BOPY_OK;
 }
@@ -988,6 +1143,8 @@ int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const do
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaSetDevice(gp->device));
     gp->ready = false;
+    state_changed(gp);
+    gp->Lfull_factor = false;
     const LsParam ls = store_hyper(gp, length_scale_host, n_ls, amplitude, noise_level, y_mean, y_std);
     const int n = (int)gp->n, nb = gp->n_blocks;
     // the working matrix is the handle's own n_pad x n_pad factor (kept for bopy_gp_append); scratch: z (n_pad),
@@ -1037,6 +1194,7 @@ int bopy_gp_fit(bopy_gp* gp, const double* X_dev, const double* yn_dev, const do
                     "K + alpha I is not positive definite (non-positive pivot in block column %d); increase alpha",
                     host_status - 1);
     gp->Lfull_valid = true;
+    gp->Lfull_factor = true;
     gp->alpha_reg = alpha_reg;
     gp->ready = true;
     return BOPY_OK;
@@ -1064,6 +1222,7 @@ int bopy_gp_append(bopy_gp* gp, const double* X_dev, const double* yn_dev, doubl
     cudaMemsetAsync(status, 0, sizeof(int), st);
     // 1. v = L^-1 k(X, x_new): the latency path's forward solve of the new point against the CURRENT state
     gp->ready = false;
+    state_changed(gp);
     rc = launch_probe(gp, probe_plan(gp, 1), X_dev + (size_t)n * gp->d, 1, BOPY_ACQ_NONE, 0.0, 0.0, nullptr, nullptr, nullptr, 0,
                       nullptr, 1, st);
     if (rc != BOPY_OK) {
@@ -1092,6 +1251,7 @@ int bopy_gp_append(bopy_gp* gp, const double* X_dev, const double* yn_dev, doubl
     cudaFreeAsync(scratch, st);
     if (rc != BOPY_OK || e != cudaSuccess || host_status != 0) {
         gp->Lfull_valid = false;   // row n was written: only a refit restores a consistent state
+        gp->Lfull_factor = false;
         if (rc != BOPY_OK) return rc;
         if (e != cudaSuccess) return fail(BOPY_ERR_CUDA, "bopy_gp_append failed: %s", cudaGetErrorString(e));
         return fail(BOPY_ERR_NOT_POSITIVE_DEFINITE, "the grown K + alpha I is not positive definite (new pivot <= 0)");
@@ -1120,6 +1280,7 @@ int bopy_gp_truncate(bopy_gp* gp, int64_t n_new, const double* X_dev, const doub
     // the factor of the first n_new points is the leading block of the kept factor: only the padding of the last
     // diagonal block, the targets and their normalisation change
     gp->ready = false;
+    state_changed(gp);
     gp->n = n_new;
     gp->y_mean = y_mean;
     gp->y_std = y_std;
@@ -1136,6 +1297,7 @@ int bopy_gp_truncate(bopy_gp* gp, int64_t n_new, const double* X_dev, const doub
     if (scratch) cudaFreeAsync(scratch, st);
     if (rc != BOPY_OK || e != cudaSuccess) {
         gp->Lfull_valid = false;
+        gp->Lfull_factor = false;
         return rc != BOPY_OK ? rc : fail(BOPY_ERR_CUDA, "bopy_gp_truncate failed: %s", cudaGetErrorString(e));
     }
     gp->ready = true;
@@ -1235,8 +1397,10 @@ int bopy_gp_posterior_acq(bopy_gp* gp, const double* Xs_dev, int64_t m, int acq,
 }
 
 int bopy_gp_resize(bopy_gp* gp, int64_t n) {
-    if (gp != nullptr) gp->Lfull_valid = false;
     if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    gp->Lfull_valid = false;
+    gp->Lfull_factor = false;
+    state_changed(gp);
     if (n < 1 || (n + BM - 1) / BM != gp->n_blocks)
         return fail(BOPY_ERR_BAD_ARG, "n = %lld does not fit this handle's %d block rows of %d (create a new handle)",
                     (long long)n, gp->n_blocks, BM);
@@ -1293,6 +1457,15 @@ int bopy_gp_set_latency_path(bopy_gp* gp, int64_t max_m, int64_t* effective_out)
     if (max_m < 0) return fail(BOPY_ERR_BAD_ARG, "max_m must be >= 0 (got %lld)", (long long)max_m);
     gp->probe_max_m = gp->probe_capable ? std::min<long long>(max_m, probe_capacity(gp)) : 0;
     if (effective_out) *effective_out = gp->probe_max_m;
+    return BOPY_OK;
+}
+
+int bopy_gp_set_inverse_path(bopy_gp* gp, int mode, int64_t* max_m_out) {
+    if (gp == nullptr) return fail(BOPY_ERR_BAD_ARG, "gp handle is NULL");
+    if (mode < -1 || mode > 1) return fail(BOPY_ERR_BAD_ARG, "mode must be -1 (auto), 0 (off) or 1 (on) (got %d)", mode);
+    gp->inv_mode = mode;
+    gp->inv_small_calls = 0;
+    if (max_m_out) *max_m_out = (mode != 0 && gp->Lfull_factor) ? std::min(gp->inv_max_m, gp->probe_max_m) : 0;
     return BOPY_OK;
 }
 
@@ -1894,6 +2067,11 @@ int bopy_gp_launch_info(const bopy_gp* gp, int64_t m, int* grid_out, int* launch
     const long long ntiles = (m + BN - 1) / BN;
     if (small_applies(gp, 0)) {
         if (grid_out) *grid_out = small_grid(gp, m);
+    } else if (inv_applies(gp, m, 0, nullptr) && (gp->Winv_valid || gp->inv_mode == 1)) {
+        if (grid_out) *grid_out = inv_grid(gp);
+        if (launches_out) *launches_out = 1;  // probe_inv_kernel finishes the call itself
+        if (workspace_bytes_out) *workspace_bytes_out = 0;
+        return BOPY_OK;
     } else if (probe_applies(gp, m, 0, nullptr)) {
         if (grid_out) *grid_out = probe_plan(gp, m).grid;
     } else if (warp_applies(gp, 0)) {

@@ -75,9 +75,16 @@ class B200GPSurrogate(Surrogate):
         Calls with at most this many candidates take the latency path of the library (`bopy_gp_set_latency_path`:
         the solve of a small batch is spread over the block rows of L, ~n/128 hops of a few microseconds, instead
         of one thread block walking all of L).  None keeps the library default (4096, less where the group-mode sweep overtakes it earlier); 0 switches it off.
+    inverse_path : 'auto' | bool
+        Calls of a handful of candidates (DIRECT probes the acquisition ONE point per call, thousands of times per
+        trial, `bopy/optimizer.py:95-107`) as one matrix-vector product with W = L^-1 (`bopy_gp_set_inverse_path`).
+        'auto' (the library default) builds W at the k-th such call on one fitted state (k = 32 up to n = 2048, 512 at
+        n = 8192: where the chained calls so far have cost what the build costs), True at the first, False never.
+        The paths agree to rounding, not bit for bit: with False a candidate's value never depends on how many
+        calls came before it.
     """
 
-    def __init__(self, gp, dtype: str = "f64", device=None, device_fit="auto", latency_max_m=None):
+    def __init__(self, gp, dtype: str = "f64", device=None, device_fit="auto", latency_max_m=None, inverse_path="auto"):
         super().__init__()
         if dtype not in ("f64", "f32"):
             raise ValueError("dtype must be 'f64' or 'f32'")
@@ -86,6 +93,9 @@ class B200GPSurrogate(Surrogate):
         self.device = device
         self.device_fit = device_fit
         self.latency_max_m = latency_max_m
+        if inverse_path not in ("auto", True, False):
+            raise ValueError("inverse_path must be 'auto', True or False")
+        self.inverse_path = inverse_path
         self.native = None          # _native.NativeGP once fitted
         self.kernel_spec = None
         self.fitted_on_device = False
@@ -155,6 +165,8 @@ class B200GPSurrogate(Surrogate):
             self.native = _native.NativeGP(n, d, kernel=kernel, dtype=self.dtype, device=self.device)
             if getattr(self, "latency_max_m", None) is not None:
                 self.native.set_latency_path(self.latency_max_m)
+            if getattr(self, "inverse_path", "auto") != "auto":
+                self.native.set_inverse_path(1 if self.inverse_path else 0)
         return self.native
 
     def _fit_on_device(self, x: np.ndarray, y: np.ndarray) -> None:

@@ -128,7 +128,7 @@ def test_direct_style_single_point_probes_through_the_public_api():
     y = np.sin(4 * X[:, 0]) + X[:, 1] ** 2 - X[:, 2]
     gp = GaussianProcessRegressor(kernel=ConstantKernel(1.3) * RBF([0.3, 0.4, 0.5]), alpha=1e-6, normalize_y=True,
                                   optimizer=None)
-    sur = B200GPSurrogate(gp, device_fit=False)
+    sur = B200GPSurrogate(gp, device_fit=False, inverse_path=False)   # every probe on probe_kernel (bit-for-bit check below)
     sur.fit(X, y)
     ei = EI(sur)
     ei.fit(X, y)

@@ -33,9 +33,12 @@ DTYPE_PATHS = [("f64", "latency"), ("f64", "sweep"), ("f32", "sweep")]
 
 
 def select_path(gp, path):
+    """"inverse": calls of a handful of candidates go to probe_inv_kernel (W = L^-1 built at the first one), larger ones to
+    probe_kernel; "latency": probe_kernel for every m, whatever the number of calls before."""
     eff = gp.set_latency_path(0 if path == "sweep" else 1 << 30)
-    if path == "latency":
+    if path in ("latency", "inverse"):
         assert eff >= 4096
+    gp.set_inverse_path(1 if path == "inverse" else 0)
     return gp
 
 

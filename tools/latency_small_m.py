@@ -54,11 +54,24 @@ def main():
         host = bench.make_problem(n, d)[2].fit(X, y)
         eta = float(y.min())
         rng = np.random.default_rng(0)
+        import torch
+        sur.native.set_latency_path(1 << 30)
+        if sur.native.set_inverse_path(1) >= 1:
+            x1 = rng.random((1, d))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ei(x1)
+            print(f"n={n:5d} d={d:2d}: first probe in mode 1 (builds W = L^-1 by blocked TRTRI, then probes): "
+                  f"{1e3 * (time.perf_counter() - t0):.3f} ms", flush=True)
         for m in ms:
             xs = rng.random((m, d))
             xd = sur.native.candidates(xs)
             reps = 50 if m <= 1024 else 10
             sur.native.set_latency_path(1 << 30)
+            t_inv_api = t_inv_dev = float("nan")
+            if m <= sur.native.set_inverse_path(1):     # W = L^-1 (probe_inv_kernel), built at the first call
+                t_inv_api, t_inv_dev = api_ms(ei, xs, reps), device_ms(sur.native, xd, eta, reps)
+            sur.native.set_inverse_path(0)
             t_lat_api, t_lat_dev = api_ms(ei, xs, reps), device_ms(sur.native, xd, eta, reps)
             sur.native.set_latency_path(0)
             t_swp_api, t_swp_dev = api_ms(ei, xs, reps), device_ms(sur.native, xd, eta, reps)
@@ -72,9 +85,10 @@ def main():
                         for s in range(0, m, 64):
                             R.ei(host, xs[s:s + 64], eta)
                     t_ref = 1e3 * (time.perf_counter() - t0) / 3
-            rows.append(dict(n=n, d=d, m=m, latency_api_ms=t_lat_api, latency_dev_ms=t_lat_dev, sweep_api_ms=t_swp_api,
+            rows.append(dict(n=n, d=d, m=m, inverse_api_ms=t_inv_api, inverse_dev_ms=t_inv_dev, latency_api_ms=t_lat_api, latency_dev_ms=t_lat_dev, sweep_api_ms=t_swp_api,
                              sweep_dev_ms=t_swp_dev, reference_ms=t_ref))
-            print(f"n={n:5d} d={d:2d} m={m:5d}: latency path {t_lat_api:8.3f} ms/call (device {t_lat_dev:7.3f})   "
+            print(f"n={n:5d} d={d:2d} m={m:5d}: inverse path {t_inv_api:8.3f} ms/call (device {t_inv_dev:7.3f})   "
+                  f"latency path {t_lat_api:8.3f} (device {t_lat_dev:7.3f})   "
                   f"throughput path {t_swp_api:8.3f} (device {t_swp_dev:7.3f})   reference {t_ref:8.3f}", flush=True)
     print(json.dumps(rows))
 
