@@ -13,7 +13,7 @@
 // is one launch whose length is the longest row (n/64 coalesced 512-byte loads per warp, 16 MB out of L2 at
 // n = 2048).  The explicit inverse is only ever multiplied from the left against k* in fp64; its forward error is the
 // same cond(L) eps as the substitution's (measured on every golden set: <= 0.3 of the 1e-9 parity bound at
-// cond(L) = 1.3e5, 3e-4 of it on the BASELINE configs, tools/numerics_study.py).  K*, the de-normalisation and the
+// cond(L) = 1.3e5, 3e-4 of it on the BASELINE configs: tools/inverse_path_study.py, profiles/r02/inverse_path_numerics.log).  K*, the de-normalisation and the
 // acquisition are the code of the other two paths (base_kernel, acquisition_value); only the order in which the n
 // products meet differs, so the paths agree to rounding, not bit for bit.  A candidate's value does not depend on m
 // or on its position in the call: rows are dealt to warps by (row, grid) alone.

@@ -295,7 +295,19 @@ class DirectOptimizer(Optimizer):
         def objective(point):
             return float(self.acquisition_function(np.asarray(point, dtype=np.float64).reshape(1, -1))[0])
 
-        res = direct(objective, bounds=list(zip(self.bounds.lowers, self.bounds.uppers)), **kwargs)
+        # DIRECT probes ONE point per call, `maxfun` times on one fitted state: with a budget well beyond the point where
+        # the library would switch by itself, build W = L^-1 at the first probe (bopy_gp_set_inverse_path)
+        surrogate = getattr(self.acquisition_function, "surrogate", None)
+        native = getattr(surrogate, "native", None)
+        eager = (native is not None and getattr(surrogate, "inverse_path", None) == "auto"
+                 and kwargs["maxfun"] >= 8 * max(32, ((native.n + 127) // 128) ** 2 // 8))
+        if eager:
+            native.set_inverse_path(1)
+        try:
+            res = direct(objective, bounds=list(zip(self.bounds.lowers, self.bounds.uppers)), **kwargs)
+        finally:
+            if eager:
+                native.set_inverse_path(-1)
         return np.array([res.x]), np.array([res.fun])
 
 

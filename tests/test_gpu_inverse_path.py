@@ -194,3 +194,31 @@ def test_default_surrogate_serves_direct_style_probes_from_w():
         np.testing.assert_allclose(got[mode], want, rtol=1e-6, atol=1e-9 * np.ptp(want))
     assert np.array_equal(got["auto"][:31], got[False][:31])      # probe_kernel until W exists ...
     assert np.array_equal(got["auto"][31:], got[True][31:])       # ... probe_inv_kernel from the 32nd probe on
+
+
+def test_direct_builds_w_at_its_first_probe_when_its_budget_is_large():
+    """DirectOptimizer (bopy/optimizer.py:70-107) knows its probe budget: with maxf well beyond the library's own
+    switch-over it asks for W = L^-1 at the first probe; the optimum is the one the chained path finds."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel
+
+    from bopy_b200.acquisition import LCB
+    from bopy_b200.bounds import Bound, Bounds
+    from bopy_b200.optimizer import DirectOptimizer
+    from bopy_b200.surrogate import B200GPSurrogate
+    rng = np.random.default_rng(5)
+    X = rng.random((200, 2))
+    y = np.sin(5 * X[:, 0]) * np.cos(3 * X[:, 1])
+    bounds = Bounds([Bound(0.0, 1.0), Bound(0.0, 1.0)])
+    found = {}
+    for mode in ("auto", False):
+        gp = GaussianProcessRegressor(kernel=ConstantKernel(1.0) * RBF([0.2, 0.2]), alpha=1e-6, normalize_y=True, optimizer=None)
+        sur = B200GPSurrogate(gp, inverse_path=mode)
+        sur.fit(X, y)
+        acq = LCB(sur, kappa=2.0)
+        acq.fit(X, y)
+        res = DirectOptimizer(acq, bounds, maxf=400).optimize()
+        found[mode] = (res.x_min, res.f_min, sur.native.launch_info(1)["launches"])
+    assert found["auto"][2] == 1 and found[False][2] == 2      # probe_inv_kernel alone / probe_kernel + the arg-min finalize
+    np.testing.assert_allclose(found["auto"][1], found[False][1], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(found["auto"][0], found[False][0], atol=1e-6)
