@@ -566,9 +566,9 @@ def run_b200(args):
         if args.dtype == "f64":
             native.set_inverse_path(0)
             chained = per_call_ms(20)
-            served = native.set_inverse_path(-1)          # the library default: W = L^-1 from the 32nd probe of a state on
+            served = native.set_inverse_path(-1)          # the library default: W = L^-1 from the 16th probe of a state on
             probe = {"ms_per_call": per_call_ms(40), "ms_per_call_chained": chained,
-                     "what": "EI(x) through the public API, x a (1, d) numpy array, numpy out, library defaults: after 32 "
+                     "what": "EI(x) through the public API, x a (1, d) numpy array, numpy out, library defaults: after 16 "
                              "probes of one state a call is ONE matrix-vector product with W = L^-1 (probe_inv_kernel"
                              + (")" if served >= 1 else " -- not available on this handle)")
                              + "; ms_per_call_chained: the same call on probe_kernel (n/128 dependent hops)"}

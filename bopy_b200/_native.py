@@ -304,8 +304,8 @@ class NativeGP:
         return eff.value
 
     def set_inverse_path(self, mode=-1):
-        """Calls of a handful of candidates as one product with W = L^-1 (probe_inv_kernel): -1 = W is built at the
-        max(32, block rows^2 / 8)-th such call on one state (default), 1 = at the first, 0 = never.  Returns the number of candidates per call that
+        """Calls of a handful of candidates as one product with W = L^-1 (probe_inv_kernel): -1 = W is built at the 16th
+        such call on one state (default), 1 = at the first, 0 = never.  Returns the number of candidates per call that
         path serves on the current state (0 = none)."""
         eff = c_int64()
         check(self.lib.bopy_gp_set_inverse_path(self._handle, int(mode), byref(eff)), "bopy_gp_set_inverse_path")

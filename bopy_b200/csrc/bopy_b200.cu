@@ -432,11 +432,38 @@ int launch_probe(bopy_gp* gp, const ProbePlan& pl, const double* Xs, long long m
     return rc;
 }
 
+// W = L^-1 (lower triangular, row-major, leading dimension ld = nb * 128; diagonal blocks = Dinv).  Default: the recursive
+// 2 x 2 block inversion on tile_gemm_async_kernel (two launches per level, log2(nb) levels; the strict upper block triangle
+// of W is its scratch).  BOPY_B200_TRTRI=diagonal: one block diagonal at a time on tile_gemm_kernel (round-2's first
+// version, for A/B runs: 4.1 ms at n = 2048, 139 ms at n = 8192).
+bool trtri_by_diagonals() {
+    const char* v = std::getenv("BOPY_B200_TRTRI");
+    return v != nullptr && std::strcmp(v, "diagonal") == 0;
+}
+int launch_trtri(const double* L, double* W, const double* Dinv, int nb, int ld, cudaStream_t st) {
+    copy_diag_blocks_kernel<<<nb, 256, 0, st>>>(Dinv, W, ld);
+    if (trtri_by_diagonals()) {
+        for (int delta = 1; delta < nb; ++delta) {
+            tile_gemm_kernel<<<nb - delta, NT, 0, st>>>(0, nb, delta, L, W, Dinv, nullptr, ld);
+            tile_gemm_kernel<<<nb - delta, NT, 0, st>>>(1, nb, delta, L, W, Dinv, nullptr, ld);
+        }
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(tile_gemm_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_BYTES));
+        for (int h = 1; h < nb; h *= 2) {
+            const int grid = ((nb + 2 * h - 1) / (2 * h)) * h * h;
+            tile_gemm_async_kernel<<<grid, NT, TG_SMEM_BYTES, st>>>(1, nb, h, L, W, nullptr, ld);
+            tile_gemm_async_kernel<<<grid, NT, TG_SMEM_BYTES, st>>>(2, nb, h, L, W, nullptr, ld);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return BOPY_OK;
+}
+
 // ---- inverse path (probe_inv_kernel.cuh): calls of a handful of candidates on a state that is probed often -----------
-// auto mode: W = L^-1 is built at the k-th small call on one state, k = max(32, block rows^2 / 8) -- about where the chained
-// calls made so far have cost what the build costs (4.1 ms against 0.105 ms per call at n = 2048, 139 ms against 0.33 ms at
-// n = 8192: profiles/r02/latency_small_m.log), so that a state that is probed less often never pays more than twice
-int inv_auto_calls(const bopy_gp* gp) { return std::max(32, gp->n_blocks * gp->n_blocks / 8); }
+// auto mode: W = L^-1 is built at the 16th small call on one state.  The build costs what 6 chained calls cost at n = 2048
+// (0.64 ms against 0.105 ms) and 24 at n = 8192 (7.9 ms against 0.33 ms; profiles/r02/trtri_bench.log), so a state that is
+// probed less often than that never pays for it and one that is probed more often loses at most the price of a build
+int inv_auto_calls(const bopy_gp*) { return 16; }
 constexpr int INV_MAX_NPAD = 8192;                  // W and the kept factor are n_pad^2 doubles each (512 MB at 8192)
 constexpr size_t INV_SMEM_BUDGET = (size_t)200 << 10;
 
@@ -459,8 +486,7 @@ void state_changed(bopy_gp* gp) {
     gp->inv_small_calls = 0;
 }
 
-// W = L^-1 by blocked TRTRI on the kept factor: diagonal blocks = Dinv, then one block diagonal at a time
-// (W_IJ = -Dinv_I sum_{K=J}^{I-1} L_IK W_KJ), on the fit's DMMA tile kernel
+// W = L^-1 by blocked triangular inversion of the kept factor (launch_trtri)
 int build_linv(bopy_gp* gp, cudaStream_t st) {
     const int nb = gp->n_blocks, np = gp->n_pad;
     if (gp->inv_ticket == nullptr) {
@@ -473,12 +499,8 @@ int build_linv(bopy_gp* gp, cudaStream_t st) {
         CUDA_TRY(cudaMemsetAsync(gp->inv_ticket, 0, sizeof(unsigned), st));
         gp->inv_ticket_base = 0;
     }
-    copy_diag_blocks_kernel<<<nb, 256, 0, st>>>(gp->Dinv, gp->Winv, np);
-    for (int delta = 1; delta < nb; ++delta) {
-        tile_gemm_kernel<<<nb - delta, NT, 0, st>>>(0, nb, delta, gp->Lfull, gp->Winv, gp->Dinv, nullptr, np);
-        tile_gemm_kernel<<<nb - delta, NT, 0, st>>>(1, nb, delta, gp->Lfull, gp->Winv, gp->Dinv, nullptr, np);
-    }
-    CUDA_TRY(cudaGetLastError());
+    const int rc = launch_trtri(gp->Lfull, gp->Winv, gp->Dinv, nb, np, st);
+    if (rc != BOPY_OK) return rc;
     gp->Winv_valid = true;
     return BOPY_OK;
 }
@@ -1342,12 +1364,14 @@ int bopy_gp_lml(bopy_gp* gp, const double* X_dev, const double* yn_dev, const do
     solve_alpha_kernel<<<1, 1024, 0, st>>>(A, n, np, nb, Dinv, yn_dev, z, alpha);
     lml_value_kernel<<<1, 1024, 0, st>>>(A, n, np, yn_dev, alpha, scal);
     if (want_grad) {
-        copy_diag_blocks_kernel<<<nb, 256, 0, st>>>(Dinv, W, np);
-        for (int delta = 1; delta < nb; ++delta) {               // W = L^-1, one block diagonal at a time
-            tile_gemm_kernel<<<nb - delta, NT, 0, st>>>(0, nb, delta, A, W, Dinv, nullptr, np);
-            tile_gemm_kernel<<<nb - delta, NT, 0, st>>>(1, nb, delta, A, W, Dinv, nullptr, np);
+        if (launch_trtri(A, W, Dinv, nb, np, st) != BOPY_OK) {   // W = L^-1
+            cudaFreeAsync(buf, st);
+            return BOPY_ERR_CUDA;
         }
-        tile_gemm_kernel<<<nb * (nb + 1) / 2, NT, 0, st>>>(2, nb, 0, A, W, Dinv, A, np);   // K^-1 (lower) over L
+        if (trtri_by_diagonals())
+            tile_gemm_kernel<<<nb * (nb + 1) / 2, NT, 0, st>>>(2, nb, 0, A, W, Dinv, A, np);   // K^-1 (lower) over L
+        else
+            tile_gemm_async_kernel<<<nb * (nb + 1) / 2, NT, TG_SMEM_BYTES, st>>>(3, nb, 0, A, W, A, np);
         dim3 block(16, 16), grid(gx, gx);
         switch (gp->kernel) {
             case BOPY_KERNEL_RBF:

@@ -649,6 +649,131 @@ __global__ void __launch_bounds__(NT) tile_gemm_kernel(int job, int nb, int delt
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same 128 x 128 fp64 DMMA output tile, organised for throughput: 16-wide k chunks travel global -> shared memory by
+// cp.async (no register staging) through a 4-stage ring, one block-wide barrier per chunk.  tile_gemm_kernel above stages
+// 8-wide chunks through registers one chunk ahead and reaches ~25 % of the DMMA rate (68 us per 128^3 product); this one
+// is what the triangular inversion below and K^-1 = W^T W run on.
+//
+// Triangular inversion W = L^-1 as a recursion over 2 x 2 block partitions instead of one block diagonal at a time:
+//   inv([[A, 0], [C, B]]) = [[inv A, 0], [-inv(B) C inv(A), inv B]]
+// Level h = 1, 2, 4, ... pairs the already inverted h-block diagonal squares; per level TWO launches cover every pair:
+//   phase 1   T_IJ = sum_{K=J}^{top end}   L_IK W_KJ       (W11 lower triangular)          -> scratch
+//   phase 2   W_IJ = -sum_{K=bottom start}^{I} W_IK T_KJ   (W22 lower triangular)          -> W
+// so the critical path is ~2 (n/128) tile products instead of (n/128)^2 / 2 and every level exposes all its tiles at once.
+// The scratch is the strict upper block triangle of W itself: T_IJ is parked at block (J, I), which nothing else reads
+// (probe_inv_kernel masks columns beyond the row, K^-1 = W^T W sums over lower blocks only).  Block counts that are not a
+// power of two: a pair whose bottom half lies beyond the last block row simply has no tiles.
+//   mode 3    Kinv_IJ = sum_{K=I}^{nb-1} W_KI^T W_KJ, I >= J (lower-triangular tile enumeration)  -> out
+constexpr int TG_KCH = 16;        // k per chunk
+constexpr int TG_STAGES = 4;
+constexpr size_t TG_SMEM_BYTES = (size_t)TG_STAGES * TG_KCH * (BM + BN) * sizeof(double);   // 128 KB
+
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(NT) tile_gemm_async_kernel(int mode, int nb, int h, const double* __restrict__ Lmat,
+                                                             double* W, double* out, int ld) {
+    extern __shared__ __align__(16) unsigned char tg_smem[];
+    double* const As = reinterpret_cast<double*>(tg_smem);                 // [STAGES][KCH][BM] (swizzled, k-major)
+    double* const Bs = As + (size_t)TG_STAGES * TG_KCH * BM;               // [STAGES][KCH][BN]
+    int I, J, kb0, kb1;
+    if (mode == 3) {
+        const int idx = blockIdx.x;   // lower-triangular tile enumeration
+        int rrow = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+        while ((rrow + 1) * (rrow + 2) / 2 <= idx) ++rrow;
+        while (rrow * (rrow + 1) / 2 > idx) --rrow;
+        I = rrow;
+        J = idx - rrow * (rrow + 1) / 2;
+        kb0 = I;
+        kb1 = nb;
+    } else {
+        const int pair = blockIdx.x / (h * h), rem = blockIdx.x - pair * h * h;
+        const int top = 2 * h * pair, bottom = top + h;
+        I = bottom + rem / h;
+        J = top + rem % h;
+        if (I >= nb) return;
+        kb0 = mode == 1 ? J : bottom;
+        kb1 = mode == 1 ? bottom : I + 1;
+    }
+    const int tid = threadIdx.x;
+    const DmmaPolicy pol(tid);
+    // operand element addressing for k-block kb:
+    //   mode 1: A(r,k) = L[I*BM+r][kb*BM+k]  (k contiguous)     B(k,c) = W[kb*BM+k][J*BM+c]
+    //   mode 2: A(r,k) = W[I*BM+r][kb*BM+k]  (k contiguous)     B(k,c) = T(kb,J)[k][c], parked at W block (J, kb)
+    //   mode 3: A(r,k) = W[kb*BM+k][I*BM+r]  (r contiguous)     B(k,c) = W[kb*BM+k][J*BM+c]
+    auto issue = [&](int chunk, int stage) {
+        const int kb = kb0 + chunk / (BM / TG_KCH), k0 = (chunk % (BM / TG_KCH)) * TG_KCH;
+        double* const as = As + (size_t)stage * TG_KCH * BM;
+        double* const bs = Bs + (size_t)stage * TG_KCH * BN;
+        if (mode == 3) {
+#pragma unroll
+            for (int e = 0; e < TG_KCH * BM / 2 / NT; ++e) {
+                const int idx = tid + NT * e, k = idx / (BM / 2), r = 2 * (idx % (BM / 2));
+                cp_async_16(&as[DmmaPolicy::a_index(k, r)], W + ((size_t)kb * BM + k0 + k) * ld + (size_t)I * BM + r);
+            }
+        } else {
+            const double* const a_src = (mode == 1 ? Lmat : W) + (size_t)I * BM * ld + (size_t)kb * BM + k0;
+#pragma unroll
+            for (int e = 0; e < TG_KCH * BM / NT; ++e) {
+                const int idx = tid + NT * e, r = idx / TG_KCH, k = idx % TG_KCH;
+                cp_async_8(&as[DmmaPolicy::a_index(k, r)], a_src + (size_t)r * ld + k);
+            }
+        }
+        const double* const b_src = mode == 2 ? W + ((size_t)J * BM + k0) * ld + (size_t)kb * BM
+                                              : W + ((size_t)kb * BM + k0) * ld + (size_t)J * BM;
+#pragma unroll
+        for (int e = 0; e < TG_KCH * BN / 2 / NT; ++e) {
+            const int idx = tid + NT * e, k = idx / (BN / 2), c = 2 * (idx % (BN / 2));
+            cp_async_16(&bs[DmmaPolicy::b_index(k, c)], b_src + (size_t)k * ld + c);
+        }
+    };
+    double acc[DmmaPolicy::RI][DmmaPolicy::CJ];
+#pragma unroll
+    for (int i = 0; i < DmmaPolicy::RI; ++i)
+#pragma unroll
+        for (int j = 0; j < DmmaPolicy::CJ; ++j) acc[i][j] = 0.0;
+    const int total = (kb1 - kb0) * (BM / TG_KCH);
+#pragma unroll
+    for (int s = 0; s < TG_STAGES - 1; ++s) {
+        if (s < total) issue(s, s);
+        cp_async_commit();
+    }
+    for (int it = 0; it < total; ++it) {
+        cp_async_wait<TG_STAGES - 2>();
+        __syncthreads();   // chunk `it` has landed for every thread; everyone is done with the stage chunk it-1 used
+        const int nx = it + TG_STAGES - 1;
+        if (nx < total) issue(nx, nx % TG_STAGES);
+        cp_async_commit();
+        const double* const as = As + (size_t)(it % TG_STAGES) * TG_KCH * BM;
+        const double* const bs = Bs + (size_t)(it % TG_STAGES) * TG_KCH * BN;
+#pragma unroll
+        for (int sub = 0; sub < TG_KCH / DmmaPolicy::KC; ++sub)
+            pol.mma_tile<false>(acc, as + sub * DmmaPolicy::KC * BM, bs + sub * DmmaPolicy::KC * BN, -1);
+    }
+    cp_async_wait<0>();
+    // mode 1 parks T_IJ in the upper block triangle, at block (J, I)
+    double* C = mode == 3 ? out + (size_t)I * BM * ld + (size_t)J * BM
+                          : (mode == 1 ? W + (size_t)J * BM * ld + (size_t)I * BM : W + (size_t)I * BM * ld + (size_t)J * BM);
+    const double scale = mode == 2 ? -1.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < DmmaPolicy::RI; ++i) {
+        const int r = pol.row_of(i);
+#pragma unroll
+        for (int jv = 0; jv < DmmaPolicy::CJ / 2; ++jv) {
+            const int c = pol.cand_of(2 * jv);
+            *reinterpret_cast<double2*>(&C[(size_t)r * ld + c]) =
+                make_double2(scale * acc[i][2 * jv], scale * acc[i][2 * jv + 1]);
+        }
+    }
+}
+
 constexpr int LML_NG = MAX_D + 2;   // gradient slots: [amplitude, length scales..., noise]
 
 // partial[b][g] = sum over this block's (i >= k) pairs of w_ik * dK_ik/dlog(theta_g), w = (2 - [i==k]) (a_i a_k - Kinv_ik)

@@ -300,7 +300,7 @@ class DirectOptimizer(Optimizer):
         surrogate = getattr(self.acquisition_function, "surrogate", None)
         native = getattr(surrogate, "native", None)
         eager = (native is not None and getattr(surrogate, "inverse_path", None) == "auto"
-                 and kwargs["maxfun"] >= 8 * max(32, ((native.n + 127) // 128) ** 2 // 8))
+                 and kwargs["maxfun"] >= 64)
         if eager:
             native.set_inverse_path(1)
         try:

@@ -78,8 +78,8 @@ class B200GPSurrogate(Surrogate):
     inverse_path : 'auto' | bool
         Calls of a handful of candidates (DIRECT probes the acquisition ONE point per call, thousands of times per
         trial, `bopy/optimizer.py:95-107`) as one matrix-vector product with W = L^-1 (`bopy_gp_set_inverse_path`).
-        'auto' (the library default) builds W at the k-th such call on one fitted state (k = 32 up to n = 2048, 512 at
-        n = 8192: where the chained calls so far have cost what the build costs), True at the first, False never.
+        'auto' (the library default) builds W at the 16th such call on one fitted state (the build costs what 6 chained
+        calls cost at n = 2048, 24 at n = 8192), True at the first, False never.
         The paths agree to rounding, not bit for bit: with False a candidate's value never depends on how many
         calls came before it.
     """

@@ -94,7 +94,7 @@ def test_other_kernels_and_acquisitions(kind, acq):
         np.testing.assert_allclose(inv["acq"][resolved], r[resolved], rtol=1e-7, atol=1e-7 * spread)
 
 
-def test_auto_mode_switches_at_the_32nd_small_call_and_every_state_change_drops_w():
+def test_auto_mode_switches_at_the_16th_small_call_and_every_state_change_drops_w():
     g, st = golden_state("c3_branin_n256")
     gp = native_for(st, "f64")
     eta = float(g["eta"])
@@ -107,7 +107,7 @@ def test_auto_mode_switches_at_the_32nd_small_call_and_every_state_change_drops_
     xs = gp.candidates(x)
     for call in range(1, 41):
         out = gp.sweep(xs, acq="ei", eta=eta, want_var=True, want_acq=True)
-        want = lat if call < 32 else inv
+        want = lat if call < 16 else inv
         assert np.array_equal(out["var"].cpu().numpy(), want["var"]), call
         assert np.array_equal(out["acq"].cpu().numpy(), want["acq"], equal_nan=True), call
     # a call that is too large for the path neither uses W nor counts
@@ -192,8 +192,8 @@ def test_default_surrogate_serves_direct_style_probes_from_w():
     _, _, want, _ = O.acquisition_sweep(st, "ei", probes, eta=float(y.min()))
     for mode in got:
         np.testing.assert_allclose(got[mode], want, rtol=1e-6, atol=1e-9 * np.ptp(want))
-    assert np.array_equal(got["auto"][:31], got[False][:31])      # probe_kernel until W exists ...
-    assert np.array_equal(got["auto"][31:], got[True][31:])       # ... probe_inv_kernel from the 32nd probe on
+    assert np.array_equal(got["auto"][:15], got[False][:15])      # probe_kernel until W exists ...
+    assert np.array_equal(got["auto"][15:], got[True][15:])       # ... probe_inv_kernel from the 16th probe on
 
 
 def test_direct_builds_w_at_its_first_probe_when_its_budget_is_large():
