@@ -7,16 +7,16 @@
 // n = 2048).  A state that is probed thousands of times can afford to pay for W = L^-1 once (blocked TRTRI on the
 // DMMA tile kernel of the fit, a few milliseconds): then
 //
-//   v = W k*        one matrix-vector product, no dependency between rows: row r goes to warp r mod (all warps)
+//   v = W k*        one matrix-vector product, no dependency between rows: rows are dealt to all warps of the grid
 //   var = k(x,x) - sum_r v_r^2,   mean = k* . alpha
 //
-// is one launch whose length is the longest row (n/64 coalesced 512-byte loads per warp, 16 MB out of L2 at
+// is one launch whose length is a warp's share of the rows (n/64 coalesced 512-byte loads per warp, 16 MB out of L2 at
 // n = 2048).  The explicit inverse is only ever multiplied from the left against k* in fp64; its forward error is the
 // same cond(L) eps as the substitution's (measured on every golden set: <= 0.3 of the 1e-9 parity bound at
 // cond(L) = 1.3e5, 3e-4 of it on the BASELINE configs: tools/inverse_path_study.py, profiles/r02/inverse_path_numerics.log).  K*, the de-normalisation and the
 // acquisition are the code of the other two paths (base_kernel, acquisition_value); only the order in which the n
 // products meet differs, so the paths agree to rounding, not bit for bit.  A candidate's value does not depend on m
-// or on its position in the call: rows are dealt to warps by (row, grid) alone.
+// or on its position in the call: rows are dealt to warps by (row, n, grid) alone.
 //
 // Per CTA (512 threads): K* for ALL n rows (every CTA needs the whole column: n exps per candidate per CTA, <= 1 us),
 // its rows of W, a fixed-order reduction of sum v^2 into part[CTA][candidate]; the CTA that draws the last ticket adds
@@ -30,7 +30,9 @@ namespace bopy {
 constexpr int INV_NT = 512;                 // 16 warps
 constexpr int INV_WARPS = INV_NT / 32;
 constexpr int INV_MAX_NC = 8;               // candidates per call
-constexpr int INV_UNROLL = 4;               // 512-byte row segments in flight per warp
+// 512-byte row segments in flight per warp: 8 for one or two candidates (64 KB per SM: what 6.5 TB/s x ~1 us of latency asks
+// of each of 148 SMs when W streams from HBM, n = 8192), 4 beyond (register budget of 512-thread blocks)
+template <int NC> __host__ __device__ constexpr int inv_unroll() { return NC <= 2 ? 8 : 4; }
 
 struct InvParams {
     const double* W;           // [n_pad][n_pad] row-major L^-1 (lower triangular; rows >= n are never read)
@@ -66,6 +68,7 @@ __device__ __forceinline__ double2 ld_nc_v2(const double* p) {
 
 template <int NC, int KIND>
 __global__ void __launch_bounds__(INV_NT, 1) probe_inv_kernel(const InvParams p) {
+    constexpr int INV_UNROLL = inv_unroll<NC>();
     extern __shared__ __align__(16) unsigned char inv_smem[];
     const int n_pad = p.n_blocks * BM;
     double* const ks = reinterpret_cast<double*>(inv_smem);        // [NC][n_pad] K*
@@ -123,8 +126,12 @@ __global__ void __launch_bounds__(INV_NT, 1) probe_inv_kernel(const InvParams p)
     double ss[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) ss[c] = 0.0;
-    const int total_warps = gridDim.x * INV_WARPS;
-    for (int r = blockIdx.x * INV_WARPS + warp; r < p.n; r += total_warps) {
+    // rows are dealt boustrophedon (0 .. T-1, 2T-1 .. T, 2T .. 3T-1, ...): row r costs r + 1 products, so every warp gets
+    // about the same number of bytes (dealt round-robin the last warp would read 1.7x what the first does at n = 8192)
+    const int total_warps = gridDim.x * INV_WARPS, gw = blockIdx.x * INV_WARPS + warp;
+    for (int k = 0; k * total_warps < p.n; ++k) {
+        const int r = (k & 1) ? (k + 1) * total_warps - 1 - gw : k * total_warps + gw;
+        if (r >= p.n) continue;
         const double* const wr = p.W + (size_t)r * n_pad;
         const int len = r + 1;
         double acc[NC];
