@@ -101,6 +101,7 @@ struct bopy_gp {
     double* inv_part = nullptr;        // [sm_count][INV_MAX_NC]
     unsigned* inv_ticket = nullptr;
     unsigned inv_ticket_base = 0;
+    double* inv_host_out = nullptr;    // [3][INV_MAX_NC] mapped pinned host memory: acq / mean / var of a host-buffer call
     // staging of the host-buffer entry point (small calls: one point per DIRECT probe)
     double* host_x = nullptr;          // [HOST_CALL_MAX_M][d]
     double* host_out = nullptr;        // [3][HOST_CALL_MAX_M]: acq / mean / var
@@ -505,6 +506,17 @@ int build_linv(bopy_gp* gp, cudaStream_t st) {
     return BOPY_OK;
 }
 
+// a call the inverse path could serve (inv_applies): is W there, or is it time to build it?  Counts the call otherwise.
+int inv_prepare(bopy_gp* gp, cudaStream_t st, bool* use) {
+    *use = gp->Winv_valid;
+    if (!*use && (gp->inv_mode == 1 || ++gp->inv_small_calls >= inv_auto_calls(gp))) {
+        const int rc = build_linv(gp, st);
+        if (rc != BOPY_OK) return rc;
+        *use = true;
+    }
+    return BOPY_OK;
+}
+
 template <int NC, int KIND> int launch_inv_t(const InvParams& q, int grid, size_t smem, cudaStream_t st) {
     CUDA_TRY(cudaFuncSetAttribute(probe_inv_kernel<NC, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     probe_inv_kernel<NC, KIND><<<grid, INV_NT, smem, st>>>(q);
@@ -529,12 +541,16 @@ int inv_grid(const bopy_gp* gp) {
 // one launch of the inverse path over m <= inv_max_m candidates (W must be valid)
 int launch_inv(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, double kappa, double* mean_out,
                double* var_out, double* acq_out, long long index_base, double* min_val, long long* min_idx,
-               cudaStream_t st) {
+               cudaStream_t st, const double* xs_inline_host = nullptr) {
     InvParams q;
     std::memset(&q, 0, sizeof(q));
     q.W = gp->Winv;
     q.Xt = gp->Xt;
     q.Xs = Xs;
+    if (xs_inline_host != nullptr) {   // host-buffer entry: the candidates are kernel parameters
+        q.Xs = nullptr;
+        std::memcpy(q.xs_inline, xs_inline_host, (size_t)m * gp->d * sizeof(double));
+    }
     q.m = (int)m;
     q.n = (int)gp->n;
     q.n_blocks = gp->n_blocks;
@@ -713,7 +729,8 @@ GroupPlan group_plan(const bopy_gp* gp, long long ntiles) {
 // the one place the sweep is launched from
 int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, double kappa, double* mean_out,
               double* var_out, double* acq_out, long long index_base, double* min_val, long long* min_idx,
-              void* Vws, int slot_per_tile, cudaStream_t st, MinLoc* tile_records = nullptr, bool allow_probe = true) {
+              void* Vws, int slot_per_tile, cudaStream_t st, MinLoc* tile_records = nullptr, bool allow_probe = true,
+              bool allow_inv = true) {
     SweepParams p;
     std::memset(&p, 0, sizeof(p));
     p.Lt = gp->Lt;
@@ -777,14 +794,11 @@ int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, d
         }
         return BOPY_OK;
     }
-    if (allow_probe && inv_applies(gp, m, slot_per_tile, tile_records)) {
+    if (allow_probe && allow_inv && inv_applies(gp, m, slot_per_tile, tile_records)) {
         // a handful of candidates on a state that is probed often: one matrix-vector product with W = L^-1
-        bool use = gp->Winv_valid;
-        if (!use && (gp->inv_mode == 1 || ++gp->inv_small_calls >= inv_auto_calls(gp))) {
-            const int rc = build_linv(gp, st);
-            if (rc != BOPY_OK) return rc;
-            use = true;
-        }
+        bool use = false;
+        const int rc = inv_prepare(gp, st, &use);
+        if (rc != BOPY_OK) return rc;
         if (use)
             return launch_inv(gp, Xs, m, acq, eta, kappa, mean_out, var_out, acq_out, index_base, min_val, min_idx, st);
     }
@@ -952,6 +966,7 @@ void bopy_gp_destroy(bopy_gp* gp) {
     cudaFree(gp->Winv);
     cudaFree(gp->inv_part);
     cudaFree(gp->inv_ticket);
+    if (gp->inv_host_out != nullptr) cudaFreeHost(gp->inv_host_out);
     cudaFree(gp->gctl);
     cudaFree(gp->gpart);
     delete gp;
@@ -1569,6 +1584,32 @@ int bopy_acq_eval_host(bopy_gp* gp, int acq, double eta, double kappa, const dou
         return fail(BOPY_ERR_BAD_ARG, "acquisition output requested with BOPY_ACQ_NONE");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaSetDevice(gp->device));
+    bool tried_inv = false;
+    if (inv_applies(gp, m, 0, nullptr)) {
+        // the DIRECT probe on the inverse path: candidates as kernel parameters, results through mapped pinned memory --
+        // one launch and one stream synchronisation, no memcpy call on either side
+        bool use = false;
+        rc = inv_prepare(gp, st, &use);
+        if (rc != BOPY_OK) return rc;
+        tried_inv = true;
+        if (use) {
+            if (gp->inv_host_out == nullptr)
+                CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&gp->inv_host_out), (size_t)3 * INV_MAX_NC * sizeof(double),
+                                       cudaHostAllocMapped));
+            double* out_dev = nullptr;
+            CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&out_dev), gp->inv_host_out, 0));
+            rc = launch_inv(gp, nullptr, m, acq, eta, kappa, mean_out_host ? out_dev + INV_MAX_NC : nullptr,
+                            var_out_host ? out_dev + 2 * INV_MAX_NC : nullptr, acq_out_host ? out_dev : nullptr, 0, nullptr,
+                            nullptr, st, Xs_host);
+            if (rc != BOPY_OK) return rc;
+            CUDA_TRY(cudaStreamSynchronize(st));
+            const size_t nbytes = (size_t)m * sizeof(double);
+            if (acq_out_host) std::memcpy(acq_out_host, gp->inv_host_out, nbytes);
+            if (mean_out_host) std::memcpy(mean_out_host, gp->inv_host_out + INV_MAX_NC, nbytes);
+            if (var_out_host) std::memcpy(var_out_host, gp->inv_host_out + 2 * INV_MAX_NC, nbytes);
+            return BOPY_OK;
+        }
+    }
     if (gp->host_x == nullptr) {
         CUDA_TRY(cudaMalloc(&gp->host_x, (size_t)HOST_CALL_MAX_M * gp->d * sizeof(double)));
         CUDA_TRY(cudaMalloc(&gp->host_out, (size_t)3 * HOST_CALL_MAX_M * sizeof(double)));
@@ -1577,7 +1618,8 @@ int bopy_acq_eval_host(bopy_gp* gp, int acq, double eta, double kappa, const dou
     double* const m_dev = mean_out_host ? gp->host_out + HOST_CALL_MAX_M : nullptr;
     double* const v_dev = var_out_host ? gp->host_out + 2 * HOST_CALL_MAX_M : nullptr;
     CUDA_TRY(cudaMemcpyAsync(gp->host_x, Xs_host, (size_t)m * gp->d * sizeof(double), cudaMemcpyHostToDevice, st));
-    rc = run_sweep(gp, gp->host_x, m, acq, eta, kappa, m_dev, v_dev, a_dev, 0, nullptr, nullptr, gp->Vws, 0, st);
+    rc = run_sweep(gp, gp->host_x, m, acq, eta, kappa, m_dev, v_dev, a_dev, 0, nullptr, nullptr, gp->Vws, 0, st, nullptr, true,
+                   !tried_inv);   // (the call has been counted above)
     if (rc != BOPY_OK) return rc;
     const size_t bytes = (size_t)m * sizeof(double);
     if (a_dev) CUDA_TRY(cudaMemcpyAsync(acq_out_host, a_dev, bytes, cudaMemcpyDeviceToHost, st));

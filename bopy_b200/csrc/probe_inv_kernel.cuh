@@ -37,7 +37,7 @@ template <int NC> __host__ __device__ constexpr int inv_unroll() { return NC <= 
 struct InvParams {
     const double* W;           // [n_pad][n_pad] row-major L^-1 (lower triangular; rows >= n are never read)
     const double* Xt;          // [n_blocks][d+1][BM]: X / l dimension-major per block row, then alpha
-    const double* Xs;          // candidates (m, d) row-major
+    const double* Xs;          // candidates (m, d) row-major, or nullptr: they are in xs_inline
     int m;
     int n, n_blocks, d;
     double ls[MAX_D];
@@ -54,6 +54,9 @@ struct InvParams {
     double* part;              // [gridDim.x][INV_MAX_NC] sum v^2 of a CTA's rows
     unsigned* ticket;          // monotonic over launches
     unsigned ticket_base;      // the CTA whose ticket is ticket_base + gridDim.x - 1 finishes the call
+    // host-buffer entry (bopy_acq_eval_host): the candidates travel as kernel parameters and the outputs are mapped pinned
+    // host memory, so that a DIRECT probe is one launch and one stream synchronisation with no memcpy call around it
+    double xs_inline[INV_MAX_NC * MAX_D];
 };
 
 inline size_t inv_smem_bytes(int nc, int n_pad, int d) {
@@ -79,10 +82,22 @@ __global__ void __launch_bounds__(INV_NT, 1) probe_inv_kernel(const InvParams p)
     int* const last_s = reinterpret_cast<int*>(ss_s + NC);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total_warps = gridDim.x * INV_WARPS, gw = blockIdx.x * INV_WARPS + warp;
+
+    // the head of this warp's first row of W does not depend on K*: its loads are in flight while K* is formed
+    double2 w_head[INV_UNROLL];
+    if (gw < p.n) {
+        const double* const wr = p.W + (size_t)gw * n_pad;
+#pragma unroll
+        for (int u = 0; u < INV_UNROLL; ++u) {
+            const int j = 2 * lane + 64 * u;
+            w_head[u] = j < gw + 1 ? ld_nc_v2(wr + j) : make_double2(0.0, 0.0);
+        }
+    }
 
     for (int e = tid; e < NC * p.d; e += INV_NT) {
         const int c = e / p.d, q = e - c * p.d;
-        const double v = c < p.m ? p.Xs[(long long)c * p.d + q] : 0.0;
+        const double v = c < p.m ? (p.Xs != nullptr ? p.Xs[(long long)c * p.d + q] : p.xs_inline[c * p.d + q]) : 0.0;
         xs_s[q * NC + c] = __ddiv_rn(v, p.ls[q]);
     }
     __syncthreads();
@@ -91,6 +106,7 @@ __global__ void __launch_bounds__(INV_NT, 1) probe_inv_kernel(const InvParams p)
     double mp[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) mp[c] = 0.0;
+#pragma unroll 4
     for (int i = tid; i < n_pad; i += INV_NT) {
         const int I = i >> 7, row = i & (BM - 1);
         const double* const xrow = p.Xt + (long long)I * (p.d + 1) * BM;
@@ -128,7 +144,6 @@ __global__ void __launch_bounds__(INV_NT, 1) probe_inv_kernel(const InvParams p)
     for (int c = 0; c < NC; ++c) ss[c] = 0.0;
     // rows are dealt boustrophedon (0 .. T-1, 2T-1 .. T, 2T .. 3T-1, ...): row r costs r + 1 products, so every warp gets
     // about the same number of bytes (dealt round-robin the last warp would read 1.7x what the first does at n = 8192)
-    const int total_warps = gridDim.x * INV_WARPS, gw = blockIdx.x * INV_WARPS + warp;
     for (int k = 0; k * total_warps < p.n; ++k) {
         const int r = (k & 1) ? (k + 1) * total_warps - 1 - gw : k * total_warps + gw;
         if (r >= p.n) continue;
@@ -142,7 +157,8 @@ __global__ void __launch_bounds__(INV_NT, 1) probe_inv_kernel(const InvParams p)
 #pragma unroll
             for (int u = 0; u < INV_UNROLL; ++u) {
                 const int j = j0 + 64 * u;
-                w[u] = j < len ? ld_nc_v2(wr + j) : make_double2(0.0, 0.0);
+                if (k == 0 && j0 == 2 * lane) w[u] = w_head[u];
+                else w[u] = j < len ? ld_nc_v2(wr + j) : make_double2(0.0, 0.0);
                 if (j + 1 >= len) w[u].y = 0.0;   // the strict upper triangle is not part of L^-1
             }
 #pragma unroll

@@ -222,3 +222,19 @@ def test_direct_builds_w_at_its_first_probe_when_its_budget_is_large():
     assert found["auto"][2] == 1 and found[False][2] == 2      # probe_inv_kernel alone / probe_kernel + the arg-min finalize
     np.testing.assert_allclose(found["auto"][1], found[False][1], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(found["auto"][0], found[False][0], atol=1e-6)
+
+
+def test_host_buffer_entry_runs_the_same_kernel_without_copies():
+    """bopy_acq_eval_host (numpy in, numpy out: the DIRECT probe) hands the candidates over as kernel parameters and reads
+    the results from mapped pinned memory: the numbers are those of the device-buffer entry, bit for bit."""
+    g, st, gp = cached_native("c4_hartmann6_n2048", "f64")
+    eta = float(g["eta"])
+    for m in (1, 3, 8, 9):
+        xs = np.ascontiguousarray(g["Xs"][20:20 + m])
+        dev = run(gp, xs, "inverse", eta=eta)
+        a, mu, var = gp.eval_host(xs, acq="ei", eta=eta, want_acq=True, want_mean=True, want_var=True)
+        assert np.array_equal(a, dev["acq"], equal_nan=True) and np.array_equal(mu, dev["mean"]) and np.array_equal(var, dev["var"])
+        only_acq, none_m, none_v = gp.eval_host(xs, acq="ei", eta=eta)
+        assert np.array_equal(only_acq, dev["acq"], equal_nan=True) and none_m is None and none_v is None
+        _, mu2, var2 = gp.eval_host(xs, acq=None, want_acq=False, want_mean=True, want_var=True)
+        assert np.array_equal(mu2, dev["mean"]) and np.array_equal(var2, dev["var"])
