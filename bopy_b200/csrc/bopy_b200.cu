@@ -1078,8 +1078,18 @@ CholStreams& chol_streams() {
     return cs;
 }
 
+// panel / trailing-update tiles of the blocked Cholesky: gemm_nt_async_kernel (cp.async ring); BOPY_B200_CHOL_GEMM=registers
+// selects the register-staged gemm_nt_kernel of the first version for A/B runs
+void launch_gemm_nt(bool staged, int grid, cudaStream_t s, double* A, int n, int ld, int J, const double* Dinv, int mode) {
+    if (staged) gemm_nt_kernel<<<grid, NT, 0, s>>>(A, n, ld, J, Dinv, mode);
+    else gemm_nt_async_kernel<<<grid, NT, TG_SMEM_BYTES, s>>>(A, n, ld, J, Dinv, mode);
+}
+
 void launch_cholesky(double* A, int n, int ld, int nb, double* Dinv, int* status, cudaStream_t st) {
     const size_t chol_smem = chol_smem_bytes();
+    const char* gemm_env = std::getenv("BOPY_B200_CHOL_GEMM");
+    const bool staged = gemm_env != nullptr && std::strcmp(gemm_env, "registers") == 0;
+    if (!staged) cudaFuncSetAttribute(gemm_nt_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM_BYTES);
     cudaFuncSetAttribute(chol_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem);
     CholStreams& cs = chol_streams();
     if (!(cs.ok && nb >= 4)) {   // plain right-looking order on one stream
@@ -1087,8 +1097,8 @@ void launch_cholesky(double* A, int n, int ld, int nb, double* Dinv, int* status
             chol_block_kernel<<<1, CHOL_NT, chol_smem, st>>>(A, n, ld, J, Dinv, status);
             const int below = nb - J - 1;
             if (below > 0) {
-                gemm_nt_kernel<<<below, NT, 0, st>>>(A, n, ld, J, Dinv, 0);
-                gemm_nt_kernel<<<below * (below + 1) / 2, NT, 0, st>>>(A, n, ld, J, Dinv, 1);
+                launch_gemm_nt(staged, below, st, A, n, ld, J, Dinv, 0);
+                launch_gemm_nt(staged, below * (below + 1) / 2, st, A, n, ld, J, Dinv, 1);
             }
         }
         return;
@@ -1114,14 +1124,14 @@ void launch_cholesky(double* A, int n, int ld, int nb, double* Dinv, int* status
         }
         const int below = nb - J - 1;
         if (below <= 0) break;
-        gemm_nt_kernel<<<below, NT, 0, hi>>>(A, n, ld, J, Dinv, 0);
+        launch_gemm_nt(staged, below, hi, A, n, ld, J, Dinv, 0);
         cudaEventRecord(cs.panel_done[J & 1], hi);
         if (rest_pending) cudaStreamWaitEvent(hi, cs.rest_done[(J - 1) & 1], 0);   // step J-1 also updated block column J+1
-        gemm_nt_kernel<<<below, NT, 0, hi>>>(A, n, ld, J, Dinv, 2);
+        launch_gemm_nt(staged, below, hi, A, n, ld, J, Dinv, 2);
         rest_pending = false;
         if (below > 1) {
             cudaStreamWaitEvent(st, cs.panel_done[J & 1], 0);
-            gemm_nt_kernel<<<(below - 1) * below / 2, NT, 0, st>>>(A, n, ld, J, Dinv, 3);
+            launch_gemm_nt(staged, (below - 1) * below / 2, st, A, n, ld, J, Dinv, 3);
             cudaEventRecord(cs.rest_done[J & 1], st);
             rest_pending = true;
         }

@@ -774,6 +774,98 @@ __global__ void __launch_bounds__(NT) tile_gemm_async_kernel(int mode, int nb, i
     }
 }
 
+// gemm_nt_kernel (the Cholesky panel / trailing update: C_tile = beta C_tile + sign A_tile B_tile^T, modes as above) on the
+// cp.async pipeline of tile_gemm_async_kernel: both operands are k-contiguous rows of a row-major matrix, scattered into the
+// k-major fragment layout by 8-byte copies; rows / k beyond n arrive as zeros (cp.async with a zero source size).
+__device__ __forceinline__ void cp_async_8_zfill(void* smem, const void* gmem, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem),
+                 "r"(valid ? 8 : 0)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(NT) gemm_nt_async_kernel(double* Amat, int n, int ld, int J, const double* Dinv, int mode) {
+    extern __shared__ __align__(16) unsigned char tg_smem[];
+    double* const As = reinterpret_cast<double*>(tg_smem);
+    double* const Bs = As + (size_t)TG_STAGES * TG_KCH * BM;
+    int I, K;
+    if (mode == 0) {
+        I = J + 1 + blockIdx.x;
+        K = J;
+    } else if (mode == 2) {
+        I = J + 1 + blockIdx.x;
+        K = J + 1;
+        mode = 1;
+    } else {
+        const int K0 = mode == 3 ? J + 2 : J + 1;
+        const int idx = blockIdx.x;
+        int rrow = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+        while ((rrow + 1) * (rrow + 2) / 2 <= idx) ++rrow;
+        while (rrow * (rrow + 1) / 2 > idx) --rrow;
+        I = K0 + rrow;
+        K = K0 + (idx - rrow * (rrow + 1) / 2);
+        mode = 1;
+    }
+    const int tid = threadIdx.x;
+    const DmmaPolicy pol(tid);
+    const double* Ablk = Amat + (size_t)I * BM * ld + (size_t)J * BM;            // A[r][k]
+    const double* Bblk = mode == 0 ? Dinv + (size_t)J * BM * BM : Amat + (size_t)K * BM * ld + (size_t)J * BM;
+    const int ldb = mode == 0 ? BM : ld;
+    const int rowsA = n - I * BM, rowsB = mode == 0 ? BM : n - K * BM, colsK = n - J * BM;   // valid extents
+    auto issue = [&](int chunk, int stage) {
+        const int k0 = chunk * TG_KCH;
+        double* const as = As + (size_t)stage * TG_KCH * BM;
+        double* const bs = Bs + (size_t)stage * TG_KCH * BN;
+#pragma unroll
+        for (int e = 0; e < TG_KCH * BM / NT; ++e) {
+            const int idx = tid + NT * e, r = idx / TG_KCH, k = idx % TG_KCH;
+            const bool va = r < rowsA && k0 + k < colsK, vb = r < rowsB && (mode == 0 || k0 + k < colsK);
+            cp_async_8_zfill(&as[DmmaPolicy::a_index(k, r)], va ? Ablk + (size_t)r * ld + k0 + k : Ablk, va);
+            cp_async_8_zfill(&bs[DmmaPolicy::b_index(k, r)], vb ? Bblk + (size_t)r * ldb + k0 + k : Bblk, vb);
+        }
+    };
+    double acc[DmmaPolicy::RI][DmmaPolicy::CJ];
+#pragma unroll
+    for (int i = 0; i < DmmaPolicy::RI; ++i)
+#pragma unroll
+        for (int j = 0; j < DmmaPolicy::CJ; ++j) acc[i][j] = 0.0;
+    constexpr int total = BM / TG_KCH;
+#pragma unroll
+    for (int s = 0; s < TG_STAGES - 1; ++s) {
+        if (s < total) issue(s, s);
+        cp_async_commit();
+    }
+    for (int it = 0; it < total; ++it) {
+        cp_async_wait<TG_STAGES - 2>();
+        __syncthreads();
+        const int nx = it + TG_STAGES - 1;
+        if (nx < total) issue(nx, nx % TG_STAGES);
+        cp_async_commit();
+        const double* const as = As + (size_t)(it % TG_STAGES) * TG_KCH * BM;
+        const double* const bs = Bs + (size_t)(it % TG_STAGES) * TG_KCH * BN;
+#pragma unroll
+        for (int sub = 0; sub < TG_KCH / DmmaPolicy::KC; ++sub)
+            pol.mma_tile<false>(acc, as + sub * DmmaPolicy::KC * BM, bs + sub * DmmaPolicy::KC * BN, -1);
+    }
+    cp_async_wait<0>();
+    double* Cblk = Amat + (size_t)I * BM * ld + (size_t)K * BM;
+    const int colsC = n - K * BM;
+#pragma unroll
+    for (int i = 0; i < DmmaPolicy::RI; ++i) {
+        const int r = pol.row_of(i);
+        if (r >= rowsA) continue;
+#pragma unroll
+        for (int j = 0; j < DmmaPolicy::CJ; ++j) {
+            const int c = pol.cand_of(j);
+            if (c >= colsC || c >= BM) continue;
+            double* dst = &Cblk[(size_t)r * ld + c];
+            if (mode == 0)
+                *dst = acc[i][j];
+            else if (I != K || c <= r)       // diagonal tiles: lower triangle only
+                *dst = *dst - acc[i][j];
+        }
+    }
+}
+
 constexpr int LML_NG = MAX_D + 2;   // gradient slots: [amplitude, length scales..., noise]
 
 // partial[b][g] = sum over this block's (i >= k) pairs of w_ik * dK_ik/dlog(theta_g), w = (2 - [i==k]) (a_i a_k - Kinv_ik)
