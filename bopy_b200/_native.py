@@ -132,7 +132,11 @@ def _ptr(t):
 
 
 def _stream(device):
+    """torch's current stream on `device` as a raw cudaStream_t."""
     import torch
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None and getattr(device, "index", None) is not None:
+        return c_void_p(raw(device.index))
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
@@ -149,11 +153,19 @@ def resolve_device(device=None):
     return torch.device("cuda", torch.cuda.current_device() if dev.index is None else dev.index)
 
 
+_CUDA_SEEN = False
+
+
 def require_cuda():
+    """torch, after checking ONCE per process that a CUDA device is visible (the check costs microseconds, and a DIRECT
+    probe is 35 of them)."""
+    global _CUDA_SEEN
     import torch
-    if not torch.cuda.is_available():
-        raise NativeLibraryError("no CUDA device is visible; bopy_b200 runs the posterior/acquisition path on a "
-                                 "B200 only (no CPU fallback)")
+    if not _CUDA_SEEN:
+        if not torch.cuda.is_available():
+            raise NativeLibraryError("no CUDA device is visible; bopy_b200 runs the posterior/acquisition path on a "
+                                     "B200 only (no CPU fallback)")
+        _CUDA_SEEN = True
     return torch
 
 
@@ -358,6 +370,11 @@ class NativeGP:
         m = x.shape[0]
         out = [np.empty(m) if w else None for w in (want_acq, want_mean, want_var)]
         ptrs = [c_void_p(o.ctypes.data) if o is not None else c_void_p(0) for o in out]
+        if torch.cuda.current_device() == self.device.index:      # (the library selects the handle's device itself)
+            check(self.lib.bopy_acq_eval_host(self._handle, ACQ_IDS[acq], float(eta), float(kappa),
+                                              c_void_p(x.ctypes.data), m, ptrs[0], ptrs[1], ptrs[2],
+                                              _stream(self.device)), "bopy_acq_eval_host")
+            return out
         with torch.cuda.device(self.device):
             check(self.lib.bopy_acq_eval_host(self._handle, ACQ_IDS[acq], float(eta), float(kappa),
                                               c_void_p(x.ctypes.data), m, ptrs[0], ptrs[1], ptrs[2],

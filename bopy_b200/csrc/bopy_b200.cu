@@ -101,7 +101,7 @@ struct bopy_gp {
     double* inv_part = nullptr;        // [sm_count][INV_MAX_NC]
     unsigned* inv_ticket = nullptr;
     unsigned inv_ticket_base = 0;
-    double* inv_host_out = nullptr;    // [3][INV_MAX_NC] mapped pinned host memory: acq / mean / var of a host-buffer call
+    double* inv_host_out = nullptr;    // [3][INV_MAX_NC] mapped pinned host memory: acq / mean / var of a host-buffer call of <= 8 candidates
     // staging of the host-buffer entry point (small calls: one point per DIRECT probe)
     double* host_x = nullptr;          // [HOST_CALL_MAX_M][d]
     double* host_out = nullptr;        // [3][HOST_CALL_MAX_M]: acq / mean / var
@@ -730,7 +730,7 @@ GroupPlan group_plan(const bopy_gp* gp, long long ntiles) {
 int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, double kappa, double* mean_out,
               double* var_out, double* acq_out, long long index_base, double* min_val, long long* min_idx,
               void* Vws, int slot_per_tile, cudaStream_t st, MinLoc* tile_records = nullptr, bool allow_probe = true,
-              bool allow_inv = true) {
+              bool allow_inv = true, const double* xs_inline_host = nullptr) {   // xs_inline_host: small_n handles, m <= 8 only
     SweepParams p;
     std::memset(&p, 0, sizeof(p));
     p.Lt = gp->Lt;
@@ -764,6 +764,10 @@ int run_sweep(bopy_gp* gp, const double* Xs, long long m, int acq, double eta, d
         q.Xt = gp->Xt;
         q.Dinv = gp->Dinv;
         q.Xs = Xs;
+        if (xs_inline_host != nullptr) {
+            q.Xs = nullptr;
+            std::memcpy(q.xs_inline, xs_inline_host, (size_t)m * gp->d * sizeof(double));
+        }
         q.m = m;
         q.ntiles = (m + SMALL_NT - 1) / SMALL_NT;
         q.n = (int)gp->n;
@@ -1594,6 +1598,33 @@ int bopy_acq_eval_host(bopy_gp* gp, int acq, double eta, double kappa, const dou
         return fail(BOPY_ERR_BAD_ARG, "acquisition output requested with BOPY_ACQ_NONE");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaSetDevice(gp->device));
+    auto pinned_out = [&](double** out_dev) -> int {   // [3][INV_MAX_NC] mapped pinned: acq / mean / var
+        if (gp->inv_host_out == nullptr)
+            CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&gp->inv_host_out), (size_t)3 * INV_MAX_NC * sizeof(double),
+                                   cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(out_dev), gp->inv_host_out, 0));
+        return BOPY_OK;
+    };
+    auto fetch_pinned = [&]() {
+        const size_t nbytes = (size_t)m * sizeof(double);
+        if (acq_out_host) std::memcpy(acq_out_host, gp->inv_host_out, nbytes);
+        if (mean_out_host) std::memcpy(mean_out_host, gp->inv_host_out + INV_MAX_NC, nbytes);
+        if (var_out_host) std::memcpy(var_out_host, gp->inv_host_out + 2 * INV_MAX_NC, nbytes);
+    };
+    static_assert(SMALL_INLINE_M == INV_MAX_NC, "one pinned result buffer serves both kernels");
+    if (small_applies(gp, 0) && m <= SMALL_INLINE_M) {
+        // n <= 32 (the reference's own examples): the thread-per-candidate kernel, candidates as kernel parameters
+        double* out_dev = nullptr;
+        rc = pinned_out(&out_dev);
+        if (rc != BOPY_OK) return rc;
+        rc = run_sweep(gp, nullptr, m, acq, eta, kappa, mean_out_host ? out_dev + INV_MAX_NC : nullptr,
+                       var_out_host ? out_dev + 2 * INV_MAX_NC : nullptr, acq_out_host ? out_dev : nullptr, 0, nullptr, nullptr,
+                       gp->Vws, 0, st, nullptr, true, false, Xs_host);
+        if (rc != BOPY_OK) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        fetch_pinned();
+        return BOPY_OK;
+    }
     bool tried_inv = false;
     if (inv_applies(gp, m, 0, nullptr)) {
         // the DIRECT probe on the inverse path: candidates as kernel parameters, results through mapped pinned memory --
@@ -1603,20 +1634,15 @@ int bopy_acq_eval_host(bopy_gp* gp, int acq, double eta, double kappa, const dou
         if (rc != BOPY_OK) return rc;
         tried_inv = true;
         if (use) {
-            if (gp->inv_host_out == nullptr)
-                CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&gp->inv_host_out), (size_t)3 * INV_MAX_NC * sizeof(double),
-                                       cudaHostAllocMapped));
             double* out_dev = nullptr;
-            CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&out_dev), gp->inv_host_out, 0));
+            rc = pinned_out(&out_dev);
+            if (rc != BOPY_OK) return rc;
             rc = launch_inv(gp, nullptr, m, acq, eta, kappa, mean_out_host ? out_dev + INV_MAX_NC : nullptr,
                             var_out_host ? out_dev + 2 * INV_MAX_NC : nullptr, acq_out_host ? out_dev : nullptr, 0, nullptr,
                             nullptr, st, Xs_host);
             if (rc != BOPY_OK) return rc;
             CUDA_TRY(cudaStreamSynchronize(st));
-            const size_t nbytes = (size_t)m * sizeof(double);
-            if (acq_out_host) std::memcpy(acq_out_host, gp->inv_host_out, nbytes);
-            if (mean_out_host) std::memcpy(mean_out_host, gp->inv_host_out + INV_MAX_NC, nbytes);
-            if (var_out_host) std::memcpy(var_out_host, gp->inv_host_out + 2 * INV_MAX_NC, nbytes);
+            fetch_pinned();
             return BOPY_OK;
         }
     }

@@ -20,12 +20,13 @@ namespace bopy {
 
 constexpr int SMALL_N_MAX = 32;
 constexpr int SMALL_CTAS_PER_SM = 8;   // the grid is capped at this many thread blocks per SM (persistent loop over the tiles)
+constexpr int SMALL_INLINE_M = 8;  // candidates a host-buffer call can pass as kernel parameters
 constexpr int SMALL_NT = 128;      // threads = candidates per tile (= BN, so that per-tile records line up with the blocked kernels)
 
 struct SmallParams {
     const double* Xt;      // block 0 of the packed X: [(d+1)][BM], X/l dimension-major then alpha
     const double* Dinv;    // block 0 of the inverted diagonal blocks: [BM][BM] row-major, lower triangular
-    const double* Xs;      // candidates (m, d) row-major
+    const double* Xs;      // candidates (m, d) row-major, or nullptr: they are in xs_inline (m <= SMALL_INLINE_M)
     long long m, ntiles;
     int n, d;
     double ls[MAX_D];
@@ -39,6 +40,9 @@ struct SmallParams {
     MinLoc* partials;       // [gridDim.x] or nullptr
     MinLoc* tile_records;   // [ntiles] or nullptr
     int nan_skip;
+    // host-buffer entry (bopy_acq_eval_host, the DIRECT probe of the reference's own examples: n ~ 10, one point per call):
+    // candidates as kernel parameters, outputs in mapped pinned host memory -- no memcpy call around the launch
+    double xs_inline[SMALL_INLINE_M * MAX_D];
 };
 
 template <int NP, int KIND>
@@ -74,7 +78,8 @@ __global__ void __launch_bounds__(SMALL_NT) small_n_kernel(const SmallParams p) 
 #pragma unroll
             for (int i = 0; i < NP; ++i) d2[i] = 0.0;
             for (int q = 0; q < p.d; ++q) {
-                const double xq = __ddiv_rn(p.Xs[gc * p.d + q], p.ls[q]);   // X / length_scale, like sklearn
+                const double xv = p.Xs != nullptr ? p.Xs[gc * p.d + q] : p.xs_inline[gc * p.d + q];
+                const double xq = __ddiv_rn(xv, p.ls[q]);   // X / length_scale, like sklearn
 #pragma unroll
                 for (int i = 0; i < NP; ++i) {
                     const double df = xq - Xn[q][i];

@@ -238,3 +238,19 @@ def test_host_buffer_entry_runs_the_same_kernel_without_copies():
         assert np.array_equal(only_acq, dev["acq"], equal_nan=True) and none_m is None and none_v is None
         _, mu2, var2 = gp.eval_host(xs, acq=None, want_acq=False, want_mean=True, want_var=True)
         assert np.array_equal(mu2, dev["mean"]) and np.array_equal(var2, dev["var"])
+
+
+@pytest.mark.parametrize("name", ["ref_forrester_matern15_fixed", "c1_forrester_rbf_n6", "edge_alpha0_nan", "edge_on_training_points"])
+def test_host_buffer_entry_on_small_n_handles(name):
+    """n <= 32 (the reference's own examples, DIRECT on ~10 observations): small_n_kernel takes up to 8 candidates of a
+    host-buffer call as kernel parameters and writes to mapped pinned memory; same numbers as the device-buffer entry."""
+    g, st, gp = cached_native(name, "f64")
+    eta = float(g["eta"])
+    for m in (1, 5, 8, 9, 40):
+        xs = np.ascontiguousarray(g["Xs"][3:3 + m])
+        dev = run(gp, xs, "latency", eta=eta)
+        a, mu, var = gp.eval_host(xs, acq="ei", eta=eta, want_acq=True, want_mean=True, want_var=True)
+        assert np.array_equal(a, dev["acq"], equal_nan=True) and np.array_equal(mu, dev["mean"])
+        assert np.array_equal(var, dev["var"], equal_nan=True)
+        (only_var,) = [o for o in gp.eval_host(xs, acq=None, want_acq=False, want_var=True) if o is not None]
+        assert np.array_equal(only_var, dev["var"], equal_nan=True)

@@ -42,7 +42,7 @@ def api_ms(ei, xs, reps):
 
 
 def main():
-    shapes = [(256, 2), (2048, 6)] + ([(8192, 20)] if "--large" in sys.argv else [])
+    shapes = [(10, 1), (256, 2), (2048, 6)] + ([(8192, 20)] if "--large" in sys.argv else [])
     ms = (1, 8, 64, 128, 512, 1024, 4096, 8192)
     rows = []
     for n, d in shapes:
