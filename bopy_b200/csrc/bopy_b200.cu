@@ -1936,6 +1936,14 @@ int bopy_gp_predict_cov(bopy_gp* gp, const double* Xs_dev, int64_t m, double* me
     if (m < 1) return fail(BOPY_ERR_BAD_ARG, "m must be >= 1 (got %lld)", (long long)m);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaSetDevice(gp->device));
+    if (m == 1) {
+        // ONE point (Surrogate.predict inside a DIRECT objective or the Kriging believer, bopy/acquisition.py:189): the 1 x 1
+        // covariance is the posterior variance -- the latency / inverse path instead of one thread block walking all of L
+        rc = run_sweep(gp, Xs_dev, 1, BOPY_ACQ_NONE, 0.0, 0.0, mean_out, cov_out, nullptr, 0, nullptr, nullptr, gp->Vws, 0, st);
+        if (rc != BOPY_OK) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return BOPY_OK;
+    }
     const long long ntiles = (m + BN - 1) / BN;
     void* Vall = nullptr;
     CUDA_TRY(cudaMalloc(&Vall, (size_t)ntiles * gp->n_pad * BN * v_entry_bytes(gp)));

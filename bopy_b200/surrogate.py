@@ -272,6 +272,12 @@ class B200GPSurrogate(Surrogate):
 
     # -- the reference contract --------------------------------------------------------------------
     def _predict(self, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        if isinstance(x, np.ndarray) and x.shape[0] == 1 and self.native.HOST_CALL_MAX_M >= 1:
+            # ONE point (a DIRECT objective built on predict, the Kriging believer's bopy/acquisition.py:189): the 1 x 1
+            # covariance is the posterior variance -- one host-buffer call on the latency / inverse path
+            _, mean, var = self.native.eval_host(np.ascontiguousarray(x, dtype=np.float64), want_acq=False, want_mean=True,
+                                                 want_var=True)
+            return mean, var.reshape(1, 1)
         xs = self.native.candidates(x)
         mean, cov = self.native.predict_cov(xs)
         return mean.cpu().numpy(), cov.cpu().numpy()

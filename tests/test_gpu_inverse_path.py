@@ -254,3 +254,42 @@ def test_host_buffer_entry_on_small_n_handles(name):
         assert np.array_equal(var, dev["var"], equal_nan=True)
         (only_var,) = [o for o in gp.eval_host(xs, acq=None, want_acq=False, want_var=True) if o is not None]
         assert np.array_equal(only_var, dev["var"], equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["c4_hartmann6_n2048", "c3_branin_n256", "ref_forrester_matern15_fixed"])
+def test_one_point_predict_is_the_posterior_variance_on_the_fast_path(name):
+    """Surrogate.predict on ONE point (bopy/surrogate.py:83-92 as a DIRECT objective or the Kriging believer call it): the
+    1 x 1 covariance is the variance of the latency / inverse path, not a walk of one thread block over all of L."""
+    g, st, gp = cached_native(name, "f64")
+    select_path(gp, "inverse")
+    pv = prior_var(st)
+    for i in (0, 7):
+        xs = gp.candidates(g["Xs"][i:i + 2])
+        mean2, cov2 = gp.predict_cov(xs)
+        mean1, cov1 = gp.predict_cov(xs[:1])
+        assert tuple(cov1.shape) == (1, 1) and tuple(mean1.shape) == (1,)
+        np.testing.assert_allclose(cov1.cpu().numpy()[0, 0], cov2.cpu().numpy()[0, 0], rtol=1e-9, atol=1e-11 * pv)
+        err, bound = check_mean(mean1.cpu().numpy(), mean2.cpu().numpy()[:1], st, "f64")
+        assert (err <= bound).all()
+        err, bound = check_var(cov1.cpu().numpy()[0], g["var"][i:i + 1], st, "f64")
+        assert (err <= bound).all()
+
+
+def test_surrogate_predict_of_one_point_through_the_public_api():
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel
+
+    from bopy_b200.surrogate import B200GPSurrogate
+    rng = np.random.default_rng(2)
+    X = rng.random((300, 3))
+    y = np.sin(4 * X[:, 0]) + X[:, 1] ** 2 - X[:, 2]
+    gp = GaussianProcessRegressor(kernel=ConstantKernel(1.3) * RBF([0.15, 0.2, 0.25]), alpha=1e-6, normalize_y=True, optimizer=None)
+    sur = B200GPSurrogate(gp)
+    sur.fit(X, y)
+    xs = rng.random((6, 3))
+    mean_all, cov_all = sur.predict(xs)
+    for i in range(6):
+        mean_i, cov_i = sur.predict(xs[i:i + 1])
+        assert mean_i.shape == (1,) and cov_i.shape == (1, 1)
+        np.testing.assert_allclose(mean_i[0], mean_all[i], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(cov_i[0, 0], cov_all[i, i], rtol=1e-8, atol=1e-11)

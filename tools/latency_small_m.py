@@ -63,6 +63,21 @@ def main():
             ei(x1)
             print(f"n={n:5d} d={d:2d}: first probe in mode 1 (builds W = L^-1 by blocked TRTRI, then probes): "
                   f"{1e3 * (time.perf_counter() - t0):.3f} ms", flush=True)
+        x1 = rng.random((1, d))
+        for _ in range(20):
+            sur.predict(x1)
+        t0 = time.perf_counter()
+        for _ in range(100):
+            sur.predict(x1)
+        t_pred = 1e3 * (time.perf_counter() - t0) / 100
+        with bench.all_host_threads():
+            host.predict(x1, return_cov=True)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                host.predict(x1, return_cov=True)
+            t_pred_ref = 1e3 * (time.perf_counter() - t0) / 20
+        print(f"n={n:5d} d={d:2d}: Surrogate.predict(x) of ONE point (mean, 1 x 1 covariance): {t_pred:.3f} ms/call   "
+              f"scikit-learn predict(return_cov=True): {t_pred_ref:.3f}", flush=True)
         for m in ms:
             xs = rng.random((m, d))
             xd = sur.native.candidates(xs)
