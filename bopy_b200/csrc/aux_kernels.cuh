@@ -144,6 +144,30 @@ __global__ void cov_kernel(const typename E::TG* __restrict__ Vws, int n_pad, in
     cov[a * m + b] = __dmul_rn(__dadd_rn(prior, -s), y_var);
 }
 
+// the same with V as the latency path leaves it (probe_kernel with keep_v: [batch][NA][n_pad][8], 8 NA candidates per batch)
+template <int KIND>
+__global__ void cov_probe_kernel(const double* __restrict__ V, int na, int n_pad, int n, const double* __restrict__ Xs,
+                                 long long m, int d, LsParam ls, double amp, double kss, double y_var, double* cov) {
+    const long long a = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= m || b >= m) return;
+    const int nc = 8 * na;
+    const double* Va = V + ((a / nc) * na + ((a % nc) >> 3)) * (long long)n_pad * 8 + (a & 7);
+    const double* Vb = V + ((b / nc) * na + ((b % nc) >> 3)) * (long long)n_pad * 8 + (b & 7);
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s = fma(Va[(long long)i * 8], Vb[(long long)i * 8], s);
+    double prior = kss;
+    if (a != b) {
+        double d2 = 0.0;
+        for (int q = 0; q < d; ++q) {
+            const double df = __dadd_rn(__ddiv_rn(Xs[a * d + q], ls.v[q]), -__ddiv_rn(Xs[b * d + q], ls.v[q]));
+            d2 = __dadd_rn(d2, __dmul_rn(df, df));
+        }
+        prior = __dmul_rn(amp, base_kernel<KIND>(d2));
+    }
+    cov[a * m + b] = __dmul_rn(__dadd_rn(prior, -s), y_var);
+}
+
 // acquisition epilogue on given moments + block-wide arg-min; one block (small m)
 __global__ void moments_kernel(int acq, double eta, double kappa, const double* __restrict__ mean,
                                const double* __restrict__ var, long long m, double* acq_out, long long index_base,

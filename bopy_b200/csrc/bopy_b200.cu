@@ -1944,17 +1944,46 @@ int bopy_gp_predict_cov(bopy_gp* gp, const double* Xs_dev, int64_t m, double* me
         CUDA_TRY(cudaStreamSynchronize(st));
         return BOPY_OK;
     }
+    if (!small_applies(gp, 0) && probe_applies(gp, m, 0, nullptr) && m <= probe_capacity(gp)) {
+        // a small candidate set (the reference's plotting grids: a few hundred points): V from the latency path -- the solve
+        // spread over the block rows of L -- instead of one thread block per 128 candidates walking all of L
+        const ProbePlan pl = probe_plan(gp, m);
+        rc = launch_probe(gp, pl, Xs_dev, m, BOPY_ACQ_NONE, 0.0, 0.0, mean_out, nullptr, nullptr, 0, nullptr, 1, st);
+        if (rc != BOPY_OK) return rc;
+        LsParam ls;
+        for (int q = 0; q < MAX_D; ++q) ls.v[q] = q < gp->d ? gp->ls[q] : 1.0;
+        dim3 block(16, 16), grid((unsigned)((m + 15) / 16), (unsigned)((m + 15) / 16));
+        const double kss = gp->amp + gp->noise, yv = gp->y_std * gp->y_std;
+        const double* V = reinterpret_cast<const double*>(gp->Vws);
+        switch (gp->kernel) {
+            case BOPY_KERNEL_RBF:
+                cov_probe_kernel<K_RBF><<<grid, block, 0, st>>>(V, pl.na, gp->n_pad, (int)gp->n, Xs_dev, m, gp->d, ls, gp->amp, kss, yv, cov_out);
+                break;
+            case BOPY_KERNEL_MATERN12:
+                cov_probe_kernel<K_M12><<<grid, block, 0, st>>>(V, pl.na, gp->n_pad, (int)gp->n, Xs_dev, m, gp->d, ls, gp->amp, kss, yv, cov_out);
+                break;
+            case BOPY_KERNEL_MATERN32:
+                cov_probe_kernel<K_M32><<<grid, block, 0, st>>>(V, pl.na, gp->n_pad, (int)gp->n, Xs_dev, m, gp->d, ls, gp->amp, kss, yv, cov_out);
+                break;
+            default:
+                cov_probe_kernel<K_M52><<<grid, block, 0, st>>>(V, pl.na, gp->n_pad, (int)gp->n, Xs_dev, m, gp->d, ls, gp->amp, kss, yv, cov_out);
+                break;
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return BOPY_OK;
+    }
     const long long ntiles = (m + BN - 1) / BN;
-    void* Vall = nullptr;
-    CUDA_TRY(cudaMalloc(&Vall, (size_t)ntiles * gp->n_pad * BN * v_entry_bytes(gp)));
+    void* Vall = nullptr;   // stream-ordered: the pool keeps the block between calls (plotting grids call this in a loop)
+    CUDA_TRY(cudaMallocAsync(&Vall, (size_t)ntiles * gp->n_pad * BN * v_entry_bytes(gp), st));
     rc = run_sweep(gp, Xs_dev, m, BOPY_ACQ_NONE, 0.0, 0.0, mean_out, nullptr, nullptr, 0, nullptr, nullptr, Vall, 1, st);
     if (rc == BOPY_OK) {
         LsParam ls;
         for (int q = 0; q < MAX_D; ++q) ls.v[q] = q < gp->d ? gp->ls[q] : 1.0;
         rc = dispatch_engine(gp, [&](auto pol) { return launch_cov_k<decltype(pol)>(gp, Vall, Xs_dev, m, ls, cov_out, st); });
     }
+    cudaFreeAsync(Vall, st);
     cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(Vall);
     if (rc != BOPY_OK) return rc;
     if (e != cudaSuccess) return fail(BOPY_ERR_CUDA, "predict_cov failed: %s", cudaGetErrorString(e));
     return BOPY_OK;

@@ -293,3 +293,24 @@ def test_surrogate_predict_of_one_point_through_the_public_api():
         assert mean_i.shape == (1,) and cov_i.shape == (1, 1)
         np.testing.assert_allclose(mean_i[0], mean_all[i], rtol=1e-9, atol=1e-9)
         np.testing.assert_allclose(cov_i[0, 0], cov_all[i, i], rtol=1e-8, atol=1e-11)
+
+
+@pytest.mark.parametrize("name", ["c4_hartmann6_n2048", "c3_branin_n256", "ragged_n333_d4_opt", "matern25_d2"])
+def test_full_covariance_of_a_small_set_from_the_latency_path(name):
+    """bopy_gp_predict_cov (Surrogate.predict, bopy/surrogate.py:83-92) on a few hundred points: V comes from probe_kernel
+    (the solve spread over the block rows of L) and agrees with the V-exporting throughput sweep to rounding."""
+    g, st, gp = cached_native(name, "f64")
+    pv = prior_var(st)
+    for m in (2, 9, 33, min(300, len(g["Xs"]))):
+        xs = gp.candidates(g["Xs"][:m])
+        select_path(gp, "latency")
+        mean_l, cov_l = (t.cpu().numpy() for t in gp.predict_cov(xs))
+        select_path(gp, "sweep")
+        mean_s, cov_s = (t.cpu().numpy() for t in gp.predict_cov(xs))
+        np.testing.assert_allclose(cov_l, cov_s, rtol=1e-9, atol=1e-11 * pv)
+        err, bound = check_mean(mean_l, mean_s, st, "f64")
+        assert (err <= bound).all()
+        assert np.array_equal(cov_l, cov_l.T)
+        c = g["cov_corner"].shape[0]
+        if m >= c:
+            np.testing.assert_allclose(cov_l[:c, :c], g["cov_corner"], rtol=1e-9, atol=1e-11 * pv)

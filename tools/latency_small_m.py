@@ -78,6 +78,21 @@ def main():
             t_pred_ref = 1e3 * (time.perf_counter() - t0) / 20
         print(f"n={n:5d} d={d:2d}: Surrogate.predict(x) of ONE point (mean, 1 x 1 covariance): {t_pred:.3f} ms/call   "
               f"scikit-learn predict(return_cov=True): {t_pred_ref:.3f}", flush=True)
+        x100 = rng.random((100, d))
+        for _ in range(5):
+            sur.predict(x100)
+        t0 = time.perf_counter()
+        for _ in range(30):
+            sur.predict(x100)
+        t_pred = 1e3 * (time.perf_counter() - t0) / 30
+        with bench.all_host_threads():
+            host.predict(x100, return_cov=True)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                host.predict(x100, return_cov=True)
+            t_pred_ref = 1e3 * (time.perf_counter() - t0) / 10
+        print(f"n={n:5d} d={d:2d}: Surrogate.predict(x) of 100 points (mean, 100 x 100 covariance): {t_pred:.3f} ms/call   "
+              f"scikit-learn predict(return_cov=True): {t_pred_ref:.3f}", flush=True)
         for m in ms:
             xs = rng.random((m, d))
             xd = sur.native.candidates(xs)
