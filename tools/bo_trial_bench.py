@@ -56,6 +56,14 @@ def main():
         row["same_winner"] = bool(np.array_equal(r0.x_min, r1.x_min) and np.array_equal(r0.f_min, r1.f_min))
         row["multistart_gradient_ms"], r2 = wall(lambda: MultiStartOptimizer(ei, bounds, n_starts=256, n_candidates=ncand, seed=1).optimize(), 3)
         row["direct_maxf100_ms"], r3 = wall(lambda: DirectOptimizer(ei, bounds, maxf=100).optimize(), 2)
+        # DIRECT at a realistic budget (the reference's default is maxf = 20000): W = L^-1 is built at the first probe
+        row["direct_maxf2000_ms"], r4 = wall(lambda: DirectOptimizer(ei, bounds, maxf=2000).optimize(), 2)
+        sur.native.set_inverse_path(0)
+        sur.inverse_path = False
+        row["direct_maxf2000_chained_path_ms"], r5 = wall(lambda: DirectOptimizer(ei, bounds, maxf=2000).optimize(), 2)
+        sur.inverse_path = "auto"
+        sur.native.set_inverse_path(-1)
+        row["direct_same_optimum"] = bool(np.allclose(r4.x_min, r5.x_min, atol=1e-6))
         row["candidates"] = ncand
         row["f_min"] = dict(sweep=float(r0.f_min[0]), multistart=float(r2.f_min[0]), direct=float(r3.f_min[0]))
         print(json.dumps(row), flush=True)
