@@ -436,7 +436,7 @@ int launch_probe(bopy_gp* gp, const ProbePlan& pl, const double* Xs, long long m
 // W = L^-1 (lower triangular, row-major, leading dimension ld = nb * 128; diagonal blocks = Dinv).  Default: the recursive
 // 2 x 2 block inversion on tile_gemm_async_kernel (two launches per level, log2(nb) levels; the strict upper block triangle
 // of W is its scratch).  BOPY_B200_TRTRI=diagonal: one block diagonal at a time on tile_gemm_kernel (round-2's first
-// version, for A/B runs: 4.1 ms at n = 2048, 139 ms at n = 8192).
+// version, for A/B runs: 3.2 ms at n = 2048 and 48 ms at n = 8192 against 0.64 / 7.8 ms, profiles/r02/trtri_bench.log).
 bool trtri_by_diagonals() {
     const char* v = std::getenv("BOPY_B200_TRTRI");
     return v != nullptr && std::strcmp(v, "diagonal") == 0;
