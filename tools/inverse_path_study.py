@@ -27,3 +27,27 @@ for name in golden_names():
     bound = 1e-9 * np.abs(ref) + 1e-11 * prior
     print(f"{name:32s} n={n:5d} cond(L)={np.linalg.cond(st.L):9.2e}  substitution: worst err/bound "
           f"{np.nanmax(np.abs(var1 - ref) / bound):8.2e}   explicit inverse: {np.nanmax(np.abs(var2 - ref) / bound):8.2e}")
+
+# ill-conditioned fits on purpose (long length scales, jitter down to 1e-10: cond(K) up to 1e13), against a substitution in
+# extended precision (np.longdouble) as the reference: is there a conditioning at which the explicit inverse leaves the bound?
+print()
+rng = np.random.default_rng(0)
+for n, d, ls, alpha in [(300, 2, 0.3, 1e-6), (300, 2, 0.6, 1e-6), (300, 2, 0.3, 1e-8), (300, 2, 0.6, 1e-8), (300, 2, 0.3, 1e-10),
+                        (300, 2, 1.0, 1e-10), (600, 3, 0.5, 1e-8), (600, 3, 1.0, 1e-10), (1000, 6, 1.0, 1e-8), (1000, 6, 2.0, 1e-10)]:
+    X = rng.random((n, d))
+    y = np.sin(3 * X.sum(1))
+    spec = O.KernelSpec(kind="rbf", length_scale=np.full(d, ls), amplitude=1.0)
+    st = O.fit_state(X, y, spec, alpha, True)
+    Xs = rng.random((512, d))
+    Ks = O.kernel_cross(spec, Xs, X).T
+    W = sl.solve_triangular(st.L, np.eye(n), lower=True)
+    Lq, Kq = st.L.astype(np.longdouble), Ks.astype(np.longdouble)
+    v = np.zeros_like(Kq)
+    for i in range(n):
+        v[i] = (Kq[i] - Lq[i, :i] @ v[:i]) / Lq[i, i]
+    ref = (1.0 - (v * v).sum(0)).astype(np.float64)
+    v1, v2 = sl.solve_triangular(st.L, Ks, lower=True), W @ Ks
+    e1, e2 = np.abs(1 - (v1 * v1).sum(0) - ref), np.abs(1 - (v2 * v2).sum(0) - ref)
+    bound = 1e-9 * np.abs(ref) + 1e-11
+    print(f"synthetic n={n:4d} d={d} length scale {ls:3.1f} jitter {alpha:7.0e}: cond(L)={np.linalg.cond(st.L):8.2e}  "
+          f"substitution: worst err/bound {np.max(e1 / bound):8.2e}   explicit inverse: {np.max(e2 / bound):8.2e}")
