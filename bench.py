@@ -360,14 +360,19 @@ def run_config(ctx, key, dtype, m, steps, peaks, multistart=False):
             res["parity"] = {"ok": False, "error": repr(exc)}
     bases = [(b * ctx.world + ctx.rank) * m for b in range(2)]
     bufs = [_native.candidates_uniform(SEED_CAND, bases[b], m, lo, hi, device=ctx.dev) for b in range(2)]
-    sweep_step(ctx, native, bufs[0][: min(m, 1 << 15)], eta, bases[0])                      # warm-up
+    sweep_step(ctx, native, bufs[0][: min(m, 1 << 15)], eta, bases[0])                      # warm-up: kernels loaded
+    # ... and full-size warm-up steps where a step is milliseconds (C1, C3: three; C4 fp32: one; a C5 step is 17 s): a five-step
+    # region of 0.5 ms steps once caught a 12 ms one-off of the first sharded exchange
+    warm = 3 if key in ("C1", "C3") else (1 if key == "C4" else 0)
+    for w in range(warm):
+        sweep_step(ctx, native, bufs[w % 2], eta, bases[w % 2])
     ms, winner = ctx.timed(lambda i: sweep_step(ctx, native, bufs[i % 2], eta, bases[i % 2]), steps)
     kms, _ = ctx.timed(lambda i: native.sweep(bufs[i % 2], acq="ei", eta=eta, want_min=True, index_base=bases[i % 2]), steps)
     kernel_ms = kms / steps
     F = flops_per_candidate(n, d)
     peak = max(peaks["fp64_fma"], peaks["fp64_mma"]) if dtype == "f64" else peaks["tf32_tcgen05"] / 3.0
     achieved = F * m / (kernel_ms * 1e-3) / 1e12
-    res.update(value=ctx.world * m * steps / (ms * 1e-3), unit=UNIT, steps=steps, ms_per_step=ms / steps, kernel_ms=kernel_ms,
+    res.update(value=ctx.world * m * steps / (ms * 1e-3), unit=UNIT, steps=steps, warmup=warm, ms_per_step=ms / steps, kernel_ms=kernel_ms,
                argmin={"index": winner[1], "value": winner[0]},
                roofline={"bound": "tensor", "pipe": "FP64 DMMA" if dtype == "f64" else "tcgen05.mma kind::tf32, 3 MMAs per product",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -409,7 +414,8 @@ def run_strong(ctx, key, total, steps):
     native.set_latency_path(0)
     start, stop = shard_range(total, ctx.rank, ctx.world)
     xs = _native.candidates_uniform(SEED_CAND, start, stop - start, lo, hi, device=ctx.dev)
-    sweep_step(ctx, native, xs, eta, start)
+    for _ in range(3 if key == "C3" else 1):                 # warm-up (a C3 step is a millisecond, a C4 step two seconds)
+        sweep_step(ctx, native, xs, eta, start)
     ms, winner = ctx.timed(lambda i: sweep_step(ctx, native, xs, eta, start), steps)
     ms_nox, _ = ctx.timed(lambda i: sweep_step(ctx, native, xs, eta, start, exchange=False), steps)
     native.close()
@@ -474,7 +480,7 @@ def run_b200(args):
 
     side, strong = {}, {}
     if not args.headline_only:
-        plan = [("C1", "f64", 1 << 22, 5, False), ("C3", "f64", 1 << 20, 10, False), ("C4_f32", "f32", CAND_PER_GPU, 3, False),
+        plan = [("C1", "f64", 1 << 22, 50, False), ("C3", "f64", 1 << 20, 30, False), ("C4_f32", "f32", CAND_PER_GPU, 3, False),
                 ("C5", "f64", args.c5_candidates, 1, True)]
         for name, dtype, mm, steps, ms_flag in plan:
             try:
