@@ -319,3 +319,52 @@ def test_matern_inf_is_flattened_to_rbf_and_unsupported_kernels_say_so():
     assert flat.kernel == "rbf" and flat.amplitude == 2.0 and np.array_equal(flat.length_scale, [0.5, 0.25])
     with pytest.raises(UnsupportedKernelError, match="no CPU fallback"):
         flatten_sklearn_kernel(RationalQuadratic())
+
+
+def test_direct_optimizer_asks_for_the_inverse_path_only_with_a_large_budget():
+    """DirectOptimizer knows how often it will probe one fitted state (bopy/optimizer.py:95-107): from maxf = 64 on it switches
+    the surrogate's handle to W = L^-1 at the first probe and hands the mode back afterwards -- unless the user fixed the mode."""
+    from bopy_b200.optimizer import DirectOptimizer
+
+    class Handle:
+        n = 2048
+
+        def __init__(self):
+            self.calls = []
+
+        def set_inverse_path(self, mode):
+            self.calls.append(mode)
+            return 8
+
+    class Sur:
+        def __init__(self, mode):
+            self.native, self.inverse_path = Handle(), mode
+
+    class Acq:
+        def __init__(self, sur):
+            self.surrogate = sur
+
+        def __call__(self, x):
+            return np.array([float(((x - 0.3) ** 2).sum())])
+
+    b = Bounds([Bound(0.0, 1.0)])
+    for mode, maxf, want in (("auto", 200, [1, -1]), ("auto", 63, []), (False, 200, []), (True, 200, [])):
+        acq = Acq(Sur(mode))
+        DirectOptimizer(acq, b, maxf=maxf).optimize()
+        assert acq.surrogate.native.calls == want, (mode, maxf)
+
+    class Failing(Acq):
+        def __call__(self, x):
+            raise RuntimeError("objective failed")
+    acq = Failing(Sur("auto"))
+    with pytest.raises(RuntimeError):
+        DirectOptimizer(acq, b, maxf=200).optimize()
+    assert acq.surrogate.native.calls == [1, -1]        # the mode is handed back even when the run dies
+
+
+def test_surrogate_rejects_an_unknown_inverse_path_setting():
+    from bopy_b200.surrogate import B200GPSurrogate
+    with pytest.raises(ValueError, match="inverse_path must be"):
+        B200GPSurrogate(object(), inverse_path="sometimes")
+    for ok in ("auto", True, False):
+        assert B200GPSurrogate(object(), inverse_path=ok).inverse_path is ok or ok == "auto"
