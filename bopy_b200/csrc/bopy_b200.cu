@@ -470,15 +470,20 @@ constexpr size_t INV_SMEM_BUDGET = (size_t)200 << 10;
 
 // most candidates one inverse-path call can hold on this handle: K* of the call lives in shared memory ([nc][n_pad])
 long long inv_capacity(const bopy_gp* gp) {
-    if (!gp->probe_capable || gp->n_pad > INV_MAX_NPAD) return 0;
-    if (gp->small_n && gp->n_pad == BM && gp->n <= SMALL_N_MAX) return 0;   // served by small_n_kernel
+    // fp64 DMMA handles, and fp32 handles too: the path only needs the fp64 factor, inv(L_II), X / l and alpha_, which every
+    // handle keeps in fp64 -- an fp32-mode surrogate probed by DIRECT gets fp64 answers in 0.03 ms instead of a 0.57 ms sweep
+    const bool served = gp->probe_capable || (gp->dtype == BOPY_F32 && gp->n_blocks <= gp->sm_count);
+    if (!served || gp->n_pad > INV_MAX_NPAD) return 0;
+    if (gp->dtype == BOPY_F64 && gp->small_n && gp->n_pad == BM && gp->n <= SMALL_N_MAX) return 0;   // served by small_n_kernel
     for (int nc = INV_MAX_NC; nc >= 1; nc >>= 1)
         if (inv_smem_bytes(nc, gp->n_pad, gp->d) <= INV_SMEM_BUDGET) return nc;
     return 0;
 }
 
 bool inv_applies(const bopy_gp* gp, long long m, int slot_per_tile, const MinLoc* tile_records) {
-    return gp->inv_mode != 0 && m <= gp->inv_max_m && gp->Lfull_factor && probe_applies(gp, m, slot_per_tile, tile_records);
+    if (gp->inv_mode == 0 || m > gp->inv_max_m || !gp->Lfull_factor || slot_per_tile != 0 || tile_records != nullptr) return false;
+    // fp64 handles: a sub-path of the latency path (bopy_gp_set_latency_path(gp, 0) switches both off)
+    return gp->dtype == BOPY_F32 || probe_applies(gp, m, slot_per_tile, tile_records);
 }
 
 // every change of the fitted state: W no longer matches, the count of small calls starts again
@@ -937,9 +942,9 @@ int bopy_gp_create(bopy_gp** out, int device, int dtype, int kernel, int64_t n, 
         if (gp->group_size >= 2) max_m = std::min<long long>(max_m, 225LL * std::max(1, gp->sm_count / gp->n_blocks));
         if (const char* v = std::getenv("BOPY_B200_PROBE_MAX_M")) max_m = std::atoll(v);
         gp->probe_max_m = std::max(0LL, std::min<long long>(max_m, probe_capacity(gp)));
-        gp->inv_max_m = inv_capacity(gp);
-        gp->inv_mode = std::max(-1, std::min(1, env_int("BOPY_B200_INVERSE_PATH", -1)));
     }
+    gp->inv_max_m = inv_capacity(gp);
+    gp->inv_mode = std::max(-1, std::min(1, env_int("BOPY_B200_INVERSE_PATH", -1)));
     if (e != cudaSuccess) {
         bopy_gp_destroy(gp);
         return fail(BOPY_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
@@ -1518,7 +1523,10 @@ int bopy_gp_set_inverse_path(bopy_gp* gp, int mode, int64_t* max_m_out) {
     if (mode < -1 || mode > 1) return fail(BOPY_ERR_BAD_ARG, "mode must be -1 (auto), 0 (off) or 1 (on) (got %d)", mode);
     gp->inv_mode = mode;
     gp->inv_small_calls = 0;
-    if (max_m_out) *max_m_out = (mode != 0 && gp->Lfull_factor) ? std::min(gp->inv_max_m, gp->probe_max_m) : 0;
+    if (max_m_out)
+        *max_m_out = (mode != 0 && gp->Lfull_factor)
+                         ? (gp->dtype == BOPY_F32 ? gp->inv_max_m : std::min(gp->inv_max_m, gp->probe_max_m))
+                         : 0;
     return BOPY_OK;
 }
 

@@ -81,7 +81,7 @@ class B200GPSurrogate(Surrogate):
         'auto' (the library default) builds W at the 16th such call on one fitted state (the build costs what 6 chained
         calls cost at n = 2048, 24 at n = 8192), True at the first, False never.
         The paths agree to rounding, not bit for bit: with False a candidate's value never depends on how many
-        calls came before it.
+        calls came before it.  dtype='f32' surrogates are served too, in fp64 (the handle keeps the fp64 factor).
     """
 
     def __init__(self, gp, dtype: str = "f64", device=None, device_fit="auto", latency_max_m=None, inverse_path="auto"):

@@ -177,7 +177,8 @@ int bopy_gp_set_latency_path(bopy_gp* gp, int64_t max_m, int64_t* effective_out)
  * latency path above leaves a chain of n/128 dependent hops per call; a state that is probed thousands of times can pay
  * for W = L^-1 once (recursive blocked inversion on the fp64 tile kernel of bopy_gp_lml: 0.64 ms at n = 2048, 7.9 ms at 8192) and then serve every call of up to 8 candidates
  * (fewer when n_pad x 8 candidates of K* do not fit in shared memory: 2 at n = 8192) as one matrix-vector product,
- * v = W k*, spread over all SMs.  fp64 handles with n_pad <= 8192 whose latency path is on; fp64 arithmetic, K* /
+ * v = W k*, spread over all SMs.  fp64 handles with n_pad <= 8192 whose latency path is on, and fp32 handles (which keep the
+ * fp64 factor, inv(L_II), X / l and alpha_: their small calls are then answered in fp64); fp64 arithmetic, K* /
  * de-normalisation / acquisition shared with the other paths, results agree with them to rounding (parity bound 1e-9).
  * mode -1 (default): W is built at the 16th call of at most that many candidates on one state (the build costs what 6 chained
  * calls cost at n = 2048 and 24 at n = 8192); 1: at the first; 0: never.  Every change of the state (set_state, fit, append, truncate, resize) drops W.  The row-major factor W is

@@ -128,8 +128,28 @@ def test_off_when_the_latency_path_is_off_and_on_fp32_handles():
     gp.set_inverse_path(1)
     out = gp.sweep(gp.candidates(g["Xs"][:4]), acq="ei", eta=eta, **WANT)
     assert np.array_equal(out["var"].cpu().numpy(), swp["var"])
-    g32, st32, gp32 = cached_native("c3_branin_n256", "f32")
-    assert gp32.set_inverse_path(1) == 0
+
+
+def test_fp32_handles_are_served_in_fp64():
+    """An fp32-mode handle keeps the fp64 factor, inv(L_II), X / l and alpha_ -- all the inverse path needs: DIRECT probes of an
+    fp32 surrogate get fp64 answers (the fp64 parity bounds hold) instead of a sweep_tc_kernel launch per probe."""
+    for name in ("c4_hartmann6_n2048", "c3_branin_n256"):
+        g, st, gp = cached_native(name, "f32")
+        assert gp.set_latency_path(4096) == 0                    # still no chained latency path on fp32 handles
+        assert gp.set_inverse_path(1) == 8
+        eta = float(g["eta"])
+        for m in (1, 8):
+            out = gp.sweep(gp.candidates(g["Xs"][:m]), acq="ei", eta=eta, index_base=5, **WANT)
+            mean, var = out["mean"].cpu().numpy(), out["var"].cpu().numpy()
+            err, bound = check_mean(mean, g["mean"][:m], st, "f64")
+            assert (err <= bound).all()
+            err, bound = check_var(var, g["var"][:m], st, "f64")
+            assert (err <= bound).all()
+            assert int(out["min_idx"][0]) - 5 == int(np.argmin(out["acq"].cpu().numpy()))
+        big = gp.sweep(gp.candidates(g["Xs"][:64]), want_var=True)["var"].cpu().numpy()      # larger calls: the fp32-mode sweep
+        err, bound = check_var(big, g["var"][:64], st, "f32", name)
+        assert (err <= bound).all()
+        gp.set_inverse_path(0)
 
 
 def test_device_fit_then_growth_by_one_point():
