@@ -272,7 +272,7 @@ class B200GPSurrogate(Surrogate):
 
     # -- the reference contract --------------------------------------------------------------------
     def _predict(self, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-        if isinstance(x, np.ndarray) and x.shape[0] == 1 and self.native.HOST_CALL_MAX_M >= 1:
+        if isinstance(x, np.ndarray) and x.shape[0] == 1:
             # ONE point (a DIRECT objective built on predict, the Kriging believer's bopy/acquisition.py:189): the 1 x 1
             # covariance is the posterior variance -- one host-buffer call on the latency / inverse path
             _, mean, var = self.native.eval_host(np.ascontiguousarray(x, dtype=np.float64), want_acq=False, want_mean=True,
